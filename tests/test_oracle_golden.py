@@ -1,0 +1,102 @@
+"""CPU: pin the numpy oracle against golden vectors produced by the reference itself
+(tests/golden/make_golden.py ran the unmodified reference modules)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_cfg, real_superpoint_weights, kp_set, match_pairs
+from image_matching_b200 import synth
+from oracle import matching_oracle as O
+
+
+def _sp_stage_checks(g, sd, H, W, seed, side):
+    img = synth.make_pair(seed, H, W)[int(side)]
+    semi, desc = O.superpoint_dense(img, sd)
+    assert np.abs(semi - g["semi_" + side]).max() < 2e-4
+    assert np.abs(desc - g["desc_" + side]).max() < 2e-5
+    # given the reference's semi, the post-processing is (nearly) bit exact
+    heat = O.heatmap(g["semi_" + side])
+    assert np.abs(heat - g["heat_" + side]).max() < 1e-6   # softmax: <= ~1 ulp vs torch
+    nms = O.simple_nms(g["heat_" + side], 4)
+    assert np.array_equal(nms, g["nms_" + side])          # compares only -> bit exact
+
+
+@pytest.mark.parametrize("name,D,seed,hw,kw", [
+    ("small_stages", 128, 1, (120, 160), dict(max_kp=256)),
+    ("d256_small", 256, 3, (120, 160), dict(D=256, kenc=(32, 64, 128, 256), max_kp=200, iters=50)),
+    ("real_small_stages", 128, 4, (160, 224), dict(max_kp=300)),
+])
+def test_stages(name, D, seed, hw, kw):
+    g = load_golden(name)
+    cfg = golden_cfg(**kw)
+    if name.startswith("real"):
+        sp = real_superpoint_weights()
+    else:
+        sp = synth.superpoint_weights(1 if D == 256 else 0, D)
+    sg = synth.superglue_weights(1 if D == 256 else 0, D, cfg["superglue"]["keypoint_encoder"])
+    H, W = hw
+    for side in "01":
+        _sp_stage_checks(g, sp, H, W, seed, side)
+    # keypoint extraction + descriptor sampling given the reference's nms / desc maps
+    for side in "01":
+        kp, sc = O.extract_keypoints(g["nms_" + side], 0.005, 4, cfg["superpoint"]["max_keypoints"])
+        assert np.array_equal(kp, g[f"keypoints{side}_0"])
+        assert np.array_equal(sc, g[f"scores{side}_0"])
+        de = O.sample_descriptors(kp, g["desc_" + side], align_corners=False)
+        assert np.abs(de - g[f"descriptors{side}_0"]).max() < 2e-6
+    # SuperGlue given the reference's SuperPoint outputs
+    r = O.superglue_forward(g["keypoints0_0"], g["scores0_0"], g["descriptors0_0"],
+                            g["keypoints1_0"], g["scores1_0"], g["descriptors1_0"],
+                            H, W, sg, cfg["superglue"], want=("kenc", "gnn", "S", "Z"))
+    assert np.abs(r["kenc0"] - g["kenc0"]).max() < 1e-5
+    assert np.abs(r["gnn0"] - g["gnn0"]).max() < 2e-4
+    assert np.abs(r["gnn1"] - g["gnn1"]).max() < 2e-4
+    assert np.abs(r["S"] - g["S"]).max() < 1e-3
+    assert np.abs(r["Z"] - g["Z"]).max() < 1e-3
+    # optimal transport + match selection given the reference's S: exact indices
+    Z = O.log_optimal_transport(g["S"], sg["bin_score"], cfg["superglue"]["sinkhorn_iterations"])
+    assert np.allclose(Z, g["Z"], rtol=0, atol=1e-4)   # summation-order ulps at |Z| ~ 1e2
+    m0, m1, s0, s1 = O.match_select(g["Z"], cfg["superglue"]["match_threshold"])
+    assert np.array_equal(m0, g["matches0"][0]) and np.array_equal(m1, g["matches1"][0])
+    assert np.abs(s0 - g["matching_scores0"][0]).max() < 1e-6
+    assert np.abs(s1 - g["matching_scores1"][0]).max() < 1e-6
+    # single layer deltas
+    d0 = O.attentional_propagation(g["kenc0"], g["kenc0"], sg, "gnn.layers.0")
+    assert np.abs(d0 - g["layer0_delta0"]).max() < 2e-5
+    d1 = O.attentional_propagation(g["kenc0"], g["kenc1"], sg, "gnn.layers.1")
+    assert np.abs(d1 - g["layer1_delta0"]).max() < 2e-5
+
+
+def _end_to_end(name, seeds, H, W, sp, cfg, min_common=0.98):
+    g = load_golden(name)
+    sg = synth.superglue_weights(0, 128)
+    for i, seed in enumerate(seeds):
+        a, b = synth.make_pair(seed, H, W)
+        r = O.matching_forward(a, b, sp, sg, cfg)
+        for side in "01":
+            ref = kp_set(g[f"keypoints{side}_{i}"])
+            got = kp_set(r["keypoints" + side])
+            assert len(ref & got) >= min_common * len(ref), (len(ref & got), len(ref))
+        ref_pairs = match_pairs(g[f"keypoints0_{i}"], g[f"keypoints1_{i}"], g["matches0"][i])
+        got_pairs = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
+        assert len(ref_pairs & got_pairs) >= 0.9 * len(ref_pairs), (len(ref_pairs & got_pairs), len(ref_pairs))
+
+
+def test_end_to_end_ragged():
+    # H, W not multiples of 8; max_keypoints=-1 -> row-major order branch
+    _end_to_end("ragged_hw", [2], 123, 165, synth.superpoint_weights(0, 128),
+                golden_cfg(max_kp=-1, iters=20))
+
+
+def test_end_to_end_c1_real():
+    _end_to_end("c1_real", [1], 480, 640, real_superpoint_weights(), golden_cfg(max_kp=1024))
+
+
+def test_empty_keypoints_branch():
+    # superglue_test.py:235-242: int32 -1 matches, zero scores
+    sg = synth.superglue_weights(0, 128)
+    kp1, sc1, de1 = synth.random_features(0, 1, 7, 128, 120, 160)
+    r = O.superglue_forward(np.zeros((0, 2), np.float32), np.zeros(0, np.float32), np.zeros((128, 0), np.float32),
+                            kp1[0], sc1[0], de1[0], 120, 160, sg, golden_cfg()["superglue"])
+    assert r["matches0"].shape == (0,) and r["matches0"].dtype == np.int32
+    assert r["matches1"].shape == (7,) and (r["matches1"] == -1).all()
+    assert (r["matching_scores1"] == 0).all()
