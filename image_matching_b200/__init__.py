@@ -1,0 +1,9 @@
+"""image_matching_b200 -- B200-native (sm_100a) SuperPoint + SuperGlue inference path.
+
+Drop-in for the reference's ``superglue.models.matching_test.Matching`` (and the two model
+classes it owns).  See DESIGN.md / INTEGRATION.md at the repo root.
+"""
+from .matching import Matching, SuperPoint, SuperGlue  # noqa: F401
+from . import synth, lib  # noqa: F401
+
+__all__ = ["Matching", "SuperPoint", "SuperGlue", "synth", "lib"]

@@ -1,0 +1,896 @@
+// C ABI of libb200match.so: handle, weight packing and the orchestration of the kernel pipeline.
+// See include/b200m.h for the reference file:line each entry point replaces.
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <cstdarg>
+
+#include "../../include/b200m.h"
+#include "kernels.cuh"
+
+using namespace b200m;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+struct ConvLayer {      // packed conv on C4-planar activations
+  int cin = 0, cout = 0, cout_pad = 0, ks = 3;
+  size_t w_off = 0, b_off = 0;   // float offsets into the device weight arena
+};
+struct Linear {         // packed [N][K] row-major weight + bias
+  int N = 0, K = 0;
+  size_t w_off = 0, b_off = 0;
+};
+
+constexpr int kHeads = 4;
+constexpr int kSpMicroBatch = 16;   // images per SuperPoint micro-batch (bounds the fp32 activation arena)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {          // bump allocator over the caller's workspace
+  char* base; size_t size; size_t off = 0; bool ok = true;
+  Arena(void* p, size_t n) : base((char*)p), size(n) {}
+  template <typename T> T* take(size_t count) {
+    off = align_up(off, 256);
+    size_t bytes = count * sizeof(T);
+    if (!base || off + bytes > size) { ok = false; off += bytes; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+struct b200m_handle {
+  b200m_config cfg;
+  int device = 0;
+  std::map<std::string, HostTensor> tensors;
+  bool packed_sp = false, packed_sg = false;   // which half b200m_pack found weights for
+  float* d_w = nullptr;          // device weight arena
+  // SuperPoint
+  size_t conv1_w = 0, conv1_b = 0;
+  ConvLayer c1b, c2a, c2b, c3a, c3b, c4a, c4b, heads, pb, db;
+  // SuperGlue
+  std::vector<Linear> kenc;
+  struct Gnn { Linear qkv, merge, mlp1, mlp2; };
+  std::vector<Gnn> gnn;
+  Linear final_proj;
+  float bin_score = 1.f;
+  long long launches = 0;
+  const char* err_where = nullptr;
+  Profiler prof;
+  std::vector<ProfRecord> prof_recs;
+};
+
+namespace {
+
+LaunchCtx make_ctx(b200m_handle* h, void* stream) {
+  LaunchCtx c;
+  c.stream = (cudaStream_t)stream;
+  c.counter = &h->launches;
+  c.err_where = &h->err_where;
+  c.err = cudaSuccess;
+  c.prof = &h->prof;
+  return c;
+}
+
+int finish(b200m_handle* h, LaunchCtx& ctx) {
+  if (ctx.err != cudaSuccess)
+    return fail(B200M_ERR_CUDA, "CUDA launch failed in %s: %s", h->err_where ? h->err_where : "?",
+                cudaGetErrorString(ctx.err));
+  return B200M_OK;
+}
+
+// ------------------------------------------------------------------ packing helpers
+struct Packer {
+  b200m_handle* h;
+  std::vector<float> host;
+  std::string err;
+  const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end()) { if (err.empty()) err = "missing tensor " + name; return nullptr; }
+    const HostTensor& t = it->second;
+    std::vector<int64_t> want(shape);
+    // accept trailing singleton dims (Conv1d weights are [out,in,1])
+    std::vector<int64_t> got = t.shape;
+    while (got.size() > want.size() && got.back() == 1) got.pop_back();
+    if (got != want) { if (err.empty()) err = "bad shape for " + name; return nullptr; }
+    return &t;
+  }
+  size_t alloc(size_t n) {
+    size_t off = align_up(host.size(), 64);
+    host.resize(off + n, 0.f);
+    return off;
+  }
+  // conv/linear weight [out][in*k*k] and bias folded with an optional BatchNorm (eval, eps 1e-5)
+  bool folded(const std::string& conv, const std::string& bn, int out, int in_kk, std::vector<double>& w,
+              std::vector<double>& b, std::initializer_list<int64_t> wshape) {
+    const HostTensor* W = get(conv + ".weight", wshape);
+    const HostTensor* Bv = get(conv + ".bias", {out});
+    if (!W || !Bv) return false;
+    w.assign(W->data.begin(), W->data.end());
+    b.assign(Bv->data.begin(), Bv->data.end());
+    if (!bn.empty()) {
+      const HostTensor* g = get(bn + ".weight", {out});
+      const HostTensor* be = get(bn + ".bias", {out});
+      const HostTensor* mu = get(bn + ".running_mean", {out});
+      const HostTensor* var = get(bn + ".running_var", {out});
+      if (!g || !be || !mu || !var) return false;
+      for (int o = 0; o < out; ++o) {
+        double s = (double)g->data[o] / std::sqrt((double)var->data[o] + 1e-5);
+        for (int k = 0; k < in_kk; ++k) w[(size_t)o * in_kk + k] *= s;
+        b[o] = (b[o] - (double)mu->data[o]) * s + (double)be->data[o];
+      }
+    }
+    return true;
+  }
+  // append a conv layer from already-folded [cout][cin][ks][ks] weights
+  ConvLayer pack_conv(const std::vector<double>& w, const std::vector<double>& b, int cout, int cin, int ks) {
+    ConvLayer L;
+    L.cin = cin; L.cout = cout; L.ks = ks; L.cout_pad = round_up(cout, 64);
+    const int taps = ks * ks, nchunks = cin / 8, ncb = L.cout_pad / 64;
+    L.w_off = alloc((size_t)ncb * nchunks * taps * 8 * 64);
+    L.b_off = alloc(L.cout_pad);
+    for (int cb = 0; cb < ncb; ++cb)
+      for (int cc = 0; cc < nchunks; ++cc)
+        for (int t = 0; t < taps; ++t)
+          for (int ci = 0; ci < 8; ++ci)
+            for (int co = 0; co < 64; ++co) {
+              int o = cb * 64 + co, i = cc * 8 + ci;
+              float v = o < cout ? (float)w[((size_t)o * cin + i) * taps + t] : 0.f;
+              host[L.w_off + ((((size_t)cb * nchunks + cc) * taps + t) * 8 + ci) * 64 + co] = v;
+            }
+    for (int o = 0; o < cout; ++o) host[L.b_off + o] = (float)b[o];
+    return L;
+  }
+  Linear pack_linear(const std::vector<double>& w, const std::vector<double>& b, int N, int K, int Kpad,
+                     const int* row_perm = nullptr, const int* col_perm = nullptr) {
+    Linear L;
+    L.N = N; L.K = Kpad;
+    L.w_off = alloc((size_t)N * Kpad);
+    L.b_off = alloc(N);
+    for (int r = 0; r < N; ++r) {
+      int sr = row_perm ? row_perm[r] : r;
+      for (int c = 0; c < K; ++c) {
+        int scol = col_perm ? col_perm[c] : c;
+        host[L.w_off + (size_t)r * Kpad + c] = (float)w[(size_t)sr * K + scol];
+      }
+      host[L.b_off + r] = (float)b[sr];
+    }
+    return L;
+  }
+};
+
+bool has_prefix(const b200m_handle* h, const std::string& prefix) {
+  auto it = h->tensors.lower_bound(prefix);
+  return it != h->tensors.end() && it->first.compare(0, prefix.size(), prefix) == 0;
+}
+
+int pack_superpoint(b200m_handle* h, Packer& P) {
+  const int D = h->cfg.descriptor_dim;
+  std::vector<double> w, b;
+  const std::string sp = "superpoint.";
+  // ---- SuperPoint (unet_parts.py:10-48; superpoint_test.py:70-84)
+  if (!P.folded(sp + "inc.conv.conv.0", sp + "inc.conv.conv.1", 64, 9, w, b, {64, 1, 3, 3}))
+    return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+  h->conv1_w = P.alloc(9 * 64);
+  h->conv1_b = P.alloc(64);
+  for (int t = 0; t < 9; ++t)
+    for (int o = 0; o < 64; ++o) P.host[h->conv1_w + t * 64 + o] = (float)w[(size_t)o * 9 + t];
+  for (int o = 0; o < 64; ++o) P.host[h->conv1_b + o] = (float)b[o];
+  auto conv3 = [&](const std::string& conv, const std::string& bn, int cin, int cout, ConvLayer& L) -> bool {
+    if (!P.folded(sp + conv, sp + bn, cout, cin * 9, w, b, {cout, cin, 3, 3})) return false;
+    L = P.pack_conv(w, b, cout, cin, 3);
+    return true;
+  };
+  bool ok = conv3("inc.conv.conv.3", "inc.conv.conv.4", 64, 64, h->c1b) &&
+            conv3("down1.mpconv.1.conv.0", "down1.mpconv.1.conv.1", 64, 64, h->c2a) &&
+            conv3("down1.mpconv.1.conv.3", "down1.mpconv.1.conv.4", 64, 64, h->c2b) &&
+            conv3("down2.mpconv.1.conv.0", "down2.mpconv.1.conv.1", 64, 128, h->c3a) &&
+            conv3("down2.mpconv.1.conv.3", "down2.mpconv.1.conv.4", 128, 128, h->c3b) &&
+            conv3("down3.mpconv.1.conv.0", "down3.mpconv.1.conv.1", 128, 128, h->c4a) &&
+            conv3("down3.mpconv.1.conv.3", "down3.mpconv.1.conv.4", 128, 128, h->c4b);
+  if (!ok) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+  {  // detector + descriptor 3x3 heads share their input x4 -> one conv with 512 output channels
+    std::vector<double> wa, ba, wd, bd;
+    if (!P.folded(sp + "convPa", sp + "bnPa", 256, 128 * 9, wa, ba, {256, 128, 3, 3}) ||
+        !P.folded(sp + "convDa", sp + "bnDa", 256, 128 * 9, wd, bd, {256, 128, 3, 3}))
+      return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    wa.insert(wa.end(), wd.begin(), wd.end());
+    ba.insert(ba.end(), bd.begin(), bd.end());
+    h->heads = P.pack_conv(wa, ba, 512, 128, 3);
+  }
+  if (!P.folded(sp + "convPb", sp + "bnPb", 65, 256, w, b, {65, 256, 1, 1}))
+    return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+  h->pb = P.pack_conv(w, b, 65, 256, 1);
+  if (!P.folded(sp + "convDb", sp + "bnDb", D, 256, w, b, {D, 256, 1, 1}))
+    return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+  h->db = P.pack_conv(w, b, D, 256, 1);
+  return B200M_OK;
+}
+
+int pack_superglue(b200m_handle* h, Packer& P) {
+  const int D = h->cfg.descriptor_dim;
+  std::vector<double> w, b;
+  // ---- SuperGlue (superglue_test.py:204-219)
+  const std::string sg = "superglue.";
+  {
+    const HostTensor* bs = P.get(sg + "bin_score", {});
+    if (!bs) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    h->bin_score = bs->data[0];
+  }
+  h->kenc.clear();
+  {
+    std::vector<int> ch = {3};
+    for (int i = 0; i < h->cfg.n_kenc; ++i) ch.push_back(h->cfg.kenc[i]);
+    ch.push_back(D);
+    int idx = 0;
+    for (size_t i = 1; i < ch.size(); ++i) {
+      bool last = (i + 1 == ch.size());
+      std::string conv = sg + "kenc.encoder." + std::to_string(idx);
+      std::string bn = last ? std::string() : sg + "kenc.encoder." + std::to_string(idx + 1);
+      if (!P.folded(conv, bn, ch[i], ch[i - 1], w, b, {ch[i], ch[i - 1]}))
+        return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+      h->kenc.push_back(P.pack_linear(w, b, ch[i], ch[i - 1], round_up(ch[i - 1], 4)));
+      idx += last ? 1 : 3;
+    }
+  }
+  const int d = D / kHeads;
+  std::vector<int> perm(D);   // head-major position -> reference channel (c = dd*heads + h)
+  for (int hh = 0; hh < kHeads; ++hh)
+    for (int dd = 0; dd < d; ++dd) perm[hh * d + dd] = dd * kHeads + hh;
+  h->gnn.clear();
+  for (int l = 0; l < h->cfg.n_gnn_layers; ++l) {
+    std::string p = sg + "gnn.layers." + std::to_string(l);
+    b200m_handle::Gnn G;
+    std::vector<double> wq, bq, wk, bk, wv, bv;
+    if (!P.folded(p + ".attn.proj.0", "", D, D, wq, bq, {D, D}) ||
+        !P.folded(p + ".attn.proj.1", "", D, D, wk, bk, {D, D}) ||
+        !P.folded(p + ".attn.proj.2", "", D, D, wv, bv, {D, D}))
+      return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    {  // fused q|k|v projection with de-interleaved heads
+      std::vector<double> wcat, bcat;
+      for (auto* src : {&wq, &wk, &wv})
+        for (int r = 0; r < D; ++r)
+          wcat.insert(wcat.end(), src->begin() + (size_t)perm[r] * D, src->begin() + (size_t)(perm[r] + 1) * D);
+      for (auto* src : {&bq, &bk, &bv})
+        for (int r = 0; r < D; ++r) bcat.push_back((*src)[perm[r]]);
+      G.qkv = P.pack_linear(wcat, bcat, 3 * D, D, D);
+    }
+    if (!P.folded(p + ".attn.merge", "", D, D, w, b, {D, D})) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    G.merge = P.pack_linear(w, b, D, D, D, nullptr, perm.data());
+    if (!P.folded(p + ".mlp.0", p + ".mlp.1", 2 * D, 2 * D, w, b, {2 * D, 2 * D}))
+      return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    G.mlp1 = P.pack_linear(w, b, 2 * D, 2 * D, 2 * D);
+    if (!P.folded(p + ".mlp.3", "", D, 2 * D, w, b, {D, 2 * D})) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+    G.mlp2 = P.pack_linear(w, b, D, 2 * D, 2 * D);
+    h->gnn.push_back(G);
+  }
+  if (!P.folded(sg + "final_proj", "", D, D, w, b, {D, D})) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
+  h->final_proj = P.pack_linear(w, b, D, D, D);
+  return B200M_OK;
+}
+
+// A handle may carry only one half (SuperPoint used alone by superpoint_flann_test.py:52-61 /
+// datasets/GlueSparse.py:18-39, or SuperGlue fed with external features): pack what is present.
+int do_pack(b200m_handle* h, cudaStream_t stream) {
+  Packer P{h, {}, {}};
+  h->packed_sp = h->packed_sg = false;
+  const bool want_sp = has_prefix(h, "superpoint."), want_sg = has_prefix(h, "superglue.");
+  if (!want_sp && !want_sg) return fail(B200M_ERR_WEIGHTS, "no tensors were set before b200m_pack");
+  if (want_sp) { int rc = pack_superpoint(h, P); if (rc) return rc; }
+  if (want_sg) { int rc = pack_superglue(h, P); if (rc) return rc; }
+
+  if (h->d_w) { cudaFree(h->d_w); h->d_w = nullptr; }
+  if (cudaMalloc(&h->d_w, P.host.size() * sizeof(float)) != cudaSuccess)
+    return fail(B200M_ERR_CUDA, "cudaMalloc of %zu weight bytes failed", P.host.size() * sizeof(float));
+  cudaError_t e = cudaMemcpyAsync(h->d_w, P.host.data(), P.host.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return fail(B200M_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(e));
+  h->packed_sp = want_sp;
+  h->packed_sg = want_sg;
+  return B200M_OK;
+}
+
+// ------------------------------------------------------------------ SuperPoint pipeline
+struct SpDims {
+  int H, W, H2, W2, H3, W3, hc, wc, H8, W8, cand_cap, dpad;
+};
+SpDims sp_dims(const b200m_handle* h, int H, int W) {
+  SpDims d;
+  d.H = H; d.W = W; d.H2 = H / 2; d.W2 = W / 2; d.H3 = d.H2 / 2; d.W3 = d.W2 / 2;
+  d.hc = d.H3 / 2; d.wc = d.W3 / 2; d.H8 = d.hc * 8; d.W8 = d.wc * 8;
+  int r = h->cfg.nms_radius + 1;
+  d.cand_cap = next_pow2(std::max(1024, cdiv(d.H8, r) * cdiv(d.W8, r)));
+  d.dpad = round_up(h->cfg.descriptor_dim, 64);
+  return d;
+}
+
+struct SpWs {
+  float *p0, *p1, *semi, *draw, *dn, *heat;
+  unsigned long long* keys;
+  int *cand_counts, *overflow;
+  size_t p0_img, p1_img, semi_img, draw_img, dn_img, heat_img;
+};
+bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w) {
+  const int D = h->cfg.descriptor_dim;
+  w.p0_img = (size_t)64 * d.H * d.W;
+  w.p1_img = std::max((size_t)64 * d.H2 * d.W2, (size_t)128 * d.H3 * d.W3);
+  w.semi_img = (size_t)128 * d.hc * d.wc;
+  w.draw_img = (size_t)d.dpad * d.hc * d.wc;
+  w.dn_img = (size_t)D * d.hc * d.wc;
+  w.heat_img = (size_t)d.H8 * d.W8;
+  w.p0 = A.take<float>(w.p0_img * mb);
+  w.p1 = A.take<float>(w.p1_img * mb);
+  w.semi = A.take<float>(w.semi_img * mb);
+  w.draw = A.take<float>(w.draw_img * mb);
+  w.dn = A.take<float>(w.dn_img * mb);
+  w.heat = A.take<float>(w.heat_img * mb);
+  w.keys = A.take<unsigned long long>((size_t)d.cand_cap * mb);
+  w.cand_counts = A.take<int>(mb + 1);
+  w.overflow = w.cand_counts ? w.cand_counts + mb : nullptr;
+  return A.ok;
+}
+
+void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in, int in_c4_total, int in_c4_off,
+              float* out, int out_c4_total, int n, int H, int W, bool relu, bool pool) {
+  ConvParams p;
+  p.in = in; p.in_c4_total = in_c4_total; p.in_c4_off = in_c4_off; p.cin = L.cin;
+  p.wpk = h->d_w + L.w_off; p.bias = h->d_w + L.b_off;
+  p.out = out; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.cout_pad = L.cout_pad;
+  p.n = n; p.H = H; p.W = W; p.relu = relu ? 1 : 0;
+  launch_conv(ctx, p, L.ks, pool);
+}
+
+// encoder + heads for `n` images (n <= micro-batch): fills w.semi (C4, 32 groups) and w.draw (C4, dpad/4 groups)
+void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, const float* images, int n) {
+  launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, n, d.H, d.W);
+  // the C4 buffers are addressed per image with each layer's own channel-group count, so ping-pong
+  // buffers are simply re-interpreted per layer
+  run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
+  run_conv(h, ctx, h->c2a, w.p1, 16, 0, w.p0, 16, n, d.H2, d.W2, true, false);
+  run_conv(h, ctx, h->c2b, w.p0, 16, 0, w.p1, 16, n, d.H2, d.W2, true, true);     // -> 64 x H3 x W3
+  run_conv(h, ctx, h->c3a, w.p1, 16, 0, w.p0, 32, n, d.H3, d.W3, true, false);    // 128 ch
+  run_conv(h, ctx, h->c3b, w.p0, 32, 0, w.p1, 32, n, d.H3, d.W3, true, true);     // -> 128 x hc x wc
+  run_conv(h, ctx, h->c4a, w.p1, 32, 0, w.p0, 32, n, d.hc, d.wc, true, false);
+  run_conv(h, ctx, h->c4b, w.p0, 32, 0, w.p1, 32, n, d.hc, d.wc, true, false);    // x4
+  run_conv(h, ctx, h->heads, w.p1, 32, 0, w.p0, 128, n, d.hc, d.wc, true, false); // cPa | cDa (512 ch)
+  run_conv(h, ctx, h->pb, w.p0, 128, 0, w.semi, 32, n, d.hc, d.wc, false, false); // semi (65 of 128 ch)
+  run_conv(h, ctx, h->db, w.p0, 128, 64, w.draw, d.dpad / 4, n, d.hc, d.wc, false, false);
+}
+
+int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_images, int H, int W,
+                    float* keypoints, float* scores, float* descriptors, int* counts, int cap,
+                    float* semi_out, float* desc_out, float* tok_out, int tok_ld, size_t tok_img_stride,
+                    void* ws, size_t ws_bytes) {
+  if (!h->packed_sp) return fail(B200M_ERR_WEIGHTS, "SuperPoint weights are not packed (b200m_set_tensor + b200m_pack)");
+  if (n_images <= 0) return B200M_OK;
+  if (H < 8 || W < 8) return fail(B200M_ERR_INVALID, "image smaller than 8x8");
+  const int D = h->cfg.descriptor_dim;
+  SpDims d = sp_dims(h, H, W);
+  const int mb = std::min(n_images, kSpMicroBatch);
+  Arena A(ws, ws_bytes);
+  SpWs w;
+  if (!sp_carve(h, d, mb, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperPoint workspace too small: need %zu bytes", A.off);
+  LaunchCtx ctx = make_ctx(h, stream);
+  for (int i0 = 0; i0 < n_images; i0 += mb) {
+    const int n = std::min(mb, n_images - i0);
+    sp_dense(h, ctx, d, w, images + (size_t)i0 * H * W, n);
+    if (semi_out)
+      launch_c4_to_nchw(ctx, w.semi, 32, 0, 65, semi_out + (size_t)i0 * 65 * d.hc * d.wc, n, d.hc, d.wc, false);
+    if (desc_out)
+      launch_c4_to_nchw(ctx, w.draw, d.dpad / 4, 0, D, desc_out + (size_t)i0 * D * d.hc * d.wc, n, d.hc, d.wc, true);
+    if (keypoints) {
+      launch_softmax_heat(ctx, w.semi, 32, w.heat, n, d.hc, d.wc);
+      cudaMemsetAsync(w.cand_counts, 0, sizeof(int) * (mb + 1), ctx.stream);
+      launch_nms_candidates(ctx, w.heat, nullptr, n, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
+                            h->cfg.remove_borders, w.keys, w.cand_counts, d.cand_cap, w.overflow);
+      launch_select_keypoints(ctx, w.keys, w.cand_counts, d.cand_cap, n, d.W8, h->cfg.max_keypoints,
+                              keypoints + (size_t)i0 * cap * 2, scores + (size_t)i0 * cap, counts + i0, cap);
+      launch_c4_l2_normalize(ctx, w.draw, d.dpad / 4, 0, w.dn, D / 4, D, n, d.hc, d.wc);
+      launch_sample_descriptors(ctx, w.dn, D / 4, D, n, d.hc, d.wc, keypoints + (size_t)i0 * cap * 2, counts + i0,
+                                cap, h->cfg.align_corners, descriptors ? descriptors + (size_t)i0 * D * cap : nullptr,
+                                tok_out ? tok_out + (size_t)i0 * tok_img_stride : nullptr, tok_ld, tok_img_stride);
+    }
+  }
+  return finish(h, ctx);
+}
+
+size_t sp_ws_bytes(const b200m_handle* h, int n_images, int H, int W) {
+  SpDims d = sp_dims(h, H, W);
+  Arena A(nullptr, 0);
+  SpWs w;
+  sp_carve(h, d, std::max(1, std::min(n_images, kSpMicroBatch)), A, w);
+  return A.off + 256;
+}
+
+// ------------------------------------------------------------------ SuperGlue pipeline
+struct SgWs {
+  int Np, ldS, ld_uv;
+  size_t rows;           // 2 * B * Np
+  float *X, *QKV, *MSG, *HID, *IN4, *S, *u, *v, *max0;
+  int *idx0, *idx1;
+};
+bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
+  const int D = h->cfg.descriptor_dim;
+  w.Np = round_up(std::max(std::max(N, M), 1), 64);
+  w.rows = (size_t)2 * B * w.Np;
+  w.ldS = round_up(std::max(M, 1), 4);
+  w.ld_uv = round_up(std::max(N, M) + 1, 4);
+  w.X = A.take<float>(w.rows * 2 * D);
+  w.QKV = A.take<float>(w.rows * 3 * D);
+  w.MSG = A.take<float>(w.rows * D);
+  w.HID = A.take<float>(w.rows * 2 * D);
+  w.IN4 = A.take<float>(w.rows * 4);
+  w.S = A.take<float>((size_t)B * std::max(N, 1) * w.ldS);
+  w.u = A.take<float>((size_t)B * w.ld_uv);
+  w.v = A.take<float>((size_t)B * w.ld_uv);
+  w.max0 = A.take<float>((size_t)B * w.ld_uv);
+  w.idx0 = A.take<int>((size_t)B * w.ld_uv);
+  w.idx1 = A.take<int>((size_t)B * w.ld_uv);
+  return A.ok;
+}
+
+void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A, int lda, float* C, int ldc,
+                size_t M, bool relu, bool accumulate) {
+  GemmParams p;
+  p.A = A; p.lda = lda; p.strideA = 0;
+  p.Bw = h->d_w + L.w_off; p.ldb = L.K; p.strideB = 0;
+  p.C = C; p.ldc = ldc; p.strideC = 0;
+  p.bias = h->d_w + L.b_off;
+  p.M = (int)M; p.N = L.N; p.K = L.K; p.batch = 1;
+  p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
+  launch_gemm(ctx, p);
+}
+
+// keypoint encoder on one side: X[:, :D] += MLP([x_norm, y_norm, score])   (X already holds the descriptors)
+void sg_kenc(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int side, const float* kpts, const float* scores,
+             int B, int N, int Himg, int Wimg) {
+  const int D = h->cfg.descriptor_dim;
+  const size_t rows = (size_t)B * w.Np;
+  float* in4 = w.IN4 + (size_t)side * rows * 4;
+  // normalize_keypoints (:63-70): center = size/2, scaling = max(W,H) * 0.7
+  const float cx = (float)Wimg / 2.f, cy = (float)Himg / 2.f;
+  const float scale = (float)std::max(Wimg, Himg) * 0.7f;
+  launch_kenc_input(ctx, kpts, scores, B, N, w.Np, cx, cy, scale, in4);
+  // ping-pong through the (currently unused) QKV / HID buffers of this side
+  float* t0 = w.QKV + (size_t)side * rows * 3 * D;
+  float* t1 = w.HID + (size_t)side * rows * 2 * D;
+  const float* cur = in4;
+  int ld = 4;
+  for (size_t i = 0; i < h->kenc.size(); ++i) {
+    const Linear& L = h->kenc[i];
+    bool last = (i + 1 == h->kenc.size());
+    if (last) {
+      run_linear(h, ctx, L, cur, ld, w.X + (size_t)side * rows * 2 * D, 2 * D, rows, false, true);
+    } else {
+      float* dst = (i & 1) ? t1 : t0;
+      run_linear(h, ctx, L, cur, ld, dst, L.N, rows, true, false);
+      cur = dst;
+      ld = L.N;
+    }
+  }
+}
+
+void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0, const int* c1, int N, int M,
+            int l_begin, int l_end) {
+  const int D = h->cfg.descriptor_dim;
+  for (int l = l_begin; l < l_end; ++l) {
+    const b200m_handle::Gnn& G = h->gnn[l];
+    run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false);
+    launch_attention(ctx, w.QKV, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, h->cfg.gnn_cross[l] != 0);
+    run_linear(h, ctx, G.merge, w.MSG, D, w.X + D, 2 * D, w.rows, false, false);     // message -> X[:, D:2D]
+    run_linear(h, ctx, G.mlp1, w.X, 2 * D, w.HID, 2 * D, w.rows, true, false);       // relu(bn(W1 [x;msg]))
+    run_linear(h, ctx, G.mlp2, w.HID, 2 * D, w.X, 2 * D, w.rows, false, true);       // x += W2 hid
+  }
+}
+
+void sg_scores(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, int N, int M) {
+  const int D = h->cfg.descriptor_dim;
+  run_linear(h, ctx, h->final_proj, w.X, 2 * D, w.MSG, D, w.rows, false, false);
+  GemmParams p;
+  p.A = w.MSG; p.lda = D; p.strideA = (long long)w.Np * D;
+  p.Bw = w.MSG + (size_t)B * w.Np * D; p.ldb = D; p.strideB = (long long)w.Np * D;
+  p.C = w.S; p.ldc = w.ldS; p.strideC = (long long)N * w.ldS;
+  p.bias = nullptr; p.M = N; p.N = M; p.K = D; p.batch = B;
+  p.alpha = 1.f / sqrtf((float)D); p.relu = 0; p.accumulate = 0;
+  launch_gemm(ctx, p);
+}
+
+OtParams ot_params(b200m_handle* h, const SgWs& w, const float* S, int ldS, long long strideS, int B, int N, int M,
+                   const int* c0, const int* c1) {
+  OtParams p;
+  p.S = S; p.ldS = ldS; p.strideS = strideS; p.u = w.u; p.v = w.v; p.ld_uv = w.ld_uv;
+  p.counts0 = c0; p.counts1 = c1; p.B = B; p.N = N; p.M = M; p.alpha = h->bin_score;
+  return p;
+}
+
+// Sinkhorn sweeps in micro-batches of pairs whose score matrices fit the L2 together
+void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters) {
+  const size_t pair_bytes = (size_t)std::max(all.N, 1) * all.ldS * sizeof(float);
+  int chunk = (int)std::max<size_t>(1, (size_t)(64u << 20) / std::max<size_t>(pair_bytes, 1));
+  launch_ot_init(ctx, all);
+  for (int b0 = 0; b0 < all.B; b0 += chunk) {
+    OtParams p = all;
+    p.B = std::min(chunk, all.B - b0);
+    p.S = all.S + (size_t)b0 * all.strideS;
+    p.u = all.u + (size_t)b0 * all.ld_uv;
+    p.v = all.v + (size_t)b0 * all.ld_uv;
+    if (p.counts0) p.counts0 += b0;
+    if (p.counts1) p.counts1 += b0;
+    for (int it = 0; it < iters; ++it) {
+      launch_ot_row_update(ctx, p);
+      launch_ot_col_update(ctx, p);
+    }
+  }
+}
+
+int sg_core(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, const float* kpts0, const float* scores0,
+            const int* c0, const float* kpts1, const float* scores1, const int* c1, int B, int N, int M,
+            int H0, int W0, int H1, int W1, int64_t* matches0, int64_t* matches1, float* ms0, float* ms1) {
+  sg_kenc(h, ctx, w, 0, kpts0, scores0, B, N, H0, W0);
+  sg_kenc(h, ctx, w, 1, kpts1, scores1, B, M, H1, W1);
+  sg_gnn(h, ctx, w, B, c0, c1, N, M, 0, h->cfg.n_gnn_layers);
+  sg_scores(h, ctx, w, B, N, M);
+  OtParams p = ot_params(h, w, w.S, w.ldS, (long long)N * w.ldS, B, N, M, c0, c1);
+  sg_sinkhorn(h, ctx, p, h->cfg.sinkhorn_iterations);
+  launch_ot_argmax(ctx, p, w.idx0, w.max0, w.idx1);
+  launch_match_select(ctx, w.idx0, w.max0, w.idx1, w.ld_uv, c0, c1, B, N, M, h->cfg.match_threshold,
+                      (long long*)matches0, (long long*)matches1, ms0, ms1);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================== exported C ABI
+extern "C" {
+
+const char* b200m_last_error(void) { return g_err.c_str(); }
+int b200m_version(void) { return 100; }
+
+int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
+  if (!cfg || !out) return fail(B200M_ERR_INVALID, "null argument");
+  const int D = cfg->descriptor_dim;
+  if (!(D == 64 || D == 128 || D == 256)) return fail(B200M_ERR_INVALID, "descriptor_dim must be 64, 128 or 256 (got %d)", D);
+  if (cfg->nms_radius < 0 || cfg->nms_radius > 4)   // reference asserts nms_radius >= 0 (superpoint_test.py:9)
+    return fail(B200M_ERR_INVALID, "nms_radius must be in [0,4] (got %d)", cfg->nms_radius);
+  if (cfg->n_kenc < 1 || cfg->n_kenc > B200M_MAX_KENC) return fail(B200M_ERR_INVALID, "bad keypoint_encoder length");
+  for (int i = 0; i < cfg->n_kenc; ++i)
+    if (cfg->kenc[i] <= 0 || cfg->kenc[i] % 4 || cfg->kenc[i] > 2 * D)
+      return fail(B200M_ERR_INVALID, "keypoint_encoder widths must be multiples of 4 and <= 2*descriptor_dim");
+  if (cfg->n_gnn_layers < 0 || cfg->n_gnn_layers > B200M_MAX_GNN) return fail(B200M_ERR_INVALID, "bad GNN layer count");
+  if (cfg->sinkhorn_iterations < 0) return fail(B200M_ERR_INVALID, "negative sinkhorn_iterations");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(B200M_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return fail(B200M_ERR_CUDA, "libb200match is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  cudaSetDevice(device);
+  b200m_handle* h = new b200m_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  *out = h;
+  return B200M_OK;
+}
+
+void b200m_destroy(b200m_handle* h) {
+  if (!h) return;
+  if (h->d_w) cudaFree(h->d_w);
+  delete h;
+}
+
+int b200m_set_tensor(b200m_handle* h, const char* name, const float* data_host, const int64_t* shape, int ndim) {
+  if (!h || !name || ndim < 0 || (ndim > 0 && !shape)) return fail(B200M_ERR_INVALID, "null argument");
+  HostTensor t;
+  for (int i = 0; i < ndim; ++i) t.shape.push_back(shape[i]);
+  size_t n = t.numel();
+  if (n && !data_host) return fail(B200M_ERR_INVALID, "null data for %s", name);
+  t.data.assign(data_host, data_host + n);
+  h->tensors[name] = std::move(t);
+  h->packed_sp = h->packed_sg = false;
+  return B200M_OK;
+}
+
+int b200m_pack(b200m_handle* h, void* stream) {
+  if (!h) return fail(B200M_ERR_INVALID, "null handle");
+  cudaSetDevice(h->device);
+  return do_pack(h, (cudaStream_t)stream);
+}
+
+long long b200m_launch_count(const b200m_handle* h) { return h ? h->launches : 0; }
+
+int b200m_profile_begin(b200m_handle* h, int max_records) {
+  if (!h || max_records <= 0) return fail(B200M_ERR_INVALID, "bad argument");
+  h->prof_recs.assign((size_t)max_records, ProfRecord{nullptr, nullptr, nullptr});
+  h->prof.recs = h->prof_recs.data();
+  h->prof.cap = max_records;
+  h->prof.n = 0;
+  h->prof.enabled = true;
+  return B200M_OK;
+}
+
+int b200m_profile_end(b200m_handle* h, char* json, size_t json_cap) {
+  if (!h || !json || json_cap < 3) return fail(B200M_ERR_INVALID, "bad argument");
+  h->prof.enabled = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(B200M_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
+  std::map<std::string, std::pair<double, long long>> acc;
+  for (int i = 0; i < h->prof.n; ++i) {
+    ProfRecord& r = h->prof_recs[i];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+      auto& a = acc[r.name];
+      a.first += ms;
+      a.second += 1;
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  cudaGetLastError();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    out += buf;
+    first = false;
+  }
+  out += "}";
+  h->prof.n = 0;
+  if (out.size() + 1 > json_cap) return fail(B200M_ERR_INVALID, "profile buffer too small");
+  memcpy(json, out.c_str(), out.size() + 1);
+  return B200M_OK;
+}
+
+int b200m_keypoint_capacity(const b200m_handle* h, int H, int W) {
+  if (!h) return 0;
+  if (h->cfg.max_keypoints >= 0) return h->cfg.max_keypoints;
+  return sp_dims(h, H, W).cand_cap;
+}
+
+size_t b200m_superpoint_workspace_bytes(const b200m_handle* h, int n_images, int H, int W) {
+  return h ? sp_ws_bytes(h, n_images, H, W) : 0;
+}
+
+int b200m_superpoint_forward(b200m_handle* h, const float* images, int n_images, int H, int W, float* keypoints,
+                             float* scores, float* descriptors, int* counts, int cap, void* ws, size_t ws_bytes,
+                             void* stream) {
+  if (!h || !images || !keypoints || !scores || !counts) return fail(B200M_ERR_INVALID, "null argument");
+  if (cap < b200m_keypoint_capacity(h, H, W)) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
+  return sp_forward_impl(h, stream, images, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
+                         nullptr, nullptr, 0, 0, ws, ws_bytes);
+}
+
+int b200m_superpoint_dense(b200m_handle* h, const float* images, int n_images, int H, int W, float* semi,
+                           float* desc, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !images) return fail(B200M_ERR_INVALID, "null argument");
+  return sp_forward_impl(h, stream, images, n_images, H, W, nullptr, nullptr, nullptr, nullptr, 0, semi, desc,
+                         nullptr, 0, 0, ws, ws_bytes);
+}
+
+int b200m_detector_post(b200m_handle* h, const float* semi, int n_images, int hc, int wc, float* heat, float* nms,
+                        float* keypoints, float* scores, int* counts, int cap, void* ws, size_t ws_bytes,
+                        void* stream) {
+  if (!h || !semi) return fail(B200M_ERR_INVALID, "null argument");
+  SpDims d = sp_dims(h, hc * 8, wc * 8);
+  if (keypoints && cap < b200m_keypoint_capacity(h, hc * 8, wc * 8))
+    return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
+  Arena A(ws, ws_bytes);
+  float* semi_c4 = A.take<float>((size_t)n_images * 128 * hc * wc);
+  float* heat_ws = A.take<float>((size_t)n_images * d.H8 * d.W8);
+  unsigned long long* keys = A.take<unsigned long long>((size_t)n_images * d.cand_cap);
+  int* cc = A.take<int>(n_images + 1);
+  if (!A.ok) return fail(B200M_ERR_WORKSPACE, "detector_post workspace too small: need %zu bytes", A.off);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_nchw_to_c4(ctx, semi, 65, semi_c4, 32, n_images, hc, wc);
+  float* hp = heat ? heat : heat_ws;
+  launch_softmax_heat(ctx, semi_c4, 32, hp, n_images, hc, wc);
+  cudaMemsetAsync(cc, 0, sizeof(int) * (n_images + 1), ctx.stream);
+  launch_nms_candidates(ctx, hp, nms, n_images, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
+                        h->cfg.remove_borders, keypoints ? keys : nullptr, cc, d.cand_cap, cc + n_images);
+  if (keypoints)
+    launch_select_keypoints(ctx, keys, cc, d.cand_cap, n_images, d.W8, h->cfg.max_keypoints, keypoints, scores,
+                            counts, cap);
+  return finish(h, ctx);
+}
+
+int b200m_sample_descriptors(b200m_handle* h, const float* keypoints, const int* counts, const float* desc,
+                             int n_images, int hc, int wc, int cap, float* descriptors, void* stream) {
+  if (!h || !keypoints || !desc || !descriptors) return fail(B200M_ERR_INVALID, "null argument");
+  const int D = h->cfg.descriptor_dim;
+  // the stage API receives the reference-layout (n,D,h,w) map; the kernel wants C4-planar
+  float* tmp = nullptr;
+  if (cudaMallocAsync(&tmp, (size_t)n_images * D * hc * wc * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+    return fail(B200M_ERR_CUDA, "scratch allocation failed");
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_nchw_to_c4(ctx, desc, D, tmp, D / 4, n_images, hc, wc);
+  launch_sample_descriptors(ctx, tmp, D / 4, D, n_images, hc, wc, keypoints, counts, cap, h->cfg.align_corners,
+                            descriptors, nullptr, 0, 0);
+  cudaFreeAsync(tmp, (cudaStream_t)stream);
+  return finish(h, ctx);
+}
+
+size_t b200m_superglue_workspace_bytes(const b200m_handle* h, int B, int N, int M) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  SgWs w;
+  sg_carve(h, std::max(B, 1), N, M, A, w);
+  // stage APIs also stage a dense Z-sized / S-sized scratch
+  return A.off + 1024;
+}
+
+int b200m_superglue_forward(b200m_handle* h, const float* kpts0, const float* scores0, const float* desc0,
+                            const int* counts0, const float* kpts1, const float* scores1, const float* desc1,
+                            const int* counts1, int B, int N, int M, int H0, int W0, int H1, int W1,
+                            int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
+                            size_t ws_bytes, void* stream) {
+  if (!h) return fail(B200M_ERR_INVALID, "null handle");
+  if (!h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed (b200m_set_tensor + b200m_pack)");
+  if (B <= 0) return B200M_OK;
+  LaunchCtx ctx = make_ctx(h, stream);
+  if (N == 0 || M == 0) {   // superglue_test.py:235-242
+    launch_match_select(ctx, nullptr, nullptr, nullptr, 0, nullptr, nullptr, B, N, M, 0.f, (long long*)matches0,
+                        (long long*)matches1, mscores0, mscores1);
+    return finish(h, ctx);
+  }
+  const int D = h->cfg.descriptor_dim;
+  Arena A(ws, ws_bytes);
+  SgWs w;
+  if (!sg_carve(h, B, N, M, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperGlue workspace too small: need %zu bytes", A.off);
+  const size_t rows = (size_t)B * w.Np;
+  launch_bcn_to_tokens(ctx, desc0, B, D, N, w.X, w.Np, 2 * D);
+  launch_bcn_to_tokens(ctx, desc1, B, D, M, w.X + rows * 2 * D, w.Np, 2 * D);
+  sg_core(h, ctx, w, kpts0, scores0, counts0, kpts1, scores1, counts1, B, N, M, H0, W0, H1, W1, matches0,
+          matches1, mscores0, mscores1);
+  return finish(h, ctx);
+}
+
+int b200m_keypoint_encode(b200m_handle* h, const float* kpts, const float* scores, const float* desc, int B, int N,
+                          int H, int W, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed");
+  const int D = h->cfg.descriptor_dim;
+  Arena A(ws, ws_bytes);
+  SgWs w;
+  if (!sg_carve(h, B, N, N, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_bcn_to_tokens(ctx, desc, B, D, N, w.X, w.Np, 2 * D);
+  sg_kenc(h, ctx, w, 0, kpts, scores, B, N, H, W);
+  launch_tokens_to_bcn(ctx, w.X, w.Np, 2 * D, out, B, D, N);
+  return finish(h, ctx);
+}
+
+int b200m_gnn(b200m_handle* h, const float* desc0, const float* desc1, const int* counts0, const int* counts1,
+              int B, int N, int M, int layer_begin, int layer_end, float* out0, float* out1, void* ws,
+              size_t ws_bytes, void* stream) {
+  if (!h || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed");
+  if (layer_begin < 0 || layer_end > h->cfg.n_gnn_layers || layer_begin > layer_end)
+    return fail(B200M_ERR_INVALID, "bad layer range");
+  const int D = h->cfg.descriptor_dim;
+  Arena A(ws, ws_bytes);
+  SgWs w;
+  if (!sg_carve(h, B, N, M, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  const size_t rows = (size_t)B * w.Np;
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_bcn_to_tokens(ctx, desc0, B, D, N, w.X, w.Np, 2 * D);
+  launch_bcn_to_tokens(ctx, desc1, B, D, M, w.X + rows * 2 * D, w.Np, 2 * D);
+  sg_gnn(h, ctx, w, B, counts0, counts1, N, M, layer_begin, layer_end);
+  launch_tokens_to_bcn(ctx, w.X, w.Np, 2 * D, out0, B, D, N);
+  launch_tokens_to_bcn(ctx, w.X + rows * 2 * D, w.Np, 2 * D, out1, B, D, M);
+  return finish(h, ctx);
+}
+
+int b200m_score_matrix(b200m_handle* h, const float* desc0, const float* desc1, int B, int N, int M, float* S,
+                       void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed");
+  const int D = h->cfg.descriptor_dim;
+  Arena A(ws, ws_bytes);
+  SgWs w;
+  if (!sg_carve(h, B, N, M, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  const size_t rows = (size_t)B * w.Np;
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_bcn_to_tokens(ctx, desc0, B, D, N, w.X, w.Np, 2 * D);
+  launch_bcn_to_tokens(ctx, desc1, B, D, M, w.X + rows * 2 * D, w.Np, 2 * D);
+  sg_scores(h, ctx, w, B, N, M);
+  // compact (B,N,ldS) -> (B,N,M)
+  cudaMemcpy2DAsync(S, (size_t)M * sizeof(float), w.S, (size_t)w.ldS * sizeof(float), (size_t)M * sizeof(float),
+                    (size_t)B * N, cudaMemcpyDeviceToDevice, ctx.stream);
+  return finish(h, ctx);
+}
+
+int b200m_sinkhorn(b200m_handle* h, const float* S, int B, int N, int M, int iters, float* Z, void* ws,
+                   size_t ws_bytes, void* stream) {
+  if (!h || !S || !Z) return fail(B200M_ERR_INVALID, "null argument");
+  Arena A(ws, ws_bytes);
+  SgWs w;
+  w.ld_uv = round_up(std::max(N, M) + 1, 4);
+  w.u = A.take<float>((size_t)B * w.ld_uv);
+  w.v = A.take<float>((size_t)B * w.ld_uv);
+  if (!A.ok) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  LaunchCtx ctx = make_ctx(h, stream);
+  OtParams p = ot_params(h, w, S, M, (long long)N * M, B, N, M, nullptr, nullptr);
+  sg_sinkhorn(h, ctx, p, iters);
+  launch_ot_write_Z(ctx, p, Z);
+  return finish(h, ctx);
+}
+
+int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M, int64_t* matches0, int64_t* matches1,
+                       float* mscores0, float* mscores1, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !Z) return fail(B200M_ERR_INVALID, "null argument");
+  Arena A(ws, ws_bytes);
+  const int ld = round_up(std::max(N, M) + 1, 4);
+  float* max0 = A.take<float>((size_t)B * ld);
+  int* idx0 = A.take<int>((size_t)B * ld);
+  int* idx1 = A.take<int>((size_t)B * ld);
+  if (!A.ok) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_dense_argmax(ctx, Z, B, N, M, idx0, max0, idx1, ld);
+  launch_match_select(ctx, idx0, max0, idx1, ld, nullptr, nullptr, B, N, M, h->cfg.match_threshold,
+                      (long long*)matches0, (long long*)matches1, mscores0, mscores1);
+  return finish(h, ctx);
+}
+
+size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W) {
+  if (!h) return 0;
+  int cap = b200m_keypoint_capacity(h, H, W);
+  return align_up(sp_ws_bytes(h, B, H, W), 256) + b200m_superglue_workspace_bytes(h, B, cap, cap) + 256;
+}
+
+int b200m_matching_forward(b200m_handle* h, const float* image0, const float* image1, int B, int H, int W,
+                           float* keypoints0, float* scores0, float* descriptors0, int* counts0, float* keypoints1,
+                           float* scores1, float* descriptors1, int* counts1, int cap, int64_t* matches0,
+                           int64_t* matches1, float* mscores0, float* mscores1, void* ws, size_t ws_bytes,
+                           void* stream) {
+  if (!h || !image0 || !image1) return fail(B200M_ERR_INVALID, "null argument");
+  if (!h->packed_sp || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "both SuperPoint and SuperGlue weights must be packed");
+  if (B <= 0) return B200M_OK;
+  if (cap < b200m_keypoint_capacity(h, H, W) || cap <= 0) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
+  const int D = h->cfg.descriptor_dim;
+  const size_t sp_bytes = align_up(sp_ws_bytes(h, B, H, W), 256);
+  if (ws_bytes < sp_bytes) return fail(B200M_ERR_WORKSPACE, "matching workspace too small");
+  Arena A((char*)ws + sp_bytes, ws_bytes - sp_bytes);
+  SgWs w;
+  if (!sg_carve(h, B, cap, cap, A, w))
+    return fail(B200M_ERR_WORKSPACE, "matching workspace too small: need %zu bytes", sp_bytes + A.off);
+  const size_t rows = (size_t)B * w.Np;
+  // token rows in [cap, Np) are never written by the sampler but are read (masked) as attention keys,
+  // so they must be finite
+  if (w.Np != cap) cudaMemsetAsync(w.X, 0, w.rows * 2 * D * sizeof(float), (cudaStream_t)stream);
+  // SuperPoint writes token-major descriptors straight into X[:, :D] of its side
+  int rc = sp_forward_impl(h, stream, image0, B, H, W, keypoints0, scores0, descriptors0, counts0, cap, nullptr,
+                           nullptr, w.X, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
+  if (rc) return rc;
+  rc = sp_forward_impl(h, stream, image1, B, H, W, keypoints1, scores1, descriptors1, counts1, cap, nullptr,
+                       nullptr, w.X + rows * 2 * D, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
+  if (rc) return rc;
+  LaunchCtx ctx = make_ctx(h, stream);
+  sg_core(h, ctx, w, keypoints0, scores0, counts0, keypoints1, scores1, counts1, B, cap, cap, H, W, H, W, matches0,
+          matches1, mscores0, mscores1);
+  return finish(h, ctx);
+}
+
+}  // extern "C"

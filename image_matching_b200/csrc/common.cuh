@@ -1,0 +1,84 @@
+// Shared helpers for libb200match (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200match is written for sm_100a (B200) only"
+#endif
+
+namespace b200m {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+// ---- cp.async (LDGSTS) helpers --------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- warp reductions ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Launch bookkeeping: every launch goes through LAUNCH_CHECK so errors surface with a name and
+// the handle's launch counter (bench.py "gpu_launches") stays truthful.
+struct ProfRecord { const char* name; cudaEvent_t start, stop; };
+struct Profiler {            // optional per-launch CUDA-event timing (bench.py roofline leg)
+  bool enabled = false;
+  ProfRecord* recs = nullptr;
+  int n = 0, cap = 0;
+};
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  long long* counter;
+  const char** err_where;
+  cudaError_t err;
+  Profiler* prof;
+};
+
+// RAII: brackets one kernel launch with events on the launching stream when profiling is on.
+struct ProfScope {
+  Profiler* p; cudaStream_t s; int idx;
+  ProfScope(LaunchCtx& ctx, const char* name) : p(ctx.prof), s(ctx.stream), idx(-1) {
+    if (p && p->enabled && p->n < p->cap) {
+      idx = p->n++;
+      p->recs[idx].name = name;
+      cudaEventCreate(&p->recs[idx].start);
+      cudaEventCreate(&p->recs[idx].stop);
+      cudaEventRecord(p->recs[idx].start, s);
+    }
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(p->recs[idx].stop, s); }
+};
+
+#define B200M_LAUNCH_CHECK(ctx, name)                         \
+  do {                                                        \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if ((ctx).counter) ++*(ctx).counter;                      \
+    if (e__ != cudaSuccess && (ctx).err == cudaSuccess) {     \
+      (ctx).err = e__;                                        \
+      if ((ctx).err_where) *(ctx).err_where = name;           \
+    }                                                         \
+  } while (0)
+
+}  // namespace b200m

@@ -1,0 +1,99 @@
+// Internal launcher interface between api.cu (orchestration) and the kernel translation units.
+// Activation layout used by every SuperPoint kernel ("C4-planar"): [image][C/4][H][W][4] fp32,
+// i.e. pixels of a 4-channel group are contiguous float4s.  It makes (a) halo tiles of a channel
+// group a dense 2-D box (one TMA box / coalesced float4 rows), (b) a shifted 3x3 tap a plain
+// +16 B / +pitch address offset, and (c) the epilogue store of 4 consecutive output channels of
+// 32 consecutive pixels one 512 B coalesced row.
+// SuperGlue token layout: [side][pair][token][ld] fp32 row-major ("token-major"), K contiguous.
+#pragma once
+#include "common.cuh"
+
+namespace b200m {
+
+// ------------------------------------------------------------------ SuperPoint dense (sp_conv.cu)
+struct ConvParams {
+  const float* in;     // C4-planar, in_c4_total groups per image
+  int in_c4_total;
+  int in_c4_off;       // first input channel group read
+  int cin;             // input channels (multiple of 8)
+  const float* wpk;    // packed [cout_blk][cin_chunk][tap][8][64]
+  const float* bias;   // [cout_pad]
+  float* out;          // C4-planar, out_c4_total groups per image
+  int out_c4_total;
+  int out_c4_off;
+  int cout_pad;        // multiple of 64
+  int n, H, W;         // input spatial size (output = H,W or H/2,W/2 when pooled)
+  int relu;
+};
+void launch_conv1_direct(LaunchCtx& ctx, const float* img, const float* w9x64, const float* bias,
+                         float* out, int n, int H, int W);
+void launch_conv(LaunchCtx& ctx, const ConvParams& p, int ksize, bool pool);
+void launch_c4_to_nchw(LaunchCtx& ctx, const float* in, int c4_total, int c4_off, int C, float* out,
+                       int n, int H, int W, bool l2_normalize);
+void launch_nchw_to_c4(LaunchCtx& ctx, const float* in, int C, float* out, int c4_total, int n, int H, int W);
+void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* out,
+                            int out_c4_total, int C, int n, int H, int W);
+
+// ------------------------------------------------------------------ detector post (sp_post.cu)
+// semi C4-planar (>= 17 groups) -> heat (n, 8h, 8w)
+void launch_softmax_heat(LaunchCtx& ctx, const float* semi_c4, int c4_total, float* heat, int n, int hc, int wc);
+// heat -> optional dense nms map + candidate list (score, linear index) per image
+void launch_nms_candidates(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8,
+                           int radius, float thr, int border, unsigned long long* cand_keys,
+                           int* cand_counts, int cand_cap, int* overflow_flag);
+// candidate list -> keypoints (x,y), scores, counts; descending-score top-k or row-major order
+void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, const int* cand_counts,
+                             int cand_cap, int n, int W8, int max_kp, float* keypoints, float* scores,
+                             int* counts, int cap);
+// normalised C4-planar descriptor map + keypoints -> descriptors (n,D,cap) and/or token-major rows
+void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_total, int D, int n, int hc, int wc,
+                               const float* keypoints, const int* counts, int cap, int align_corners,
+                               float* out_dcn /* (n,D,cap) or null */,
+                               float* out_tok /* token-major rows or null */, int tok_ld, size_t tok_img_stride);
+
+// ------------------------------------------------------------------ SuperGlue linear (sg_linear.cu)
+struct GemmParams {
+  const float* A; int lda; long long strideA;   // [M,K] row-major
+  const float* Bw; int ldb; long long strideB;  // [N,K] row-major (weights / second operand)
+  float* C; int ldc; long long strideC;         // [M,N]
+  const float* bias;                            // [N] or null
+  int M, N, K, batch;
+  float alpha;       // C = alpha * (A B^T) + bias
+  int relu;
+  int accumulate;    // C += ...
+};
+void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
+// (B,C,N) channel-major <-> token-major [B][N][ld] (first C columns)
+void launch_bcn_to_tokens(LaunchCtx& ctx, const float* in, int B, int C, int N, float* out, int Np, int ld);
+void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float* out, int B, int C, int N);
+// normalised keypoints + score -> [rows][4] (x, y, score, 0)
+void launch_kenc_input(LaunchCtx& ctx, const float* kpts, const float* scores, int B, int N, int Np,
+                       float cx, float cy, float scale, float* out4);
+
+// ------------------------------------------------------------------ attention (sg_attn.cu)
+// qkv: [2*B*Np][3D] head-major columns (q | k | v); cross: source side = other side.
+void launch_attention(LaunchCtx& ctx, const float* qkv, float* msg, int B, int Np, int D, int heads,
+                      const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross);
+
+// ------------------------------------------------------------------ optimal transport (sg_ot.cu)
+struct OtParams {
+  const float* S; int ldS; long long strideS;   // scores (B, N, M) with leading dim ldS
+  float* u; float* v;                           // (B, ld_uv) each
+  int ld_uv;
+  const int* counts0; const int* counts1;       // device per-pair sizes or null
+  int B, N, M;                                  // full sizes (used when counts are null)
+  float alpha;
+};
+void launch_ot_init(LaunchCtx& ctx, const OtParams& p);
+void launch_ot_row_update(LaunchCtx& ctx, const OtParams& p);
+void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p);
+void launch_ot_write_Z(LaunchCtx& ctx, const OtParams& p, float* Z);   // dense (B,N+1,M+1), full sizes only
+// argmax over rows / columns of the final Z (computed on the fly from S,u,v)
+void launch_ot_argmax(LaunchCtx& ctx, const OtParams& p, int* idx0, float* max0, int* idx1);
+// same from a dense Z (stage API)
+void launch_dense_argmax(LaunchCtx& ctx, const float* Z, int B, int N, int M, int* idx0, float* max0, int* idx1, int ld);
+void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, const int* idx1, int ld,
+                         const int* counts0, const int* counts1, int B, int N, int M, float thr,
+                         long long* matches0, long long* matches1, float* ms0, float* ms1);
+
+}  // namespace b200m

@@ -1,0 +1,274 @@
+// Log-domain Sinkhorn optimal transport and mutual-nearest-neighbour match selection.
+// Reference: superglue/models/superglue_test.py:141-170 (log_sinkhorn_iterations, log_optimal_transport),
+// :268-285 (match selection).  HBM/L2-bound streaming kernels: the (N+1)x(M+1) couplings matrix is never
+// materialised -- the bin row/column are the scalar alpha -- and every sweep re-reads S (L2-resident when
+// the caller micro-batches pairs).  LSE uses the same max-shifted two-pass form as torch.logsumexp.
+#include "kernels.cuh"
+
+namespace b200m {
+
+struct PairDims { int n, m; float norm, mu_bin, nu_bin; };
+
+__device__ __forceinline__ PairDims pair_dims(const OtParams& p, int b) {
+  PairDims d;
+  d.n = p.counts0 ? p.counts0[b] : p.N;
+  d.m = p.counts1 ? p.counts1[b] : p.M;
+  d.norm = -logf((float)d.m + (float)d.n);          // norm = -(ms + ns).log()
+  d.mu_bin = logf((float)d.m) + d.norm;             // log_mu[-1] = ns.log() + norm  (ns = #columns)
+  d.nu_bin = logf((float)d.n) + d.norm;             // log_nu[-1] = ms.log() + norm  (ms = #rows)
+  return d;
+}
+
+__global__ void ot_init_kernel(float* u, float* v, int total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) { u[i] = 0.f; v[i] = 0.f; }
+}
+
+void launch_ot_init(LaunchCtx& ctx, const OtParams& p) {
+  ProfScope prof__(ctx, "ot_init");
+  int total = p.B * p.ld_uv;
+  ot_init_kernel<<<cdiv(total, 256), 256, 0, ctx.stream>>>(p.u, p.v, total);
+  B200M_LAUNCH_CHECK(ctx, "ot_init");
+}
+
+// u = log_mu - logsumexp(Z + v, dim=2): one warp per row (row n is the dustbin row).
+__global__ void __launch_bounds__(256) ot_row_kernel(OtParams p) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const PairDims d = pair_dims(p, b);
+  if (i > d.n || d.n == 0 || d.m == 0) return;
+  const float* v = p.v + (size_t)b * p.ld_uv;
+  const float* srow = p.S + (size_t)b * p.strideS + (size_t)i * p.ldS;
+  const bool bin_row = (i == d.n);
+  float mx = -INFINITY;
+  for (int j = lane; j <= d.m; j += 32) {
+    float c = (bin_row || j == d.m) ? p.alpha : srow[j];
+    mx = fmaxf(mx, c + v[j]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j <= d.m; j += 32) {
+    float c = (bin_row || j == d.m) ? p.alpha : srow[j];
+    sum += expf((c + v[j]) - mx);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) p.u[(size_t)b * p.ld_uv + i] = (bin_row ? d.mu_bin : d.norm) - (logf(sum) + mx);
+}
+
+void launch_ot_row_update(LaunchCtx& ctx, const OtParams& p) {
+  ProfScope prof__(ctx, "ot_row_update");
+  dim3 grid(cdiv(p.N + 1, 8), p.B);
+  ot_row_kernel<<<grid, 256, 0, ctx.stream>>>(p);
+  B200M_LAUNCH_CHECK(ctx, "ot_row");
+}
+
+// v = log_nu - logsumexp(Z + u, dim=1): a block owns 32 columns, its 8 warps stride over the rows with
+// coalesced 128 B row reads; per-column partial max / sum are combined through shared memory.
+__global__ void __launch_bounds__(256) ot_col_kernel(OtParams p) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const PairDims d = pair_dims(p, b);
+  if (d.n == 0 || d.m == 0) return;               // uniform per block
+  if (blockIdx.x * 32 > d.m) return;              // uniform per block
+  const float* u = p.u + (size_t)b * p.ld_uv;
+  const float* S = p.S + (size_t)b * p.strideS;
+  const bool active = j <= d.m;
+  const bool bin_col = (j == d.m);
+  float mx = -INFINITY;
+  if (active)
+    for (int i = w; i <= d.n; i += 8) {
+      float c = (bin_col || i == d.n) ? p.alpha : S[(size_t)i * p.ldS + j];
+      mx = fmaxf(mx, c + u[i]);
+    }
+  red[w][lane] = mx;
+  __syncthreads();
+  mx = red[0][lane];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k][lane]);
+  __syncthreads();
+  float sum = 0.f;
+  if (active)
+    for (int i = w; i <= d.n; i += 8) {
+      float c = (bin_col || i == d.n) ? p.alpha : S[(size_t)i * p.ldS + j];
+      sum += expf((c + u[i]) - mx);
+    }
+  red[w][lane] = sum;
+  __syncthreads();
+  if (w == 0 && active) {
+    sum = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) sum += red[k][lane];
+    p.v[(size_t)b * p.ld_uv + j] = (bin_col ? d.nu_bin : d.norm) - (logf(sum) + mx);
+  }
+}
+
+void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
+  ProfScope prof__(ctx, "ot_col_update");
+  dim3 grid(cdiv(p.M + 1, 32), p.B);
+  ot_col_kernel<<<grid, 256, 0, ctx.stream>>>(p);
+  B200M_LAUNCH_CHECK(ctx, "ot_col");
+}
+
+// Z = couplings + u + v - norm, dense (stage API; full sizes)
+__global__ void ot_write_Z_kernel(OtParams p, float* __restrict__ Z) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > p.M) return;
+  const PairDims d = pair_dims(p, b);
+  float c = (i == p.N || j == p.M) ? p.alpha : p.S[(size_t)b * p.strideS + (size_t)i * p.ldS + j];
+  float z = ((c + p.u[(size_t)b * p.ld_uv + i]) + p.v[(size_t)b * p.ld_uv + j]) - d.norm;
+  Z[((size_t)b * (p.N + 1) + i) * (p.M + 1) + j] = z;
+}
+
+void launch_ot_write_Z(LaunchCtx& ctx, const OtParams& p, float* Z) {
+  dim3 grid(cdiv(p.M + 1, 256), p.N + 1, p.B);
+  ot_write_Z_kernel<<<grid, 256, 0, ctx.stream>>>(p, Z);
+  B200M_LAUNCH_CHECK(ctx, "ot_write_Z");
+}
+
+// ---- argmax over rows / columns of Z[:, :-1, :-1]  (scores.max(2), scores.max(1); first index on ties)
+struct ZSource {
+  const float* S; int ldS; long long strideS; const float* u; const float* v; int ld_uv;
+  const float* Z; int ldZ; long long strideZ;   // dense alternative
+};
+__device__ __forceinline__ float z_at(const ZSource& z, int b, int i, int j, float norm) {
+  if (z.Z) return z.Z[(size_t)b * z.strideZ + (size_t)i * z.ldZ + j];
+  float c = z.S[(size_t)b * z.strideS + (size_t)i * z.ldS + j];
+  return ((c + z.u[(size_t)b * z.ld_uv + i]) + z.v[(size_t)b * z.ld_uv + j]) - norm;
+}
+
+__global__ void __launch_bounds__(256) row_argmax_kernel(ZSource z, const int* counts0, const int* counts1,
+                                                         int N, int M, int* __restrict__ idx0,
+                                                         float* __restrict__ max0, int ld) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n = counts0 ? counts0[b] : N, m = counts1 ? counts1[b] : M;
+  if (i >= n || m == 0) return;
+  const float norm = -logf((float)m + (float)n);
+  float best = -INFINITY;
+  int bj = 0x7fffffff;
+  for (int j = lane; j < m; j += 32) {
+    float val = z_at(z, b, i, j, norm);
+    if (val > best) { best = val; bj = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+  }
+  if (lane == 0) { idx0[(size_t)b * ld + i] = bj; max0[(size_t)b * ld + i] = best; }
+}
+
+__global__ void __launch_bounds__(256) col_argmax_kernel(ZSource z, const int* counts0, const int* counts1,
+                                                         int N, int M, int* __restrict__ idx1, int ld) {
+  __shared__ float rv[8][33];
+  __shared__ int ri[8][33];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const int n = counts0 ? counts0[b] : N, m = counts1 ? counts1[b] : M;
+  if (n == 0 || blockIdx.x * 32 >= m) return;   // uniform per block
+  const float norm = -logf((float)m + (float)n);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (j < m)
+    for (int i = w; i < n; i += 8) {
+      float val = z_at(z, b, i, j, norm);
+      if (val > best) { best = val; bi = i; }
+    }
+  rv[w][lane] = best;
+  ri[w][lane] = bi;
+  __syncthreads();
+  if (w == 0 && j < m) {
+    for (int k = 1; k < 8; ++k) {
+      float ov = rv[k][lane];
+      int oi = ri[k][lane];
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    idx1[(size_t)b * ld + j] = bi;
+  }
+}
+
+static void launch_argmax_common(LaunchCtx& ctx, const ZSource& z, const int* c0, const int* c1, int B, int N,
+                                 int M, int* idx0, float* max0, int* idx1, int ld) {
+  ProfScope prof__(ctx, "argmax");
+  if (N <= 0 || M <= 0) return;
+  dim3 g0(cdiv(N, 8), B);
+  row_argmax_kernel<<<g0, 256, 0, ctx.stream>>>(z, c0, c1, N, M, idx0, max0, ld);
+  B200M_LAUNCH_CHECK(ctx, "row_argmax");
+  dim3 g1(cdiv(M, 32), B);
+  col_argmax_kernel<<<g1, 256, 0, ctx.stream>>>(z, c0, c1, N, M, idx1, ld);
+  B200M_LAUNCH_CHECK(ctx, "col_argmax");
+}
+
+void launch_ot_argmax(LaunchCtx& ctx, const OtParams& p, int* idx0, float* max0, int* idx1) {
+  ZSource z{p.S, p.ldS, p.strideS, p.u, p.v, p.ld_uv, nullptr, 0, 0};
+  launch_argmax_common(ctx, z, p.counts0, p.counts1, p.B, p.N, p.M, idx0, max0, idx1, p.ld_uv);
+}
+
+void launch_dense_argmax(LaunchCtx& ctx, const float* Z, int B, int N, int M, int* idx0, float* max0, int* idx1,
+                         int ld) {
+  ZSource z{nullptr, 0, 0, nullptr, nullptr, 0, Z, M + 1, (long long)(N + 1) * (M + 1)};
+  launch_argmax_common(ctx, z, nullptr, nullptr, B, N, M, idx0, max0, idx1, ld);
+}
+
+// mutual check + exp + threshold (:270-278); indices widened to int64 at the boundary
+__global__ void match_select_kernel(const int* __restrict__ idx0, const float* __restrict__ max0,
+                                    const int* __restrict__ idx1, int ld, const int* counts0, const int* counts1,
+                                    int N, int M, float thr, long long* __restrict__ matches0,
+                                    long long* __restrict__ matches1, float* __restrict__ ms0,
+                                    float* __restrict__ ms1) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = counts0 ? counts0[b] : N, m = counts1 ? counts1[b] : M;
+  const int* i0 = idx0 + (size_t)b * ld;
+  const int* i1 = idx1 + (size_t)b * ld;
+  const float* mx = max0 + (size_t)b * ld;
+  const bool empty = (n == 0 || m == 0);
+  if (t < N) {
+    long long mt = -1;
+    float sc = 0.f;
+    if (!empty && t < n) {
+      int j = i0[t];
+      bool mutual = (i1[j] == t);
+      sc = mutual ? expf(mx[t]) : 0.f;
+      if (mutual && sc > thr) mt = j;
+    }
+    matches0[(size_t)b * N + t] = mt;
+    ms0[(size_t)b * N + t] = sc;
+  }
+  if (t < M) {
+    long long mt = -1;
+    float sc = 0.f;
+    if (!empty && t < m) {
+      int i = i1[t];
+      bool mutual1 = (i0[i] == t);
+      // mscores0[i] and valid0[i] of the row this column points at
+      bool mutual0 = (i1[i0[i]] == i);
+      float s0 = mutual0 ? expf(mx[i]) : 0.f;
+      sc = mutual1 ? s0 : 0.f;
+      if (mutual1 && mutual0 && s0 > thr) mt = i;
+    }
+    matches1[(size_t)b * M + t] = mt;
+    ms1[(size_t)b * M + t] = sc;
+  }
+}
+
+void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, const int* idx1, int ld,
+                         const int* counts0, const int* counts1, int B, int N, int M, float thr,
+                         long long* matches0, long long* matches1, float* ms0, float* ms1) {
+  ProfScope prof__(ctx, "match_select");
+  int T = N > M ? N : M;
+  if (T <= 0) return;
+  dim3 grid(cdiv(T, 256), B);
+  match_select_kernel<<<grid, 256, 0, ctx.stream>>>(idx0, max0, idx1, ld, counts0, counts1, N, M, thr, matches0,
+                                                    matches1, ms0, ms1);
+  B200M_LAUNCH_CHECK(ctx, "match_select");
+}
+
+}  // namespace b200m

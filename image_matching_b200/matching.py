@@ -1,0 +1,405 @@
+"""Drop-in replacements for the reference's inference modules, backed by libb200match.so.
+
+    reference                                                      here
+    superglue/models/matching_test.py:47-82   Matching          -> Matching
+    superpoint/models/superpoint_test.py:55-161 SuperPoint      -> SuperPoint
+    superglue/models/superglue_test.py:177-285 SuperGlue        -> SuperGlue
+
+Same constructor config dicts and defaults, same state_dict key names (so the reference's
+checkpoints load with ``load_state_dict``), same ``forward`` inputs/outputs (container
+types, dtypes, layouts).  torch is only the boundary: tensors in / tensors out, device
+memory and the current CUDA stream.  All arithmetic happens in the hand-written sm_100a
+kernels behind the C ABI; there is no eager/CPU fallback -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import lib as _lib
+
+
+def _align_corners_from_torch_version() -> bool:
+    # the reference's switch, verbatim semantics (superpoint_test.py:47): third character of the
+    # version string; "2.11.0" -> '1' -> False
+    try:
+        return int(torch.__version__[2]) > 2
+    except ValueError:
+        return False
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _register(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool = False):
+    """Create nested container modules so that state_dict() yields exactly `dotted`."""
+    parts = dotted.split(".")
+    m = root
+    for p in parts[:-1]:
+        if p not in m._modules:
+            m.add_module(p, nn.Module())
+        m = m._modules[p]
+    if buffer:
+        m.register_buffer(parts[-1], tensor)
+    else:
+        m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _conv_bn_params(root, conv, bn, cout, cin, k, ndim=2):
+    shape = (cout, cin, k, k) if ndim == 2 else (cout, cin, 1)
+    fan_in = cin * k * k
+    bound = 1.0 / np.sqrt(fan_in)
+    _register(root, conv + ".weight", torch.empty(shape).uniform_(-bound, bound))
+    _register(root, conv + ".bias", torch.empty(cout).uniform_(-bound, bound))
+    if bn:
+        _register(root, bn + ".weight", torch.ones(cout))
+        _register(root, bn + ".bias", torch.zeros(cout))
+        _register(root, bn + ".running_mean", torch.zeros(cout), buffer=True)
+        _register(root, bn + ".running_var", torch.ones(cout), buffer=True)
+        _register(root, bn + ".num_batches_tracked", torch.tensor(0, dtype=torch.long), buffer=True)
+
+
+class _Engine:
+    """Owns one b200m handle (per device) for a set of modules and their packed weights."""
+
+    def __init__(self):
+        self.handle = None
+        self.device = None
+        self.cfg_key = None
+        self.dirty = True
+        self.ws = None
+
+    def close(self):
+        if self.handle is not None:
+            _lib.load().b200m_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ensure(self, device: torch.device, sp: "SuperPoint | None", sg: "SuperGlue | None"):
+        if device.type != "cuda":
+            raise RuntimeError("image_matching_b200 runs on CUDA (sm_100a) only; got a %s tensor -- "
+                               "there is no CPU fallback" % device.type)
+        L = _lib.load()
+        spc = sp.config if sp is not None else SuperPoint.default_config
+        # a SuperPoint-only engine never runs the SuperGlue half: give it a minimal, always-valid shape
+        sgc = sg.config if sg is not None else {"keypoint_encoder": [32], "GNN_layers": [],
+                                                "sinkhorn_iterations": 0, "match_threshold": 0.2}
+        D = (sp or sg).config["descriptor_dim"]
+        names = list(sgc["GNN_layers"])
+        key = (device.index, D, spc["nms_radius"], float(spc["keypoint_threshold"]), spc["max_keypoints"],
+               spc["remove_borders"], tuple(sgc["keypoint_encoder"]), tuple(names),
+               sgc["sinkhorn_iterations"], float(sgc["match_threshold"]))
+        if self.handle is None or key != self.cfg_key:
+            self.close()
+            cfg = _lib.Config()
+            cfg.descriptor_dim = D
+            cfg.nms_radius = spc["nms_radius"]
+            cfg.keypoint_threshold = spc["keypoint_threshold"]
+            cfg.max_keypoints = spc["max_keypoints"]
+            cfg.remove_borders = spc["remove_borders"]
+            cfg.align_corners = int(_align_corners_from_torch_version())
+            kenc = list(sgc["keypoint_encoder"])
+            cfg.n_kenc = len(kenc)
+            for i, v in enumerate(kenc):
+                cfg.kenc[i] = v
+            cfg.n_gnn_layers = len(names)
+            for i, nme in enumerate(names):
+                cfg.gnn_cross[i] = 1 if nme == "cross" else 0
+            cfg.sinkhorn_iterations = sgc["sinkhorn_iterations"]
+            cfg.match_threshold = sgc["match_threshold"]
+            hp = C.c_void_p()
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            _lib.check(L.b200m_create(C.byref(cfg), idx, C.byref(hp)), "b200m_create")
+            self.handle, self.device, self.cfg_key, self.dirty = hp, device, key, True
+        if self.dirty or (sp is not None and sp._dirty) or (sg is not None and sg._dirty):
+            for prefix, mod in (("superpoint.", sp), ("superglue.", sg)):
+                if mod is None:
+                    continue
+                for k, v in mod.state_dict().items():
+                    if k.endswith("num_batches_tracked"):
+                        continue
+                    a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
+                    shp = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+                    _lib.check(L.b200m_set_tensor(self.handle, (prefix + k).encode(),
+                                                  a.ctypes.data_as(C.c_void_p), shp, a.ndim), "b200m_set_tensor")
+                mod._dirty = False
+            with torch.cuda.device(device):
+                _lib.check(L.b200m_pack(self.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                           "b200m_pack")
+            self.dirty = False
+        return L
+
+    def workspace(self, nbytes: int, device):
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
+            self.ws = None
+            self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.ws
+
+    def launch_count(self) -> int:
+        return int(_lib.load().b200m_launch_count(self.handle)) if self.handle is not None else 0
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _B200Module(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._dirty = True
+        self._engine = _Engine()
+
+    def _load_from_state_dict(self, *a, **k):   # weights changed -> repack on next forward
+        self._dirty = True
+        return super()._load_from_state_dict(*a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._dirty = True
+        return super().load_state_dict(*a, **k)
+
+
+class SuperPoint(_B200Module):
+    """B200-native SuperPoint (reference: superpoint/models/superpoint_test.py:55-161)."""
+    default_config = {
+        "descriptor_dim": 256,
+        "nms_radius": 4,
+        "keypoint_threshold": 0.005,
+        "max_keypoints": -1,
+        "remove_borders": 4,
+    }
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = {**self.default_config, **config}
+        d1 = self.config["descriptor_dim"]
+        c1, c2, c3, c4, c5, det_h = 64, 64, 128, 128, 256, 65
+        for prefix, cin, cout in (("inc.conv.conv", 1, c1), ("down1.mpconv.1.conv", c1, c2),
+                                  ("down2.mpconv.1.conv", c2, c3), ("down3.mpconv.1.conv", c3, c4)):
+            _conv_bn_params(self, prefix + ".0", prefix + ".1", cout, cin, 3)
+            _conv_bn_params(self, prefix + ".3", prefix + ".4", cout, cout, 3)
+        _conv_bn_params(self, "convPa", "bnPa", c5, c4, 3)
+        _conv_bn_params(self, "convPb", "bnPb", det_h, c5, 1)
+        _conv_bn_params(self, "convDa", "bnDa", c5, c4, 3)
+        _conv_bn_params(self, "convDb", "bnDb", d1, c5, 1)
+        if self.config["weights"]:   # KeyError if absent, like the reference (superpoint_test.py:87)
+            checkpoints = torch.load(self.config["weights"], map_location="cpu")
+            sd = OrderedDict((k[7:] if "module" in k else k, v)
+                             for k, v in checkpoints["model_state_dict"].items())
+            self.load_state_dict(sd)
+            print("Loaded SuperPoint model")
+
+    def _run(self, engine, L, x, sg=None):
+        B, _, H, W = x.shape
+        dev = x.device
+        D = self.config["descriptor_dim"]
+        cap = int(L.b200m_keypoint_capacity(engine.handle, H, W))
+        kp = torch.empty((B, cap, 2), dtype=torch.float32, device=dev)
+        sc = torch.empty((B, cap), dtype=torch.float32, device=dev)
+        de = torch.empty((B, D, cap), dtype=torch.float32, device=dev)
+        cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        nbytes = L.b200m_superpoint_workspace_bytes(engine.handle, B, H, W)
+        ws = engine.workspace(nbytes, dev)
+        _lib.check(L.b200m_superpoint_forward(engine.handle, _ptr(x), B, H, W, _ptr(kp), _ptr(sc), _ptr(de),
+                                              _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream()),
+                   "b200m_superpoint_forward")
+        return kp, sc, de, cnt
+
+    @staticmethod
+    def _to_lists(kp, sc, de, cnt_host):
+        keypoints = [kp[i, :n] for i, n in enumerate(cnt_host)]
+        scores = tuple(sc[i, :n] for i, n in enumerate(cnt_host))
+        descriptors = [de[i, :, :n] for i, n in enumerate(cnt_host)]
+        return keypoints, scores, descriptors
+
+    def forward(self, x):
+        x = x.contiguous().float()
+        L = self._engine.ensure(x.device, self, None)
+        kp, sc, de, cnt = self._run(self._engine, L, x)
+        keypoints, scores, descriptors = self._to_lists(kp, sc, de, cnt.cpu().tolist())
+        return {"keypoints": keypoints, "scores": scores, "descriptors": descriptors}
+
+
+class SuperGlue(_B200Module):
+    """B200-native SuperGlue (reference: superglue/models/superglue_test.py:177-285)."""
+    default_config = {
+        "descriptor_dim": 256,
+        "weights": "indoor",
+        "keypoint_encoder": [32, 64, 128, 256],
+        "GNN_layers": ["self", "cross"] * 9,
+        "sinkhorn_iterations": 100,
+        "match_threshold": 0.2,
+    }
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = {**self.default_config, **config}
+        D = self.config["descriptor_dim"]
+        ch = [3] + list(self.config["keypoint_encoder"]) + [D]
+        idx = 0
+        for i in range(1, len(ch)):
+            last = i == len(ch) - 1
+            _conv_bn_params(self, f"kenc.encoder.{idx}", None if last else f"kenc.encoder.{idx + 1}",
+                            ch[i], ch[i - 1], 1, ndim=1)
+            idx += 1 if last else 3
+        for l in range(len(self.config["GNN_layers"])):
+            p = f"gnn.layers.{l}"
+            _conv_bn_params(self, p + ".attn.merge", None, D, D, 1, ndim=1)
+            for j in range(3):
+                _conv_bn_params(self, p + f".attn.proj.{j}", None, D, D, 1, ndim=1)
+            _conv_bn_params(self, p + ".mlp.0", p + ".mlp.1", 2 * D, 2 * D, 1, ndim=1)
+            _conv_bn_params(self, p + ".mlp.3", None, D, 2 * D, 1, ndim=1)
+        _conv_bn_params(self, "final_proj", None, D, D, 1, ndim=1)
+        _register(self, "bin_score", torch.tensor(1.0))
+        # state_dict order of the reference: bin_score first; order does not matter for loading
+        if self.config["weights"]:
+            checkpoints = torch.load(config["weights"], map_location="cpu")
+            if "indoor" in self.config["weights"] or "outdoor" in self.config["weights"]:
+                state_dict = checkpoints
+            else:
+                state_dict = checkpoints["net"]
+            self.load_state_dict(state_dict)
+            print("Loaded SuperGlue model weights")
+
+    def _run(self, engine, L, data, counts0=None, counts1=None):
+        kpts0, kpts1 = data["keypoints0"].contiguous().float(), data["keypoints1"].contiguous().float()
+        desc0, desc1 = data["descriptors0"].contiguous().float(), data["descriptors1"].contiguous().float()
+        sc0, sc1 = data["scores0"].contiguous().float(), data["scores1"].contiguous().float()
+        B, N, M = kpts0.shape[0], kpts0.shape[1], kpts1.shape[1]
+        dev = kpts0.device
+        _, _, H0, W0 = data["image0"].shape
+        _, _, H1, W1 = data["image1"].shape
+        m0 = torch.empty((B, N), dtype=torch.int64, device=dev)
+        m1 = torch.empty((B, M), dtype=torch.int64, device=dev)
+        s0 = torch.empty((B, N), dtype=torch.float32, device=dev)
+        s1 = torch.empty((B, M), dtype=torch.float32, device=dev)
+        nbytes = L.b200m_superglue_workspace_bytes(engine.handle, B, N, M)
+        ws = engine.workspace(nbytes, dev)
+        _lib.check(L.b200m_superglue_forward(engine.handle, _ptr(kpts0), _ptr(sc0), _ptr(desc0), _ptr(counts0),
+                                             _ptr(kpts1), _ptr(sc1), _ptr(desc1), _ptr(counts1),
+                                             B, N, M, H0, W0, H1, W1, _ptr(m0), _ptr(m1), _ptr(s0), _ptr(s1),
+                                             _ptr(ws), ws.numel(), _stream()), "b200m_superglue_forward")
+        return m0, m1, s0, s1
+
+    def forward(self, data, _engine=None):
+        kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
+        if kpts0.shape[1] == 0 or kpts1.shape[1] == 0:  # no keypoints (superglue_test.py:235-242)
+            shape0, shape1 = kpts0.shape[:-1], kpts1.shape[:-1]
+            return {
+                "matches0": kpts0.new_full(shape0, -1, dtype=torch.int),
+                "matches1": kpts1.new_full(shape1, -1, dtype=torch.int),
+                "matching_scores0": kpts0.new_zeros(shape0),
+                "matching_scores1": kpts1.new_zeros(shape1),
+            }
+        engine = _engine or self._engine
+        L = engine.ensure(kpts0.device, None if _engine is None else _engine._sp, self)
+        m0, m1, s0, s1 = self._run(engine, L, data)
+        return {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1}
+
+
+class Matching(nn.Module):
+    """Image Matching Frontend (SuperPoint + SuperGlue); reference: superglue/models/matching_test.py:47-82."""
+
+    def __init__(self, config={}):
+        super().__init__()
+        self.superpoint = SuperPoint(config.get("superpoint", {}))
+        self.superglue = SuperGlue(config.get("superglue", {}))
+        self._engine = _Engine()
+        self._engine._sp = self.superpoint
+
+    def _ensure(self, device):
+        return self._engine.ensure(device, self.superpoint, self.superglue)
+
+    # ---- fused fast path: one C call for SuperPoint x2 + SuperGlue, no host sync inside
+    def forward_device(self, image0: torch.Tensor, image1: torch.Tensor):
+        """Device-resident results without any host synchronisation: dict of padded tensors plus
+        per-pair `counts0/1` (number of valid leading keypoints)."""
+        image0 = image0.contiguous().float()
+        image1 = image1.contiguous().float()
+        if image0.shape != image1.shape:
+            raise ValueError("forward_device needs equally shaped image batches")
+        L = self._ensure(image0.device)
+        e = self._engine
+        B, _, H, W = image0.shape
+        dev = image0.device
+        D = self.superpoint.config["descriptor_dim"]
+        cap = int(L.b200m_keypoint_capacity(e.handle, H, W))
+        f32, i64 = torch.float32, torch.int64
+        out = {
+            "keypoints0": torch.empty((B, cap, 2), dtype=f32, device=dev),
+            "scores0": torch.empty((B, cap), dtype=f32, device=dev),
+            "descriptors0": torch.empty((B, D, cap), dtype=f32, device=dev),
+            "keypoints1": torch.empty((B, cap, 2), dtype=f32, device=dev),
+            "scores1": torch.empty((B, cap), dtype=f32, device=dev),
+            "descriptors1": torch.empty((B, D, cap), dtype=f32, device=dev),
+            "counts": torch.empty((2, B), dtype=torch.int32, device=dev),
+            "matches0": torch.empty((B, cap), dtype=i64, device=dev),
+            "matches1": torch.empty((B, cap), dtype=i64, device=dev),
+            "matching_scores0": torch.empty((B, cap), dtype=f32, device=dev),
+            "matching_scores1": torch.empty((B, cap), dtype=f32, device=dev),
+        }
+        nbytes = L.b200m_matching_workspace_bytes(e.handle, B, H, W)
+        ws = e.workspace(nbytes, dev)
+        c0, c1 = out["counts"][0], out["counts"][1]
+        _lib.check(L.b200m_matching_forward(
+            e.handle, _ptr(image0), _ptr(image1), B, H, W,
+            _ptr(out["keypoints0"]), _ptr(out["scores0"]), _ptr(out["descriptors0"]), _ptr(c0),
+            _ptr(out["keypoints1"]), _ptr(out["scores1"]), _ptr(out["descriptors1"]), _ptr(c1), cap,
+            _ptr(out["matches0"]), _ptr(out["matches1"]), _ptr(out["matching_scores0"]),
+            _ptr(out["matching_scores1"]), _ptr(ws), ws.numel(), _stream()), "b200m_matching_forward")
+        return out
+
+    def forward(self, data):
+        """Run SuperPoint (optionally) and SuperGlue; same contract as the reference's Matching.forward."""
+        pred = {}
+        need0, need1 = "keypoints0" not in data, "keypoints1" not in data
+        if need0 and need1 and data["image0"].shape == data["image1"].shape:
+            out = self.forward_device(data["image0"], data["image1"])
+            cnt = out["counts"].cpu()          # the only host sync: list lengths are data dependent
+            c0, c1 = cnt[0].tolist(), cnt[1].tolist()
+            k0, s0, d0 = SuperPoint._to_lists(out["keypoints0"], out["scores0"], out["descriptors0"], c0)
+            k1, s1, d1 = SuperPoint._to_lists(out["keypoints1"], out["scores1"], out["descriptors1"], c1)
+            pred = {"keypoints0": k0, "scores0": s0, "descriptors0": d0,
+                    "keypoints1": k1, "scores1": s1, "descriptors1": d1}
+            if len(set(c0)) > 1 or len(set(c1)) > 1:
+                # the reference stacks the per-image lists (matching_test.py:75-77) and fails here
+                raise RuntimeError("stack expects each tensor to be equal size, but got keypoint counts "
+                                   f"{c0} / {c1} in the batch")
+            n, m = c0[0], c1[0]
+            if n == 0 or m == 0:
+                dev = data["image0"].device
+                B = len(c0)
+                pred.update({"matches0": torch.full((B, n), -1, dtype=torch.int, device=dev),
+                             "matches1": torch.full((B, m), -1, dtype=torch.int, device=dev),
+                             "matching_scores0": torch.zeros((B, n), device=dev),
+                             "matching_scores1": torch.zeros((B, m), device=dev)})
+            else:
+                pred.update({"matches0": out["matches0"][:, :n], "matches1": out["matches1"][:, :m],
+                             "matching_scores0": out["matching_scores0"][:, :n],
+                             "matching_scores1": out["matching_scores1"][:, :m]})
+            return pred
+
+        # general path (features supplied for one or both sides; matching_test.py:63-80)
+        dev = data["image0"].device
+        L = self._ensure(dev)
+        for side, need in (("0", need0), ("1", need1)):
+            if need:
+                x = data["image" + side].contiguous().float()
+                kp, sc, de, cnt = self.superpoint._run(self._engine, L, x)
+                ks, ss, ds = SuperPoint._to_lists(kp, sc, de, cnt.cpu().tolist())
+                pred.update({"keypoints" + side: ks, "scores" + side: ss, "descriptors" + side: ds})
+        data = {**data, **pred}
+        for k in data:
+            if isinstance(data[k], (list, tuple)):
+                data[k] = torch.stack(data[k])
+        pred = {**pred, **self.superglue.forward(data, _engine=self._engine)}
+        return pred

@@ -43,21 +43,33 @@ def fold_bn(w, b, sd, bn, eps=1e-5):
     return wf.astype(F32), bf.astype(F32)
 
 
-def conv3x3(x, w, b, relu):
-    """3x3 stride-1 zero-pad-1 cross-correlation; x (C,H,W), w (O,C,3,3)  (unet_parts.py:15,18)."""
-    C, H, W = x.shape
+def conv3x3_hwc(x, w, b, relu):
+    """3x3 stride-1 zero-pad-1 cross-correlation; x (H,W,C) channel-last, w (O,C,3,3) -> (H,W,O)
+    (unet_parts.py:15,18).  im2col over strips of rows + one BLAS sgemm per strip (pixels x 9C @ 9C x O;
+    the pixel-major operand order is the one OpenBLAS runs at full speed)."""
+    H, W, C = x.shape
     O = w.shape[0]
-    xp = np.zeros((C, H + 2, W + 2), F32)
-    xp[:, 1:-1, 1:-1] = x
-    out = np.zeros((O, H * W), F32)
-    for ky in range(3):
-        for kx in range(3):
-            patch = np.ascontiguousarray(xp[:, ky:ky + H, kx:kx + W]).reshape(C, H * W)
-            out += w[:, :, ky, kx] @ patch
-    out += b[:, None]
+    xp = np.zeros((H + 2, W + 2, C), F32)
+    xp[1:-1, 1:-1] = x
+    w2t = np.ascontiguousarray(w.transpose(2, 3, 1, 0).reshape(9 * C, O))    # (ky, kx, c) x O
+    out = np.empty((H, W, O), F32)
+    R = max(1, min(H, (1 << 22) // max(1, 9 * C * W)))                       # ~16 MB im2col strip
+    for r0 in range(0, H, R):
+        r1 = min(H, r0 + R)
+        col = np.empty((r1 - r0, W, 9, C), F32)
+        for ky in range(3):
+            for kx in range(3):
+                col[:, :, ky * 3 + kx, :] = xp[ky + r0:ky + r1, kx:kx + W, :]
+        out[r0:r1] = (col.reshape(-1, 9 * C) @ w2t).reshape(r1 - r0, W, O)
+    out += b
     if relu:
         np.maximum(out, 0, out=out)
-    return out.reshape(O, H, W)
+    return out
+
+
+def conv3x3(x, w, b, relu):
+    """CHW wrapper of conv3x3_hwc (used by the tests)."""
+    return np.ascontiguousarray(conv3x3_hwc(np.ascontiguousarray(x.transpose(1, 2, 0)), w, b, relu).transpose(2, 0, 1))
 
 
 def conv1x1(x, w, b, relu=False):
@@ -70,38 +82,42 @@ def conv1x1(x, w, b, relu=False):
     return out.reshape((w2.shape[0],) + sh).astype(F32)
 
 
-def maxpool2(x):
-    """nn.MaxPool2d(2) floor mode (unet_parts.py:42)."""
-    C, H, W = x.shape
+def maxpool2_hwc(x):
+    """nn.MaxPool2d(2) floor mode (unet_parts.py:42), channel-last."""
+    H, W, C = x.shape
     h, w = H // 2, W // 2
-    v = x[:, :2 * h, :2 * w].reshape(C, h, 2, w, 2)
-    return v.max(axis=(2, 4))
+    v = x[:2 * h, :2 * w]
+    return np.maximum(np.maximum(v[0::2, 0::2], v[0::2, 1::2]), np.maximum(v[1::2, 0::2], v[1::2, 1::2]))
 
 
 # ----------------------------------------------------------------------------- SuperPoint
 def superpoint_dense(img, sd):
     """Encoder + heads -> (semi (65,h,w), desc (D,h,w) channel-L2-normalised).
     superpoint/models/superpoint_test.py:113-126, unet_parts.py:10-48."""
-    x = img.reshape(1, img.shape[-2], img.shape[-1]).astype(F32)
+    x = img.reshape(img.shape[-2], img.shape[-1], 1).astype(F32)       # channel-last internally
 
     def dconv(x, p):
         w, b = fold_bn(sd[p + ".0.weight"], sd[p + ".0.bias"], sd, p + ".1")
-        x = conv3x3(x, w, b, True)
+        x = conv3x3_hwc(x, w, b, True)
         w, b = fold_bn(sd[p + ".3.weight"], sd[p + ".3.bias"], sd, p + ".4")
-        return conv3x3(x, w, b, True)
+        return conv3x3_hwc(x, w, b, True)
+
+    def c1(x, w, b):                                                    # 1x1 conv, channel-last
+        return (x.reshape(-1, x.shape[-1]) @ np.ascontiguousarray(w.reshape(w.shape[0], -1).T) + b).reshape(
+            x.shape[0], x.shape[1], -1).astype(F32)
 
     x1 = dconv(x, "inc.conv.conv")
-    x2 = dconv(maxpool2(x1), "down1.mpconv.1.conv")
-    x3 = dconv(maxpool2(x2), "down2.mpconv.1.conv")
-    x4 = dconv(maxpool2(x3), "down3.mpconv.1.conv")
+    x2 = dconv(maxpool2_hwc(x1), "down1.mpconv.1.conv")
+    x3 = dconv(maxpool2_hwc(x2), "down2.mpconv.1.conv")
+    x4 = dconv(maxpool2_hwc(x3), "down3.mpconv.1.conv")
     w, b = fold_bn(sd["convPa.weight"], sd["convPa.bias"], sd, "bnPa")
-    cPa = conv3x3(x4, w, b, True)
+    cPa = conv3x3_hwc(x4, w, b, True)
     w, b = fold_bn(sd["convPb.weight"], sd["convPb.bias"], sd, "bnPb")
-    semi = conv1x1(cPa, w, b)
+    semi = np.ascontiguousarray(c1(cPa, w, b).transpose(2, 0, 1))
     w, b = fold_bn(sd["convDa.weight"], sd["convDa.bias"], sd, "bnDa")
-    cDa = conv3x3(x4, w, b, True)
+    cDa = conv3x3_hwc(x4, w, b, True)
     w, b = fold_bn(sd["convDb.weight"], sd["convDb.bias"], sd, "bnDb")
-    desc = conv1x1(cDa, w, b)
+    desc = np.ascontiguousarray(c1(cDa, w, b).transpose(2, 0, 1))
     dn = np.sqrt((desc.astype(F32) ** 2).sum(0, dtype=F32))
     desc = desc / dn[None]                      # no eps (superpoint_test.py:125-126)
     return semi.astype(F32), desc.astype(F32)

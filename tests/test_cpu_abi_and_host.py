@@ -1,0 +1,132 @@
+"""CPU-only tests: the C-ABI library builds/loads and exports every symbol of include/b200m.h, the
+host-side shim mirrors the reference's module interface, and the multi-rank gather works (gloo)."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, real_superpoint_weights
+
+
+def test_library_exports_every_declared_symbol():
+    from image_matching_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        lib.build()
+    L = lib.load()
+    header = open(os.path.join(ROOT, "include", "b200m.h")).read()
+    declared = set(re.findall(r"\b(b200m_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b200m_version() >= 100
+    # error path without a GPU: create must fail loudly with a message, not crash
+    if not torch.cuda.is_available():
+        import ctypes as C
+        cfg = lib.Config()
+        cfg.descriptor_dim = 128
+        cfg.nms_radius = 4
+        cfg.n_kenc = 1
+        cfg.kenc[0] = 32
+        hp = C.c_void_p()
+        rc = L.b200m_create(C.byref(cfg), 0, C.byref(hp))
+        assert rc != 0 and len(lib.last_error()) > 0
+    # invalid configuration is rejected before touching the device
+    import ctypes as C
+    bad = lib.Config()
+    bad.descriptor_dim = 100
+    hp = C.c_void_p()
+    assert L.b200m_create(C.byref(bad), 0, C.byref(hp)) == -1
+    assert "descriptor_dim" in lib.last_error()
+
+
+def test_only_sm100a_code_in_library():
+    from image_matching_b200 import lib
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_shim_mirrors_reference_interface():
+    from image_matching_b200 import Matching, SuperPoint, SuperGlue, synth
+    assert SuperPoint.default_config == {"descriptor_dim": 256, "nms_radius": 4, "keypoint_threshold": 0.005,
+                                         "max_keypoints": -1, "remove_borders": 4}
+    assert SuperGlue.default_config["GNN_layers"] == ["self", "cross"] * 9
+    assert SuperGlue.default_config["sinkhorn_iterations"] == 100
+    m = Matching({"superpoint": {"weights": None, "descriptor_dim": 128},
+                  "superglue": {"weights": "", "descriptor_dim": 128, "keypoint_encoder": [32, 64, 128]}}).eval()
+    # the reference's trained checkpoint keys load unchanged (84 tensors), as do the 332 SuperGlue keys
+    real = real_superpoint_weights()
+    assert set(m.superpoint.state_dict()) == set(real)
+    r = m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in real.items()})
+    assert not r.missing_keys and not r.unexpected_keys
+    sg = synth.superglue_weights(0, 128)
+    assert set(m.superglue.state_dict()) == set(sg) and len(sg) == 332
+    assert m.superpoint.config["max_keypoints"] == -1 and m.superglue.config["match_threshold"] == 0.2
+    with pytest.raises(KeyError):       # reference: self.config['weights'] has no default (superpoint_test.py:87)
+        SuperPoint({})
+    # no CPU fallback: the product path must fail loudly off-GPU
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m({"image0": torch.zeros(1, 1, 32, 32), "image1": torch.zeros(1, 1, 32, 32)})
+    # zero-keypoint early-out needs no device (superglue_test.py:235-242)
+    out = m.superglue({"keypoints0": torch.zeros(1, 0, 2), "keypoints1": torch.zeros(1, 5, 2)})
+    assert out["matches0"].dtype == torch.int32 and out["matches1"].shape == (1, 5)
+    assert (out["matches1"] == -1).all()
+
+
+def test_product_path_does_not_import_oracle():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import image_matching_b200; "
+            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for fn in os.listdir(os.path.join(ROOT, "image_matching_b200")):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "image_matching_b200", fn)).read(), fn
+
+
+def test_synthetic_inputs_are_deterministic():
+    from image_matching_b200 import synth
+    a0, b0 = synth.make_pair(3, 64, 96)
+    a1, b1 = synth.make_pair(3, 64, 96)
+    assert np.array_equal(a0, a1) and np.array_equal(b0, b1)
+    assert a0.dtype == np.float32 and a0.min() >= 0 and a0.max() <= 1
+    w0, w1 = synth.superpoint_weights(0, 128), synth.superpoint_weights(0, 128)
+    assert all(np.array_equal(w0[k], w1[k]) for k in w0) and len(w0) == 84
+
+
+def test_shard_range_partitions():
+    from image_matching_b200.dist import shard_range
+    for n in (1, 7, 64, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, n_pairs, N):
+    import torch.distributed as dist
+    from image_matching_b200.dist import shard_range, gather_matches
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full_m = (torch.arange(n_pairs * N).reshape(n_pairs, N) % 97 - 1).to(torch.int64)
+    full_s = torch.arange(n_pairs * N, dtype=torch.float32).reshape(n_pairs, N) / 7
+    lo, hi = shard_range(n_pairs, rank, world)
+    m, s = gather_matches(full_m[lo:hi].clone(), full_s[lo:hi].clone(), n_pairs)
+    assert m.dtype == torch.int64 and torch.equal(m, full_m) and torch.equal(s, full_s)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pairs", [4, 5])
+def test_gather_matches_world2_gloo(n_pairs):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gather_worker, args=(2, port, n_pairs, 16), nprocs=2, join=True)

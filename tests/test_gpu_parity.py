@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+ (a) golden vectors produced by the unmodified reference (tests/golden/make_golden.py), and
+ (b) the numpy oracle on freshly seeded inputs.
+Tolerances: integer / index outputs exact given identical inputs; fp32 tensors within the
+budgets of SURVEY.md 8(d): semi/heat-level 1e-6..5e-4 (stated per assert), descriptors / S / Z 1e-3.
+End-to-end keypoint / match equality is ill-conditioned (adjacent score gaps ~6e-8), so it is
+asserted on order-canonical sets with the flip count printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_cfg, real_superpoint_weights, kp_set, match_pairs
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _matching(cfg, sp_sd, sg_sd):
+    from image_matching_b200 import Matching
+    c = {"superpoint": dict(cfg["superpoint"], weights=None), "superglue": dict(cfg["superglue"], weights="")}
+    m = Matching(c).eval()
+    m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sp_sd.items()})
+    m.superglue.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sg_sd.items()})
+    return m.to(DEV)
+
+
+def _case(name):
+    from image_matching_b200 import synth
+    if name == "small_stages":
+        return dict(g=load_golden(name), cfg=golden_cfg(max_kp=256), sp=synth.superpoint_weights(0, 128),
+                    sg=synth.superglue_weights(0, 128), H=120, W=160, seeds=[1])
+    if name == "d256_small":
+        return dict(g=load_golden(name), cfg=golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=200, iters=50),
+                    sp=synth.superpoint_weights(1, 256), sg=synth.superglue_weights(1, 256, (32, 64, 128, 256)),
+                    H=120, W=160, seeds=[3])
+    if name == "real_small_stages":
+        return dict(g=load_golden(name), cfg=golden_cfg(max_kp=300), sp=real_superpoint_weights(),
+                    sg=synth.superglue_weights(0, 128), H=160, W=224, seeds=[4])
+    if name == "ragged_hw":
+        return dict(g=load_golden(name), cfg=golden_cfg(max_kp=-1, iters=20), sp=synth.superpoint_weights(0, 128),
+                    sg=synth.superglue_weights(0, 128), H=123, W=165, seeds=[2])
+    if name == "c1_pair":
+        return dict(g=load_golden(name), cfg=golden_cfg(max_kp=1024), sp=synth.superpoint_weights(0, 128),
+                    sg=synth.superglue_weights(0, 128), H=480, W=640, seeds=[1, 2])
+    if name == "c1_real":
+        return dict(g=load_golden(name), cfg=golden_cfg(max_kp=1024), sp=real_superpoint_weights(),
+                    sg=synth.superglue_weights(0, 128), H=480, W=640, seeds=[1])
+    raise KeyError(name)
+
+
+STAGE_CASES = ["small_stages", "d256_small", "real_small_stages"]
+
+
+@pytest.fixture(scope="module", params=STAGE_CASES)
+def stage(request):
+    c = _case(request.param)
+    c["m"] = _matching(c["cfg"], c["sp"], c["sg"])
+    return c
+
+
+def test_library_loaded_and_native():
+    from image_matching_b200 import lib
+    L = lib.load()
+    assert L.b200m_version() >= 100
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_stage_dense(stage):
+    from image_matching_b200 import synth, stages
+    g = stage["g"]
+    a, b = synth.make_pair_batch(stage["seeds"], stage["H"], stage["W"])
+    for side, img in (("0", a), ("1", b)):
+        semi, desc = stages.superpoint_dense(stage["m"], _t(img))
+        ds = np.abs(semi[0].cpu().numpy() - g["semi_" + side]).max()
+        dd = np.abs(desc[0].cpu().numpy() - g["desc_" + side]).max()
+        print(f"dense side{side}: max|semi diff|={ds:.3e} max|desc diff|={dd:.3e}")
+        assert ds < 5e-4      # fp32 accumulate-order differences on |semi| ~ 10
+        assert dd < 1e-4
+
+
+def test_stage_detector_post(stage):
+    from image_matching_b200 import stages
+    g, cfg = stage["g"], stage["cfg"]
+    for side in "01":
+        heat, nms, kp, sc, cnt = stages.detector_post(stage["m"], _t(g["semi_" + side][None]))
+        assert np.abs(heat[0].cpu().numpy() - g["heat_" + side]).max() < 1e-6     # softmax <= ~1 ulp
+        nm = nms[0].cpu().numpy()
+        # NMS is compare-only: the surviving positions must be identical
+        assert np.array_equal(nm > 0, g["nms_" + side] > 0)
+        assert np.abs(nm - g["nms_" + side]).max() < 1e-6
+        n = int(cnt[0])
+        ref_kp, ref_sc = g[f"keypoints{side}_0"], g[f"scores{side}_0"]
+        assert n == ref_kp.shape[0]
+        got_kp, got_sc = kp[0, :n].cpu().numpy(), sc[0, :n].cpu().numpy()
+        assert kp_set(got_kp) == kp_set(ref_kp)
+        assert np.abs(np.sort(got_sc) - np.sort(ref_sc)).max() < 1e-6
+        if cfg["superpoint"]["max_keypoints"] >= 0 and n == cfg["superpoint"]["max_keypoints"]:
+            assert np.all(np.diff(got_sc) <= 0)          # top-k: descending scores
+        flips = int((got_kp != ref_kp).any(1).sum())
+        print(f"detector side{side}: {n} keypoints, {flips} order flips vs reference")
+
+
+def test_stage_sample_descriptors(stage):
+    from image_matching_b200 import stages
+    g = stage["g"]
+    for side in "01":
+        kp = _t(g[f"keypoints{side}_0"][None])
+        de = stages.sample_descriptors(stage["m"], kp, None, _t(g["desc_" + side][None]))
+        d = np.abs(de[0].cpu().numpy() - g[f"descriptors{side}_0"]).max()
+        print(f"sample side{side}: max diff {d:.3e}")
+        assert d < 1e-5
+
+
+def test_stage_kenc(stage):
+    from image_matching_b200 import stages
+    g = stage["g"]
+    out = stages.keypoint_encode(stage["m"], _t(g["keypoints0_0"][None]), _t(g["scores0_0"][None]),
+                                 _t(g["descriptors0_0"][None]), stage["H"], stage["W"])
+    d = np.abs(out[0].cpu().numpy() - g["kenc0"]).max()
+    print(f"kenc: max diff {d:.3e}")
+    assert d < 1e-4
+
+
+def test_stage_gnn(stage):
+    from image_matching_b200 import stages
+    g = stage["g"]
+    k0, k1 = _t(g["kenc0"][None]), _t(g["kenc1"][None])
+    # layer 0 (self): delta = out - in
+    o0, _ = stages.gnn(stage["m"], k0, k0, 0, 1)
+    d = np.abs((o0 - k0)[0].cpu().numpy() - g["layer0_delta0"]).max()
+    print(f"gnn layer0 delta: max diff {d:.3e}")
+    assert d < 1e-4
+    # all 18 layers
+    o0, o1 = stages.gnn(stage["m"], k0, k1)
+    d0 = np.abs(o0[0].cpu().numpy() - g["gnn0"]).max()
+    d1 = np.abs(o1[0].cpu().numpy() - g["gnn1"]).max()
+    print(f"gnn 18 layers: max diff {d0:.3e} {d1:.3e}")
+    assert d0 < 1e-3 and d1 < 1e-3
+
+
+def test_stage_scores_and_ot(stage):
+    from image_matching_b200 import stages
+    g, cfg = stage["g"], stage["cfg"]
+    S = stages.score_matrix(stage["m"], _t(g["gnn0"][None]), _t(g["gnn1"][None]))
+    d = np.abs(S[0].cpu().numpy() - g["S"]).max()
+    print(f"S: max diff {d:.3e}")
+    assert d < 1e-3
+    Z = stages.sinkhorn(stage["m"], _t(g["S"][None]))
+    dz = np.abs(Z[0].cpu().numpy() - g["Z"]).max()
+    print(f"Z: max diff {dz:.3e}")
+    assert dz < 1e-3
+    m0, m1, s0, s1 = stages.match_select(stage["m"], _t(g["Z"][None]))
+    assert np.array_equal(m0.cpu().numpy(), g["matches0"])          # exact given identical Z
+    assert np.array_equal(m1.cpu().numpy(), g["matches1"])
+    assert np.abs(s0.cpu().numpy() - g["matching_scores0"]).max() < 1e-6
+    assert np.abs(s1.cpu().numpy() - g["matching_scores1"]).max() < 1e-6
+
+
+def test_superglue_given_reference_features(stage):
+    """SuperGlue.forward on the reference's own SuperPoint outputs: match indices must agree."""
+    g = stage["g"]
+    m = stage["m"]
+    data = {"image0": torch.empty(1, 1, stage["H"], stage["W"], device=DEV),
+            "image1": torch.empty(1, 1, stage["H"], stage["W"], device=DEV)}
+    for side in "01":
+        data["keypoints" + side] = _t(g[f"keypoints{side}_0"][None])
+        data["scores" + side] = _t(g[f"scores{side}_0"][None])
+        data["descriptors" + side] = _t(g[f"descriptors{side}_0"][None])
+    pred = m(data)
+    m0 = pred["matches0"].cpu().numpy()
+    assert pred["matches0"].dtype == torch.int64 and m0.shape == g["matches0"].shape
+    agree = (m0 == g["matches0"]).mean()
+    valid_ref = g["matches0"] > -1
+    print(f"superglue: matches0 agreement {agree:.4f}, {valid_ref.sum()} valid in reference")
+    assert agree >= 0.99
+    both = valid_ref & (m0 > -1)
+    assert np.abs(pred["matching_scores0"].cpu().numpy() - g["matching_scores0"])[both].max() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["ragged_hw", "c1_real", "c1_pair", "small_stages", "d256_small"])
+def test_end_to_end_vs_reference(name):
+    from image_matching_b200 import synth
+    c = _case(name)
+    g = c["g"]
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    a, b = synth.make_pair_batch(c["seeds"], c["H"], c["W"])
+    pred = m({"image0": _t(a), "image1": _t(b)})
+    assert isinstance(pred["keypoints0"], list) and isinstance(pred["scores0"], tuple)
+    assert pred["matches0"].dtype == torch.int64
+    for i in range(len(c["seeds"])):
+        for side in "01":
+            ref = kp_set(g[f"keypoints{side}_{i}"])
+            got = kp_set(pred["keypoints" + side][i].cpu().numpy())
+            print(f"{name}[{i}] side{side}: {len(ref)} ref keypoints, {len(ref ^ got)} differ")
+            assert len(ref & got) >= 0.99 * len(ref)
+            assert pred["descriptors" + side][i].shape == (c["cfg"]["superpoint"]["descriptor_dim"], len(got))
+        ref_pairs = match_pairs(g[f"keypoints0_{i}"], g[f"keypoints1_{i}"], g["matches0"][i])
+        got_pairs = match_pairs(pred["keypoints0"][i].cpu().numpy(), pred["keypoints1"][i].cpu().numpy(),
+                                pred["matches0"][i].cpu().numpy())
+        print(f"{name}[{i}]: {len(ref_pairs)} ref matches, {len(ref_pairs & got_pairs)} identical, "
+              f"{len(got_pairs - ref_pairs)} extra")
+        assert len(ref_pairs & got_pairs) >= 0.9 * len(ref_pairs)
+    if name == "ragged_hw":
+        # max_keypoints = -1 -> row-major (y, then x) order as torch.nonzero produces
+        k = pred["keypoints0"][0].cpu().numpy()
+        lin = k[:, 1] * 10000 + k[:, 0]
+        assert np.all(np.diff(lin) > 0)
+
+
+def test_against_oracle_fresh_seed():
+    """Same seeded inputs through the numpy oracle and the CUDA path (seed not in the goldens)."""
+    from image_matching_b200 import synth
+    from oracle import matching_oracle as O
+    cfg = golden_cfg(max_kp=128, iters=25)
+    sp, sg = synth.superpoint_weights(7, 128), synth.superglue_weights(7, 128)
+    a, b = synth.make_pair(11, 96, 136)
+    r = O.matching_forward(a, b, sp, sg, cfg)
+    m = _matching(cfg, sp, sg)
+    pred = m({"image0": _t(a[None, None]), "image1": _t(b[None, None])})
+    for side in "01":
+        ref, got = kp_set(r["keypoints" + side]), kp_set(pred["keypoints" + side][0].cpu().numpy())
+        assert len(ref & got) >= 0.98 * len(ref)
+    rp = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
+    gp = match_pairs(pred["keypoints0"][0].cpu().numpy(), pred["keypoints1"][0].cpu().numpy(),
+                     pred["matches0"][0].cpu().numpy())
+    assert len(rp & gp) >= 0.9 * len(rp)
+
+
+def test_batch_equals_single():
+    """B=3 batched forward is bit-identical per pair to three B=1 calls (reference property)."""
+    from image_matching_b200 import synth
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    a, b = synth.make_pair_batch([5, 6, 7], 120, 160)
+    out = m.forward_device(_t(a), _t(b))
+    out = {k: v.clone() for k, v in out.items()}
+    for i in range(3):
+        o1 = m.forward_device(_t(a[i:i + 1]), _t(b[i:i + 1]))
+        for k in ("keypoints0", "scores0", "descriptors1", "matches0", "matches1", "matching_scores0"):
+            assert torch.equal(out[k][i], o1[k][0]), k
+
+
+def test_ragged_batch_raises_like_reference():
+    from image_matching_b200 import synth
+    c = _case("ragged_hw")              # max_keypoints = -1 -> counts differ between pairs
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    a, b = synth.make_pair_batch([2, 9], 123, 165)
+    with pytest.raises(RuntimeError, match="stack expects each tensor to be equal size"):
+        m({"image0": _t(a), "image1": _t(b)})
+    # the device path itself handles ragged counts: per-pair results equal the B=1 results
+    out = m.forward_device(_t(a), _t(b))
+    cnt = out["counts"].cpu().numpy()
+    for i in range(2):
+        o1 = m.forward_device(_t(a[i:i + 1]), _t(b[i:i + 1]))
+        n = int(cnt[0, i])
+        assert int(o1["counts"][0, 0]) == n
+        assert torch.equal(out["matches0"][i, :n], o1["matches0"][0, :n])
+        assert (out["matches0"][i, n:] == -1).all()
+
+
+def test_empty_and_tiny_inputs():
+    from image_matching_b200 import synth
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    # zero keypoints on one side -> int32 all -1 (superglue_test.py:235-242)
+    kp1, sc1, de1 = synth.random_features(0, 1, 7, 128, 120, 160)
+    data = {"image0": torch.empty(1, 1, 120, 160, device=DEV), "image1": torch.empty(1, 1, 120, 160, device=DEV),
+            "keypoints0": torch.zeros(1, 0, 2, device=DEV), "scores0": torch.zeros(1, 0, device=DEV),
+            "descriptors0": torch.zeros(1, 128, 0, device=DEV),
+            "keypoints1": _t(kp1), "scores1": _t(sc1), "descriptors1": _t(de1)}
+    pred = m(data)
+    assert pred["matches0"].shape == (1, 0) and pred["matches0"].dtype == torch.int32
+    assert pred["matches1"].shape == (1, 7) and (pred["matches1"] == -1).all()
+    # a constant image has no keypoints above threshold after the border test at 16x16
+    tiny = torch.full((1, 1, 16, 16), 0.5, device=DEV)
+    pred = m({"image0": tiny, "image1": tiny})
+    assert pred["keypoints0"][0].shape[1] == 2
+    assert pred["matches0"].shape[1] == pred["keypoints0"][0].shape[0]
+
+
+def test_sinkhorn_properties_full_size():
+    """Size-independent properties at BASELINE's full size (1024x1024, 30 iterations):
+    after the last column update the column marginals of exp(Z - log(N+M)... ) are exact."""
+    from image_matching_b200 import stages, synth
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    rng = np.random.default_rng(0)
+    N = M = 1024
+    S = (rng.standard_normal((2, N, M)) * 3).astype(np.float32)
+    Z = stages.sinkhorn(m, _t(S), iters=30).double()
+    norm = -np.log(N + M)
+    # Z = log P + log(N+M); last half-iteration normalised the columns: sum_i P[i,j] = nu_j
+    colsum = torch.logsumexp(Z + norm, dim=1)
+    log_nu = torch.full((M + 1,), norm, dtype=torch.double, device=DEV)
+    log_nu[-1] = np.log(N) + norm
+    assert (colsum - log_nu[None]).abs().max() < 1e-4
+    # permutation equivariance: permuting rows of S permutes rows of Z
+    perm = torch.randperm(N, device=DEV)
+    Zp = stages.sinkhorn(m, _t(S)[:, perm], iters=30)
+    assert (Zp[:, :N] - Z[:, perm].float()[:, :N]).abs().max() < 1e-3
+
+
+def test_full_size_batch_runs_and_is_consistent():
+    """C2-shaped smoke at reduced batch: 4 pairs of 640x480, 1024 keypoints each; matches are mutual."""
+    from image_matching_b200 import synth
+    c = _case("c1_real")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    a, b = synth.make_pair_batch([21, 22, 23, 24], 480, 640)
+    out = m.forward_device(_t(a), _t(b))
+    cnt = out["counts"].cpu().numpy()
+    assert (cnt == 1024).all()
+    m0, m1 = out["matches0"].cpu().numpy(), out["matches1"].cpu().numpy()
+    for i in range(4):
+        v = m0[i] > -1
+        assert v.sum() > 50
+        assert np.array_equal(m1[i][m0[i][v]], np.nonzero(v)[0])      # mutual consistency
+        s = out["scores0"][i].cpu().numpy()
+        assert np.all(np.diff(s) <= 0)                                # sortedness of top-k
