@@ -35,6 +35,8 @@ struct HostTensor {
 struct ConvLayer {      // packed conv on C4-planar activations
   int cin = 0, cout = 0, cout_pad = 0, ks = 3;
   size_t w_off = 0, b_off = 0;   // float offsets into the device weight arena
+  int nb = 0;                    // tensor-core path: output channels per CTA tile (0 = no tc weights)
+  size_t tc_w_off = 0;
 };
 struct Linear {         // packed [N][K] row-major weight + bias
   int N = 0, K = 0;
@@ -82,6 +84,8 @@ struct b200m_handle {
   const char* err_where = nullptr;
   Profiler prof;
   std::vector<ProfRecord> prof_recs;
+  bool use_tc = true;            // tcgen05 3xTF32 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
+  int num_sms = 148;
 };
 
 namespace {
@@ -165,6 +169,11 @@ struct Packer {
     for (int o = 0; o < cout; ++o) host[L.b_off + o] = (float)b[o];
     return L;
   }
+  void pack_tc(ConvLayer& L, const std::vector<double>& w) {   // 3x3 layers with cin % 16 == 0
+    L.nb = L.cout_pad >= 128 ? 128 : 64;
+    L.tc_w_off = alloc(tc_conv_weight_floats(L.cin, L.cout_pad, L.nb));
+    tc_conv_pack_weights(w.data(), L.cout, L.cin, L.cout_pad, L.nb, host.data() + L.tc_w_off);
+  }
   Linear pack_linear(const std::vector<double>& w, const std::vector<double>& b, int N, int K, int Kpad,
                      const int* row_perm = nullptr, const int* col_perm = nullptr) {
     Linear L;
@@ -203,6 +212,7 @@ int pack_superpoint(b200m_handle* h, Packer& P) {
   auto conv3 = [&](const std::string& conv, const std::string& bn, int cin, int cout, ConvLayer& L) -> bool {
     if (!P.folded(sp + conv, sp + bn, cout, cin * 9, w, b, {cout, cin, 3, 3})) return false;
     L = P.pack_conv(w, b, cout, cin, 3);
+    P.pack_tc(L, w);
     return true;
   };
   bool ok = conv3("inc.conv.conv.3", "inc.conv.conv.4", 64, 64, h->c1b) &&
@@ -221,6 +231,7 @@ int pack_superpoint(b200m_handle* h, Packer& P) {
     wa.insert(wa.end(), wd.begin(), wd.end());
     ba.insert(ba.end(), bd.begin(), bd.end());
     h->heads = P.pack_conv(wa, ba, 512, 128, 3);
+    P.pack_tc(h->heads, wa);
   }
   if (!P.folded(sp + "convPb", sp + "bnPb", 65, 256, w, b, {65, 256, 1, 1}))
     return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
@@ -329,7 +340,7 @@ SpDims sp_dims(const b200m_handle* h, int H, int W) {
 }
 
 struct SpWs {
-  float *p0, *p1, *semi, *draw, *dn, *heat;
+  float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat;
   unsigned long long* keys;
   int *cand_counts, *overflow;
   size_t p0_img, p1_img, semi_img, draw_img, dn_img, heat_img;
@@ -344,6 +355,8 @@ bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w)
   w.heat_img = (size_t)d.H8 * d.W8;
   w.p0 = A.take<float>(w.p0_img * mb);
   w.p1 = A.take<float>(w.p1_img * mb);
+  w.p0_lo = h->use_tc ? A.take<float>(w.p0_img * mb) : nullptr;
+  w.p1_lo = h->use_tc ? A.take<float>(w.p1_img * mb) : nullptr;
   w.semi = A.take<float>(w.semi_img * mb);
   w.draw = A.take<float>(w.draw_img * mb);
   w.dn = A.take<float>(w.dn_img * mb);
@@ -364,19 +377,42 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
   launch_conv(ctx, p, L.ks, pool);
 }
 
+// One 3x3 layer on the tensor cores; falls back to the fp32 CUDA-core kernel if the launch is refused.
+// in/out are (hi, lo) plane pairs; out_lo == nullptr -> full-precision output in out_hi.
+void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
+                 float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool) {
+  TcConvParams p;
+  p.in_hi = in_hi; p.in_lo = in_lo; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
+  p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0;
+  p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = 1; p.pool = pool ? 1 : 0;
+  launch_tc_conv3x3(ctx, p, h->num_sms);
+}
+
 // encoder + heads for `n` images (n <= micro-batch): fills w.semi (C4, 32 groups) and w.draw (C4, dpad/4 groups)
 void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, const float* images, int n) {
-  launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, n, d.H, d.W);
-  // the C4 buffers are addressed per image with each layer's own channel-group count, so ping-pong
+  // the C4 buffers are addressed per image with each layer's own channel-group count, so the ping-pong
   // buffers are simply re-interpreted per layer
-  run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
-  run_conv(h, ctx, h->c2a, w.p1, 16, 0, w.p0, 16, n, d.H2, d.W2, true, false);
-  run_conv(h, ctx, h->c2b, w.p0, 16, 0, w.p1, 16, n, d.H2, d.W2, true, true);     // -> 64 x H3 x W3
-  run_conv(h, ctx, h->c3a, w.p1, 16, 0, w.p0, 32, n, d.H3, d.W3, true, false);    // 128 ch
-  run_conv(h, ctx, h->c3b, w.p0, 32, 0, w.p1, 32, n, d.H3, d.W3, true, true);     // -> 128 x hc x wc
-  run_conv(h, ctx, h->c4a, w.p1, 32, 0, w.p0, 32, n, d.hc, d.wc, true, false);
-  run_conv(h, ctx, h->c4b, w.p0, 32, 0, w.p1, 32, n, d.hc, d.wc, true, false);    // x4
-  run_conv(h, ctx, h->heads, w.p1, 32, 0, w.p0, 128, n, d.hc, d.wc, true, false); // cPa | cDa (512 ch)
+  if (h->use_tc) {
+    launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, w.p0_lo, n, d.H, d.W);
+    run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H, d.W, true);      // -> 64 x H2 x W2
+    run_conv_tc(h, ctx, h->c2a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.H2, d.W2, false);
+    run_conv_tc(h, ctx, h->c2b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H2, d.W2, true);    // -> 64 x H3 x W3
+    run_conv_tc(h, ctx, h->c3a, w.p1, w.p1_lo, w.p0, w.p0_lo, 32, n, d.H3, d.W3, false);   // 128 ch
+    run_conv_tc(h, ctx, h->c3b, w.p0, w.p0_lo, w.p1, w.p1_lo, 32, n, d.H3, d.W3, true);    // -> 128 x hc x wc
+    run_conv_tc(h, ctx, h->c4a, w.p1, w.p1_lo, w.p0, w.p0_lo, 32, n, d.hc, d.wc, false);
+    run_conv_tc(h, ctx, h->c4b, w.p0, w.p0_lo, w.p1, w.p1_lo, 32, n, d.hc, d.wc, false);   // x4
+    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, nullptr, 128, n, d.hc, d.wc, false); // cPa | cDa, full fp32
+  } else {
+    launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, nullptr, n, d.H, d.W);
+    run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
+    run_conv(h, ctx, h->c2a, w.p1, 16, 0, w.p0, 16, n, d.H2, d.W2, true, false);
+    run_conv(h, ctx, h->c2b, w.p0, 16, 0, w.p1, 16, n, d.H2, d.W2, true, true);     // -> 64 x H3 x W3
+    run_conv(h, ctx, h->c3a, w.p1, 16, 0, w.p0, 32, n, d.H3, d.W3, true, false);    // 128 ch
+    run_conv(h, ctx, h->c3b, w.p0, 32, 0, w.p1, 32, n, d.H3, d.W3, true, true);     // -> 128 x hc x wc
+    run_conv(h, ctx, h->c4a, w.p1, 32, 0, w.p0, 32, n, d.hc, d.wc, true, false);
+    run_conv(h, ctx, h->c4b, w.p0, 32, 0, w.p1, 32, n, d.hc, d.wc, true, false);    // x4
+    run_conv(h, ctx, h->heads, w.p1, 32, 0, w.p0, 128, n, d.hc, d.wc, true, false); // cPa | cDa (512 ch)
+  }
   run_conv(h, ctx, h->pb, w.p0, 128, 0, w.semi, 32, n, d.hc, d.wc, false, false); // semi (65 of 128 ch)
   run_conv(h, ctx, h->db, w.p0, 128, 64, w.draw, d.dpad / 4, n, d.hc, d.wc, false, false);
 }
@@ -593,6 +629,9 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   b200m_handle* h = new b200m_handle();
   h->cfg = *cfg;
   h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  const char* impl = getenv("B200M_CONV_IMPL");
+  h->use_tc = !(impl && strcmp(impl, "simt") == 0);
   *out = h;
   return B200M_OK;
 }
@@ -619,6 +658,36 @@ int b200m_pack(b200m_handle* h, void* stream) {
   if (!h) return fail(B200M_ERR_INVALID, "null handle");
   cudaSetDevice(h->device);
   return do_pack(h, (cudaStream_t)stream);
+}
+
+int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* in, float* out, int n, int H,
+                           int W, void* stream) {
+  if (!h || !h->packed_sp || !in || !out) return fail(B200M_ERR_INVALID, "bad argument / SuperPoint not packed");
+  const ConvLayer* Ls[8] = {&h->c1b, &h->c2a, &h->c2b, &h->c3a, &h->c3b, &h->c4a, &h->c4b, &h->heads};
+  const bool pools[8] = {true, false, true, false, true, false, false, false};
+  if (layer < 0 || layer >= 8) return fail(B200M_ERR_INVALID, "layer must be in [0,8)");
+  const ConvLayer& L = *Ls[layer];
+  const bool pool = pools[layer];
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const size_t in_f = (size_t)n * L.cin * H * W, out_f = (size_t)n * L.cout_pad * Ho * Wo;
+  float* buf = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMallocAsync(&buf, (3 * in_f + 2 * out_f) * sizeof(float), st) != cudaSuccess)
+    return fail(B200M_ERR_CUDA, "scratch allocation failed");
+  float *a = buf, *a_hi = a + in_f, *a_lo = a_hi + in_f, *o_hi = a_lo + in_f, *o_lo = o_hi + out_f;
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_nchw_to_c4(ctx, in, L.cin, a, L.cin / 4, n, H, W);
+  if (use_tc) {
+    launch_c4_split(ctx, a, a_hi, a_lo, in_f / 4);
+    const bool split_out = layer != 7;
+    run_conv_tc(h, ctx, L, a_hi, a_lo, o_hi, split_out ? o_lo : nullptr, L.cout_pad / 4, n, H, W, pool);
+    launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false, split_out ? o_lo : nullptr);
+  } else {
+    run_conv(h, ctx, L, a, L.cin / 4, 0, o_hi, L.cout_pad / 4, n, H, W, true, pool);
+    launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false);
+  }
+  cudaFreeAsync(buf, st);
+  return finish(h, ctx);
 }
 
 long long b200m_launch_count(const b200m_handle* h) { return h ? h->launches : 0; }

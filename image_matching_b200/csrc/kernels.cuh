@@ -25,11 +25,29 @@ struct ConvParams {
   int n, H, W;         // input spatial size (output = H,W or H/2,W/2 when pooled)
   int relu;
 };
+// out_lo != null: write tf32-exact hi / lo planes (3xTF32 operand split for the tensor-core convs)
 void launch_conv1_direct(LaunchCtx& ctx, const float* img, const float* w9x64, const float* bias,
-                         float* out, int n, int H, int W);
+                         float* out, float* out_lo, int n, int H, int W);
 void launch_conv(LaunchCtx& ctx, const ConvParams& p, int ksize, bool pool);
 void launch_c4_to_nchw(LaunchCtx& ctx, const float* in, int c4_total, int c4_off, int C, float* out,
-                       int n, int H, int W, bool l2_normalize);
+                       int n, int H, int W, bool l2_normalize, const float* in_lo = nullptr);
+// full-precision C4-planar -> tf32-exact hi / lo planes
+void launch_c4_split(LaunchCtx& ctx, const float* in, float* hi, float* lo, size_t n_float4);
+
+// ------------------------------------------------------------------ tensor-core 3x3 conv (tc_conv.cu)
+struct TcConvParams {
+  const float* in_hi; const float* in_lo;   // C4-planar activation planes, cin/4 groups per image
+  const float* wpk;                         // tc_conv_pack_weights layout
+  const float* bias;                        // [cout_pad]
+  float* out_hi; float* out_lo;             // out_lo == null: out_hi receives the full fp32 value
+  int out_c4_total, out_c4_off;
+  int cin, cout_pad, nb;                    // nb = output channels per CTA tile (64 or 128)
+  int n, H, W;
+  int relu, pool;
+};
+bool launch_tc_conv3x3(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
+size_t tc_conv_weight_floats(int cin, int cout_pad, int nb);
+void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst);
 void launch_nchw_to_c4(LaunchCtx& ctx, const float* in, int C, float* out, int c4_total, int n, int H, int W);
 void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* out,
                             int out_c4_total, int C, int n, int H, int W);

@@ -10,10 +10,14 @@ namespace b200m {
 // Block (32,8) = 32x8 pixels; every thread produces the 64 output channels of one pixel and stores
 // them as 16 float4 (one per channel group): a warp writes 512 contiguous bytes per group.
 // HBM-bound on the 64-channel fp32 output (256 B per pixel).
+// round-to-nearest onto the tf32 grid (10 explicit mantissa bits): unbiased, unlike truncation
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
 __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restrict__ img,
                                                            const float* __restrict__ w9x64,
                                                            const float* __restrict__ bias,
-                                                           float* __restrict__ out, int H, int W) {
+                                                           float* __restrict__ out,
+                                                           float* __restrict__ out_lo, int H, int W) {
   __shared__ float4 sw[9 * 16];
   __shared__ float4 sb[16];
   __shared__ float tile[10][34];
@@ -49,15 +53,23 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
       a.w = fmaf(v[t], wv.w, a.w);
     }
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-    o[(size_t)g * H * W] = a;
+    if (out_lo) {
+      float4 hi, lo;
+      hi.x = tf32_hi(a.x); hi.y = tf32_hi(a.y); hi.z = tf32_hi(a.z); hi.w = tf32_hi(a.w);
+      lo.x = tf32_hi(a.x - hi.x); lo.y = tf32_hi(a.y - hi.y); lo.z = tf32_hi(a.z - hi.z); lo.w = tf32_hi(a.w - hi.w);
+      o[(size_t)g * H * W] = hi;
+      (reinterpret_cast<float4*>(out_lo) + (size_t)n * 16 * H * W + (size_t)y * W + x)[(size_t)g * H * W] = lo;
+    } else {
+      o[(size_t)g * H * W] = a;
+    }
   }
 }
 
 void launch_conv1_direct(LaunchCtx& ctx, const float* img, const float* w9x64, const float* bias,
-                         float* out, int n, int H, int W) {
+                         float* out, float* out_lo, int n, int H, int W) {
   ProfScope prof__(ctx, "conv1_direct");
   dim3 grid(cdiv(W, 32), cdiv(H, 8), n), block(32, 8);
-  conv1_direct_kernel<<<grid, block, 0, ctx.stream>>>(img, w9x64, bias, out, H, W);
+  conv1_direct_kernel<<<grid, block, 0, ctx.stream>>>(img, w9x64, bias, out, out_lo, H, W);
   B200M_LAUNCH_CHECK(ctx, "conv1_direct");
 }
 
@@ -247,12 +259,13 @@ void launch_conv(LaunchCtx& ctx, const ConvParams& p, int ksize, bool pool) {
 
 // ------------------------------------------------------------------------------------------------
 // Layout conversions at the stage-API boundary.
-__global__ void c4_to_nchw_kernel(const float4* __restrict__ in, int c4_total, int c4_off, int C,
-                                  float* __restrict__ out, int HW, int normalize) {
+__global__ void c4_to_nchw_kernel(const float4* __restrict__ in, const float4* __restrict__ in_lo, int c4_total,
+                                  int c4_off, int C, float* __restrict__ out, int HW, int normalize) {
   const int n = blockIdx.y;
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= HW) return;
   const float4* src = in + ((size_t)n * c4_total + c4_off) * HW + px;
+  const float4* slo = in_lo ? in_lo + ((size_t)n * c4_total + c4_off) * HW + px : nullptr;
   float* dst = out + (size_t)n * C * HW + px;
   const int G = cdiv(C, 4);
   float nrm = 1.f;
@@ -268,6 +281,10 @@ __global__ void c4_to_nchw_kernel(const float4* __restrict__ in, int c4_total, i
   }
   for (int g = 0; g < G; ++g) {
     float4 v = src[(size_t)g * HW];
+    if (slo) {
+      float4 l = slo[(size_t)g * HW];
+      v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+    }
     float e[4] = {v.x, v.y, v.z, v.w};
     for (int j = 0; j < 4; ++j) {
       int c = g * 4 + j;
@@ -276,12 +293,30 @@ __global__ void c4_to_nchw_kernel(const float4* __restrict__ in, int c4_total, i
   }
 }
 
+__global__ void c4_split_kernel(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = in[i], h, l;
+  h.x = tf32_hi(a.x); h.y = tf32_hi(a.y); h.z = tf32_hi(a.z); h.w = tf32_hi(a.w);
+  l.x = tf32_hi(a.x - h.x); l.y = tf32_hi(a.y - h.y); l.z = tf32_hi(a.z - h.z); l.w = tf32_hi(a.w - h.w);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+void launch_c4_split(LaunchCtx& ctx, const float* in, float* hi, float* lo, size_t n_float4) {
+  ProfScope prof__(ctx, "c4_split");
+  c4_split_kernel<<<(unsigned)cdivz(n_float4, 256), 256, 0, ctx.stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n_float4);
+  B200M_LAUNCH_CHECK(ctx, "c4_split");
+}
+
 void launch_c4_to_nchw(LaunchCtx& ctx, const float* in, int c4_total, int c4_off, int C, float* out,
-                       int n, int H, int W, bool l2_normalize) {
+                       int n, int H, int W, bool l2_normalize, const float* in_lo) {
   ProfScope prof__(ctx, "c4_to_nchw");
   int HW = H * W;
   dim3 grid(cdiv(HW, 128), n);
-  c4_to_nchw_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const float4*>(in), c4_total, c4_off, C,
+  c4_to_nchw_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const float4*>(in),
+                                                   reinterpret_cast<const float4*>(in_lo), c4_total, c4_off, C,
                                                    out, HW, l2_normalize ? 1 : 0);
   B200M_LAUNCH_CHECK(ctx, "c4_to_nchw");
 }

@@ -1,0 +1,325 @@
+// SuperPoint 3x3 convolutions on the 5th-generation tensor cores (tcgen05), fp32-class accuracy via 3xTF32.
+// Reference: superpoint/models/unet_parts.py:10-48, superpoint/models/superpoint_test.py:113-126.
+//
+// Implicit GEMM, one persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   - per 16-channel K block ONE halo tile (18x18 pixels x 16 ch, hi and lo planes) is
+//                                fetched with cp.async.bulk.tensor (out-of-bounds = zero = the conv's zero padding);
+//                                the nine taps are NOT re-fetched: a tap is just a +16 B / +288 B shift of the UMMA
+//                                shared-memory descriptor's start address inside that tile (no-swizzle K-major
+//                                canonical layout == the C4-planar activation layout).  Weight slabs [tap][kblock]
+//                                arrive pre-laid-out with 1-D bulk copies.
+//   warp 1      MMA issuer     - one thread issues tcgen05.mma.kind::tf32, M=128 (16 rows x 8 px), N=NB, K=8;
+//                                two accumulators (left / right 8-px half of the 16x16 tile) share every weight slab;
+//                                D = Ahi*Bhi + (Ahi*Blo + Alo*Bhi)  (3xTF32: fp32-class accuracy, keeps the detector
+//                                logits stable enough for keypoint equality).  The tensor core truncates (RZ) when
+//                                it adds a K=8 dot product into the fp32 accumulator, so the error grows with the
+//                                number of accumulation steps: the small cross terms get their OWN accumulator
+//                                (1/3 of the steps hit the large one; measured 3x lower error) and the two are
+//                                summed with a rounded fp32 add in the epilogue.  NB=64: 2 x (2 px-halves x
+//                                {main, cross} x 64) = 512 TMEM columns, double-buffered; NB=128: single-buffered.
+//   warps 2..5  epilogue       - tcgen05.ld accumulators -> +bias, ReLU, optional 2x2 max-pool (warp shuffles),
+//                                split into tf32-exact hi/lo planes for the next layer, coalesced float4 stores.
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace b200m {
+
+using namespace tc;
+
+constexpr int kTcTile = 16;                       // output tile is 16 x 16 pixels
+constexpr int kTcHalo = kTcTile + 2;              // 18
+constexpr int kTcPlaneB = kTcHalo * kTcHalo * 16; // bytes of one channel-group plane of the halo tile (5184)
+constexpr int kTcKbGroups = 4;                    // channel groups (of 4) per K block -> 16 channels
+constexpr int kTcAPlane = kTcKbGroups * kTcPlaneB;   // 20736: hi (or lo) part of an A stage
+constexpr int kTcAStage = 2 * kTcAPlane;          // 41472
+constexpr int kTcNA = 3;                          // A stages
+constexpr int kTcNB = 4;                          // B (weight slab) ring slots
+constexpr uint32_t kTf32Mask = 0xFFFFE000u;
+
+template <int NB>
+struct TcConvSmem {
+  static constexpr int B_PLANE = kTcKbGroups * NB * 16;
+  static constexpr int B_SLOT = 2 * B_PLANE;
+  static constexpr int BAR_OFF = kTcNA * kTcAStage + kTcNB * B_SLOT;
+  static constexpr int N_BARS = 2 * kTcNA + 2 * kTcNB + 4;
+  static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
+  static constexpr size_t BYTES = 128 /*align slack*/ + BAR_OFF + N_BARS * 8 + 16;
+};
+
+template <int NB, bool POOL>
+__global__ void __launch_bounds__(192, 1)
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
+  using SM = TcConvSmem<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTcNA * kTcAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kTcNA;
+  uint64_t* b_full = a_empty + kTcNA;
+  uint64_t* b_empty = b_full + kTcNB;
+  uint64_t* acc_full = b_empty + kTcNB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = cdiv(p.W, kTcTile), tiles_y = cdiv(p.H, kTcTile);
+  const int ncb = p.cout_pad / NB;
+  const int nkb = p.cin / 16;
+  const int total = p.n * tiles_y * tiles_x * ncb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kTcNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& cb, int& x0, int& y0, int& img) {
+    cb = tile % ncb;
+    int t = tile / ncb;
+    x0 = (t % tiles_x) * kTcTile;
+    t /= tiles_x;
+    y0 = (t % tiles_y) * kTcTile;
+    img = t / tiles_y;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    auto issue_A = [&](int tile, int kb) {
+      int cb, x0, y0, img;
+      decode(tile, cb, x0, y0, img);
+      mbar_wait(&a_empty[sa], pa ^ 1);
+      mbar_expect_tx(&a_full[sa], kTcAStage);
+      uint8_t* dst = sA + sa * kTcAStage;
+      tma_load_4d(dst, &tm_hi, &a_full[sa], 4 * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
+      tma_load_4d(dst + kTcAPlane, &tm_lo, &a_full[sa], 4 * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
+      if (++sa == kTcNA) { sa = 0; pa ^= 1; }
+    };
+    if ((int)blockIdx.x < total) issue_A(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int cb = tile % ncb;
+      for (int kb = 0; kb < nkb; ++kb) {
+        // keep the activation halo one K block ahead of the weight slabs
+        if (kb + 1 < nkb) issue_A(tile, kb + 1);
+        else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
+        const float* wsrc = p.wpk + (size_t)(cb * nkb + kb) * 9 * (SM::B_SLOT / 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          mbar_expect_tx(&b_full[sb], SM::B_SLOT);
+          bulk_load(sB + sb * SM::B_SLOT, wsrc + (size_t)tap * (SM::B_SLOT / 4), SM::B_SLOT, &b_full[sb]);
+          if (++sb == kTcNB) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = instr_desc(2 /*tf32*/, 128, NB);
+    const uint64_t a_hi32 = (smem_desc_nosw(0, kTcPlaneB, kTcHalo * 16) >> 32) << 32;
+    const uint32_t a_lo16 = (uint32_t)((kTcPlaneB >> 4) << 16);
+    const uint64_t b_hi32 = (smem_desc_nosw(0, NB * 16, 128) >> 32) << 32;
+    const uint32_t b_lo16 = (uint32_t)(((NB * 16) >> 4) << 16);
+    int sa = 0, pa = 0, sb = 0, pb = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      const int buf = SM::ACC_BUFS == 2 ? (lt & 1) : 0;
+      const int aph = SM::ACC_BUFS == 2 ? ((lt >> 1) & 1) : (lt & 1);
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * (4 * NB);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + sa * kTcAStage);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(sB + sb * SM::B_SLOT);
+          const int ky = tap / 3, kx = tap - 3 * ky;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t b_off = b_base + ks * 2 * NB * 16;
+            const uint64_t bh = b_hi32 | (uint64_t)(b_lo16 | ((b_off >> 4) & 0x3FFF));
+            const uint64_t bl = b_hi32 | (uint64_t)(b_lo16 | (((b_off + SM::B_PLANE) >> 4) & 0x3FFF));
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t a_off = a_base + ks * 2 * kTcPlaneB + (ky * kTcHalo + kx + sub * 8) * 16;
+              const uint64_t ah = a_hi32 | (uint64_t)(a_lo16 | ((a_off >> 4) & 0x3FFF));
+              const uint64_t al = a_hi32 | (uint64_t)(a_lo16 | (((a_off + kTcAPlane) >> 4) & 0x3FFF));
+              const uint32_t d = d0 + sub * (2 * NB);      // main accumulator; cross accumulator at d + NB
+              const uint32_t acc = (kb | tap | ks) != 0;
+              mma_tf32(d, ah, bh, idesc, acc);
+              mma_tf32(d + NB, ah, bl, idesc, acc);
+              mma_tf32(d + NB, al, bh, idesc, 1);
+            }
+          }
+          tc_commit(&b_empty[sb]);
+          if (++sb == kTcNB) { sb = 0; pb ^= 1; }
+        }
+        tc_commit(&a_empty[sa]);
+        if (++sa == kTcNA) { sa = 0; pa ^= 1; }
+      }
+      tc_commit(&acc_full[buf]);
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)
+    const int w4 = warp & 3;
+    const int m = w4 * 32 + lane;
+    const int xs = m & 7, ys = m >> 3;
+    const int Ho = POOL ? p.H / 2 : p.H, Wo = POOL ? p.W / 2 : p.W;
+    const size_t oplane = (size_t)Ho * Wo;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      int cb, x0, y0, img;
+      decode(tile, cb, x0, y0, img);
+      const int buf = SM::ACC_BUFS == 2 ? (lt & 1) : 0;
+      const int aph = SM::ACC_BUFS == 2 ? ((lt >> 1) & 1) : (lt & 1);
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int x = x0 + sub * 8 + xs, y = y0 + ys;
+        int X, Y;
+        bool writer;
+        if (POOL) {
+          X = x >> 1; Y = y >> 1;
+          writer = !(xs & 1) && !(ys & 1) && (Y < Ho) && (X < Wo);
+        } else {
+          X = x; Y = y;
+          writer = (y < p.H) && (x < p.W);
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < NB / 32; ++ch) {
+          float v[32], vc[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(w4 * 32) << 16) + buf * (4 * NB) + sub * (2 * NB) + ch * 32;
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + NB, vc);
+          const int c0 = cb * NB + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = (v[j] + vc[j]) + __ldg(p.bias + c0 + j);
+            if (p.relu) t = fmaxf(t, 0.f);
+            if (POOL) {
+              t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+              t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+            }
+            v[j] = t;
+          }
+          if (writer) {
+            const size_t g0 = (size_t)img * p.out_c4_total + p.out_c4_off + (c0 >> 2);
+            float4* oh = reinterpret_cast<float4*>(p.out_hi) + g0 * oplane + (size_t)Y * Wo + X;
+            if (p.out_lo) {
+              float4* ol = reinterpret_cast<float4*>(p.out_lo) + g0 * oplane + (size_t)Y * Wo + X;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  h[j] = __uint_as_float((__float_as_uint(v[4 * g + j]) + 0x1000u) & kTf32Mask);
+                  l[j] = __uint_as_float((__float_as_uint(v[4 * g + j] - h[j]) + 0x1000u) & kTf32Mask);
+                }
+                oh[(size_t)g * oplane] = make_float4(h[0], h[1], h[2], h[3]);
+                ol[(size_t)g * oplane] = make_float4(l[0], l[1], l[2], l[3]);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                oh[(size_t)g * oplane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static bool make_act_map(CUtensorMap* m, const float* base, int n, int c4, int H, int W) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)4 * W, (cuuint64_t)H, (cuuint64_t)c4, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)c4 * H * W * 16};
+  cuuint32_t box[4] = {4 * kTcHalo, kTcHalo, kTcKbGroups, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int NB, bool POOL>
+static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
+  ProfScope prof__(ctx, "tc_conv3x3");
+  CUtensorMap tm_hi, tm_lo;
+  if (!make_act_map(&tm_hi, p.in_hi, p.n, p.cin / 4, p.H, p.W)) return false;
+  if (!make_act_map(&tm_lo, p.in_lo, p.n, p.cin / 4, p.H, p.W)) return false;
+  static bool attr_set = false;
+  auto kern = tc_conv3x3_kernel<NB, POOL>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcConvSmem<NB>::BYTES) != cudaSuccess)
+      return false;
+    attr_set = true;
+  }
+  const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, 192, TcConvSmem<NB>::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
+  B200M_LAUNCH_CHECK(ctx, "tc_conv3x3");
+  return true;
+}
+
+bool launch_tc_conv3x3(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
+  if (p.cin % 16 || p.cout_pad % p.nb || (p.nb != 64 && p.nb != 128)) return false;
+  if (p.nb == 64) return p.pool ? launch_tc_t<64, true>(ctx, p, num_sms) : launch_tc_t<64, false>(ctx, p, num_sms);
+  return p.pool ? launch_tc_t<128, true>(ctx, p, num_sms) : launch_tc_t<128, false>(ctx, p, num_sms);
+}
+
+size_t tc_conv_weight_floats(int cin, int cout_pad, int nb) {
+  return (size_t)(cout_pad / nb) * (cin / 16) * 9 * 2 * kTcKbGroups * nb * 4;
+}
+
+// Host-side weight packing: w[cout][cin][3][3] (BatchNorm already folded, fp32) ->
+// [cout_blk][kblock][tap][plane hi/lo][chunk of 4 ch][n][4], i.e. the exact shared-memory image of a B slab.
+void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst) {
+  const int ncb = cout_pad / nb, nkb = cin / 16;
+  for (int cb = 0; cb < ncb; ++cb)
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < kTcKbGroups; ++kc)
+          for (int n = 0; n < nb; ++n)
+            for (int j = 0; j < 4; ++j) {
+              const int o = cb * nb + n, ci = kb * 16 + kc * 4 + j;
+              float v = o < cout ? (float)w[((size_t)o * cin + ci) * 9 + tap] : 0.f;
+              uint32_t bits;                       // round-to-nearest tf32 split: v = hi + lo (+ O(2^-22 |v|))
+              memcpy(&bits, &v, 4);
+              bits = (bits + 0x1000u) & kTf32Mask;
+              float hi;
+              memcpy(&hi, &bits, 4);
+              float lo = v - hi;
+              memcpy(&bits, &lo, 4);
+              bits = (bits + 0x1000u) & kTf32Mask;
+              memcpy(&lo, &bits, 4);
+              size_t slab = ((size_t)(cb * nkb + kb) * 9 + tap) * 2;
+              size_t idx_hi = ((slab + 0) * kTcKbGroups + kc) * nb * 4 + (size_t)n * 4 + j;
+              size_t idx_lo = ((slab + 1) * kTcKbGroups + kc) * nb * 4 + (size_t)n * 4 + j;
+              dst[idx_hi] = hi;
+              dst[idx_lo] = lo;
+            }
+}
+
+}  // namespace b200m

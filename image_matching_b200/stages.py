@@ -136,3 +136,17 @@ def match_select(m: Matching, Z):
     _lib.check(L.b200m_match_select(e.handle, _ptr(Z), B, N, M, _ptr(m0), _ptr(m1), _ptr(s0), _ptr(s1), _ptr(ws),
                                     ws.numel(), _stream()), "b200m_match_select")
     return m0, m1, s0, s1
+
+
+def debug_conv_layer(m: Matching, layer: int, use_tc: bool, x: torch.Tensor):
+    """One packed 3x3 SuperPoint layer (0..7) with the tcgen05 (use_tc) or the fp32 CUDA-core kernel."""
+    x = x.contiguous().float()
+    L, e = _prep(m, x.device)
+    n, cin, H, W = x.shape
+    cout = [64, 64, 64, 128, 128, 128, 128, 512][layer]
+    pool = layer in (0, 2, 4)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.empty((n, cout, Ho, Wo), device=x.device)
+    _lib.check(L.b200m_debug_conv_layer(e.handle, layer, int(use_tc), _ptr(x), _ptr(out), n, H, W, _stream()),
+               "b200m_debug_conv_layer")
+    return out

@@ -149,6 +149,12 @@ int b200m_matching_forward(b200m_handle* h, const float* image0, const float* im
                            int cap, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* Test hook: run ONE packed 3x3 encoder/head layer (0=inc.conv[3], 1..2=down1, 3..4=down2, 5..6=down3, 7=convPa|convDa)
+ * on `in` (n,cin,H,W) -> `out` (n,cout,H',W') with the tcgen05 3xTF32 kernel (use_tc=1) or the fp32 CUDA-core
+ * kernel (use_tc=0), so the two implementations can be compared layer by layer. */
+int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* in, float* out, int n, int H,
+                           int W, void* stream);
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long b200m_launch_count(const b200m_handle* h);
 

@@ -80,7 +80,9 @@ def test_stage_dense(stage):
         ds = np.abs(semi[0].cpu().numpy() - g["semi_" + side]).max()
         dd = np.abs(desc[0].cpu().numpy() - g["desc_" + side]).max()
         print(f"dense side{side}: max|semi diff|={ds:.3e} max|desc diff|={dd:.3e}")
-        assert ds < 5e-4      # fp32 accumulate-order differences on |semi| ~ 10
+        scale = float(np.abs(g["semi_" + side]).max())
+        print(f"   |semi|max = {scale:.2f}, relative {ds / scale:.2e}")
+        assert ds < 5e-5 * scale   # fp32-class (3xTF32 tensor-core accumulate); plain TF32 would be ~1e-3 * scale
         assert dd < 1e-4
 
 

@@ -1,0 +1,64 @@
+"""GPU: the tcgen05 3xTF32 implicit-GEMM convolution against (a) the fp32 CUDA-core kernel of the same
+library and (b) a plain PyTorch fp32 conv2d of the same folded layer, layer by layer."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CIN = [64, 64, 64, 64, 128, 128, 128, 128]
+NAMES = [("inc.conv.conv.3", "inc.conv.conv.4"), ("down1.mpconv.1.conv.0", "down1.mpconv.1.conv.1"),
+         ("down1.mpconv.1.conv.3", "down1.mpconv.1.conv.4"), ("down2.mpconv.1.conv.0", "down2.mpconv.1.conv.1"),
+         ("down2.mpconv.1.conv.3", "down2.mpconv.1.conv.4"), ("down3.mpconv.1.conv.0", "down3.mpconv.1.conv.1"),
+         ("down3.mpconv.1.conv.3", "down3.mpconv.1.conv.4")]
+
+
+@pytest.fixture(scope="module")
+def model():
+    from image_matching_b200 import Matching, synth
+    cfg = golden_cfg(max_kp=128)
+    sp, sg = synth.superpoint_weights(3, 128), synth.superglue_weights(3, 128)
+    m = Matching({"superpoint": dict(cfg["superpoint"], weights=None),
+                  "superglue": dict(cfg["superglue"], weights="")}).eval()
+    m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sp.items()})
+    m.superglue.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sg.items()})
+    return m.to(DEV), sp
+
+
+def _torch_ref(sp, layer, x):
+    from oracle.matching_oracle import fold_bn
+    if layer < 7:
+        conv, bn = NAMES[layer]
+        w, b = fold_bn(sp[conv + ".weight"], sp[conv + ".bias"], sp, bn)
+    else:
+        wa, ba = fold_bn(sp["convPa.weight"], sp["convPa.bias"], sp, "bnPa")
+        wd, bd = fold_bn(sp["convDa.weight"], sp["convDa.bias"], sp, "bnDa")
+        w, b = np.concatenate([wa, wd]), np.concatenate([ba, bd])
+    y = torch.relu(torch.nn.functional.conv2d(x.double(), torch.from_numpy(w).to(DEV).double(),
+                                              torch.from_numpy(b).to(DEV).double(), padding=1))
+    if layer in (0, 2, 4):
+        y = torch.nn.functional.max_pool2d(y, 2)
+    return y
+
+
+@pytest.mark.parametrize("layer", range(8))
+@pytest.mark.parametrize("shape", [(2, 48, 64), (1, 37, 53), (3, 16, 16)])
+def test_tc_conv_matches_fp32(model, layer, shape):
+    from image_matching_b200 import stages
+    m, sp = model
+    n, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(100 * layer + H)
+    x = torch.relu(torch.randn((n, CIN[layer], H, W), device=DEV, generator=g)) * 3.0
+    ref = _torch_ref(sp, layer, x)
+    simt = stages.debug_conv_layer(m, layer, False, x)
+    tc = stages.debug_conv_layer(m, layer, True, x)
+    scale = float(ref.abs().max())
+    e_simt = float((simt.double() - ref).abs().max()) / scale
+    e_tc = float((tc.double() - ref).abs().max()) / scale
+    bias = float((tc.double() - ref).mean()) / scale
+    print(f"layer {layer} {shape}: rel err simt {e_simt:.2e}  tc(3xTF32) {e_tc:.2e} (mean signed {bias:+.2e})")
+    assert e_simt < 2e-6
+    assert e_tc < 6e-6          # fp32-class: 3xTF32 keeps ~21 mantissa bits per product (plain TF32: ~5e-4)
