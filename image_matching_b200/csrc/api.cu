@@ -85,6 +85,7 @@ struct b200m_handle {
   Profiler prof;
   std::vector<ProfRecord> prof_recs;
   bool use_tc = true;            // tcgen05 3xTF32 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
+  bool use_tc_attn = true;       // tcgen05 flash attention (B200M_ATTN_IMPL=simt selects the fp32 CUDA-core kernel)
   int num_sms = 148;
 };
 
@@ -466,7 +467,7 @@ size_t sp_ws_bytes(const b200m_handle* h, int n_images, int H, int W) {
 struct SgWs {
   int Np, ldS, ld_uv;
   size_t rows;           // 2 * B * Np
-  float *X, *QKV, *MSG, *HID, *IN4, *S, *u, *v, *max0;
+  float *X, *QKV, *QKV_lo, *VT, *VT_lo, *MSG, *HID, *IN4, *S, *u, *v, *max0;
   int *idx0, *idx1;
 };
 bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
@@ -477,6 +478,9 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
   w.ld_uv = round_up(std::max(N, M) + 1, 4);
   w.X = A.take<float>(w.rows * 2 * D);
   w.QKV = A.take<float>(w.rows * 3 * D);
+  w.QKV_lo = h->use_tc_attn ? A.take<float>(w.rows * 3 * D) : nullptr;
+  w.VT = h->use_tc_attn ? A.take<float>(w.rows * D) : nullptr;
+  w.VT_lo = h->use_tc_attn ? A.take<float>(w.rows * D) : nullptr;
   w.MSG = A.take<float>(w.rows * D);
   w.HID = A.take<float>(w.rows * 2 * D);
   w.IN4 = A.take<float>(w.rows * 4);
@@ -490,7 +494,8 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
 }
 
 void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A, int lda, float* C, int ldc,
-                size_t M, bool relu, bool accumulate) {
+                size_t M, bool relu, bool accumulate, float* C_lo = nullptr, float* VT = nullptr,
+                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1) {
   GemmParams p;
   p.A = A; p.lda = lda; p.strideA = 0;
   p.Bw = h->d_w + L.w_off; p.ldb = L.K; p.strideB = 0;
@@ -498,6 +503,8 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.bias = h->d_w + L.b_off;
   p.M = (int)M; p.N = L.N; p.K = L.K; p.batch = 1;
   p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
+  p.C_lo = C_lo;
+  p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np;
   launch_gemm(ctx, p);
 }
 
@@ -535,8 +542,16 @@ void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0
   const int D = h->cfg.descriptor_dim;
   for (int l = l_begin; l < l_end; ++l) {
     const b200m_handle::Gnn& G = h->gnn[l];
-    run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false);
-    launch_attention(ctx, w.QKV, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, h->cfg.gnn_cross[l] != 0);
+    const bool cross = h->cfg.gnn_cross[l] != 0;
+    bool done = false;
+    if (h->use_tc_attn) {
+      run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false, w.QKV_lo, w.VT, w.VT_lo, 2 * D, w.Np);
+      done = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, cross);
+    }
+    if (!done) {
+      run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false);
+      launch_attention(ctx, w.QKV, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, cross);
+    }
     run_linear(h, ctx, G.merge, w.MSG, D, w.X + D, 2 * D, w.rows, false, false);     // message -> X[:, D:2D]
     run_linear(h, ctx, G.mlp1, w.X, 2 * D, w.HID, 2 * D, w.rows, true, false);       // relu(bn(W1 [x;msg]))
     run_linear(h, ctx, G.mlp2, w.HID, 2 * D, w.X, 2 * D, w.rows, false, true);       // x += W2 hid
@@ -632,6 +647,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   const char* impl = getenv("B200M_CONV_IMPL");
   h->use_tc = !(impl && strcmp(impl, "simt") == 0);
+  impl = getenv("B200M_ATTN_IMPL");
+  h->use_tc_attn = !(impl && strcmp(impl, "simt") == 0);
   *out = h;
   return B200M_OK;
 }
@@ -687,6 +704,30 @@ int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* 
     launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false);
   }
   cudaFreeAsync(buf, st);
+  return finish(h, ctx);
+}
+
+int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, int Np, int n0, int n1, int cross,
+                          int use_tc, void* stream) {
+  if (!h || !qkv || !msg) return fail(B200M_ERR_INVALID, "null argument");
+  const int D = h->cfg.descriptor_dim;
+  const size_t rows = (size_t)2 * B * Np, n = rows * 3 * D;
+  LaunchCtx ctx = make_ctx(h, stream);
+  if (use_tc) {
+    float* planes = nullptr;
+    const size_t nv = rows * D;
+    if (cudaMallocAsync(&planes, (2 * n + 2 * nv) * sizeof(float), ctx.stream) != cudaSuccess)
+      return fail(B200M_ERR_CUDA, "scratch allocation failed");
+    float *vt_hi = planes + 2 * n, *vt_lo = vt_hi + nv;
+    launch_c4_split(ctx, qkv, planes, planes + n, n / 4);
+    launch_vt_from_qkv(ctx, planes, planes + n, vt_hi, vt_lo, 2 * B, Np, D);
+    bool ok = launch_tc_attention(ctx, planes, planes + n, vt_hi, vt_lo, msg, B, Np, D, kHeads, nullptr, nullptr, n0, n1,
+                                  cross != 0);
+    cudaFreeAsync(planes, ctx.stream);
+    if (!ok) return fail(B200M_ERR_CUDA, "tcgen05 attention launch refused");
+  } else {
+    launch_attention(ctx, qkv, msg, B, Np, D, kHeads, nullptr, nullptr, n0, n1, cross != 0);
+  }
   return finish(h, ctx);
 }
 

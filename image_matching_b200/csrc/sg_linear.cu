@@ -94,7 +94,20 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(GemmParams p) {
       float v = p.alpha * acc[i][j] + bz4[j];
       if (p.relu) v = fmaxf(v, 0.f);
       if (p.accumulate) v += crow[c];
-      crow[c] = v;
+      if (p.C_lo) {
+        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+        crow[c] = hi;
+        p.C_lo[(size_t)bz * p.strideC + (size_t)r * p.ldc + c] = lo;
+        if (p.VT && c >= p.vt_col0) {
+          const int blk = r / p.vt_np, rr = r - blk * p.vt_np;
+          const size_t o = ((size_t)blk * (p.N - p.vt_col0) + (c - p.vt_col0)) * p.vt_np + rr;
+          p.VT[o] = hi;
+          p.VT_lo[o] = lo;
+        }
+      } else {
+        crow[c] = v;
+      }
     }
   }
 }
@@ -158,6 +171,36 @@ void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float
   dim3 grid(cdiv(N, 32), cdiv(C, 32), B), block(32, 8);
   tokens_to_bcn_kernel<<<grid, block, 0, ctx.stream>>>(in, Np, ld, out, C, N);
   B200M_LAUNCH_CHECK(ctx, "tokens_to_bcn");
+}
+
+__global__ void vt_from_qkv_kernel(const float* __restrict__ qh, const float* __restrict__ ql, float* __restrict__ vh,
+                                   float* __restrict__ vl, int Np, int D) {
+  __shared__ float th[32][33], tl[32][33];
+  const int blk = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int nn = n0 + i, c = c0 + threadIdx.x;
+    bool ok = nn < Np && c < D;
+    size_t src = ((size_t)blk * Np + nn) * 3 * D + 2 * D + c;
+    th[i][threadIdx.x] = ok ? qh[src] : 0.f;
+    tl[i][threadIdx.x] = ok ? ql[src] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, nn = n0 + threadIdx.x;
+    if (c < D && nn < Np) {
+      size_t dst = ((size_t)blk * D + c) * Np + nn;
+      vh[dst] = th[threadIdx.x][i];
+      vl[dst] = tl[threadIdx.x][i];
+    }
+  }
+}
+
+void launch_vt_from_qkv(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, float* vt_hi, float* vt_lo,
+                        int blocks, int Np, int D) {
+  ProfScope prof__(ctx, "vt_from_qkv");
+  dim3 grid(cdiv(Np, 32), cdiv(D, 32), blocks), block(32, 8);
+  vt_from_qkv_kernel<<<grid, block, 0, ctx.stream>>>(qkv_hi, qkv_lo, vt_hi, vt_lo, Np, D);
+  B200M_LAUNCH_CHECK(ctx, "vt_from_qkv");
 }
 
 // normalize_keypoints (:63-70) fused with the cat([kpts^T, scores]) of KeypointEncoder.forward (:80-82):

@@ -139,6 +139,17 @@ __host__ __device__ inline uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// MN-major SWIZZLE_128B: 128 B (32 fp32) contiguous along MN per K row, 8 K rows per 1024 B group (SBO);
+// further 128 B MN atoms are LBO bytes apart.
+__host__ __device__ inline uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor (upper 32 bits of idescE): fp32 accumulate, K-major A and B.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ inline uint32_t instr_desc(int fmt, int M, int N) {

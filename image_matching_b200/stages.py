@@ -150,3 +150,14 @@ def debug_conv_layer(m: Matching, layer: int, use_tc: bool, x: torch.Tensor):
     _lib.check(L.b200m_debug_conv_layer(e.handle, layer, int(use_tc), _ptr(x), _ptr(out), n, H, W, _stream()),
                "b200m_debug_conv_layer")
     return out
+
+
+def debug_attention(m: Matching, qkv: torch.Tensor, B: int, Np: int, n0: int, n1: int, cross: bool, use_tc: bool):
+    """Attention on a fused q|k|v buffer (2*B*Np, 3D) with head-major columns -> (2*B*Np, D)."""
+    qkv = qkv.contiguous().float()
+    L, e = _prep(m, qkv.device)
+    D = qkv.shape[1] // 3
+    out = torch.zeros((qkv.shape[0], D), device=qkv.device)
+    _lib.check(L.b200m_debug_attention(e.handle, _ptr(qkv), _ptr(out), B, Np, n0, n1, int(cross), int(use_tc),
+                                       _stream()), "b200m_debug_attention")
+    return out

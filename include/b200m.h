@@ -155,6 +155,11 @@ int b200m_matching_forward(b200m_handle* h, const float* image0, const float* im
 int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* in, float* out, int n, int H,
                            int W, void* stream);
 
+/* Test hook: multi-head attention on a fused projection buffer qkv (2*B*Np rows x 3D, head-major q|k|v columns)
+ * -> msg (2*B*Np x D); n0/n1 valid tokens per side; tcgen05 kernel (use_tc=1) or fp32 CUDA-core kernel (0). */
+int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, int Np, int n0, int n1, int cross,
+                          int use_tc, void* stream);
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long b200m_launch_count(const b200m_handle* h);
 
