@@ -41,6 +41,7 @@ struct ConvLayer {      // packed conv on C4-planar activations
 struct Linear {         // packed [N][K] row-major weight + bias
   int N = 0, K = 0;
   size_t w_off = 0, b_off = 0;
+  size_t w_hi_off = 0, w_lo_off = 0;   // tf32-exact hi / lo planes of the same matrix (tensor-core path)
 };
 
 constexpr int kHeads = 4;
@@ -86,6 +87,7 @@ struct b200m_handle {
   std::vector<ProfRecord> prof_recs;
   bool use_tc = true;            // tcgen05 3xTF32 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
   bool use_tc_attn = true;       // tcgen05 flash attention (B200M_ATTN_IMPL=simt selects the fp32 CUDA-core kernel)
+  bool use_tc_gemm = true;       // tcgen05 linear layers (B200M_GEMM_IMPL=simt selects the fp32 CUDA-core GEMM)
   int num_sms = 148;
 };
 
@@ -188,6 +190,17 @@ struct Packer {
         host[L.w_off + (size_t)r * Kpad + c] = (float)w[(size_t)sr * K + scol];
       }
       host[L.b_off + r] = (float)b[sr];
+    }
+    L.w_hi_off = alloc((size_t)N * Kpad);
+    L.w_lo_off = alloc((size_t)N * Kpad);
+    for (size_t i = 0; i < (size_t)N * Kpad; ++i) {
+      float v = host[L.w_off + i], hi, lo;
+      uint32_t bits;
+      memcpy(&bits, &v, 4); bits = (bits + 0x1000u) & 0xFFFFE000u; memcpy(&hi, &bits, 4);
+      lo = v - hi;
+      memcpy(&bits, &lo, 4); bits = (bits + 0x1000u) & 0xFFFFE000u; memcpy(&lo, &bits, 4);
+      host[L.w_hi_off + i] = hi;
+      host[L.w_lo_off + i] = lo;
     }
     return L;
   }
@@ -505,6 +518,7 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
   p.C_lo = C_lo;
   p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np;
+  if (h->use_tc_gemm && launch_tc_gemm(ctx, p, h->d_w + L.w_hi_off, h->d_w + L.w_lo_off, h->num_sms)) return;
   launch_gemm(ctx, p);
 }
 
@@ -649,6 +663,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_tc = !(impl && strcmp(impl, "simt") == 0);
   impl = getenv("B200M_ATTN_IMPL");
   h->use_tc_attn = !(impl && strcmp(impl, "simt") == 0);
+  impl = getenv("B200M_GEMM_IMPL");
+  h->use_tc_gemm = !(impl && strcmp(impl, "simt") == 0);
   *out = h;
   return B200M_OK;
 }

@@ -84,6 +84,8 @@ struct GemmParams {
   float* VT = nullptr; float* VT_lo = nullptr; int vt_col0 = 0; int vt_np = 1;
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
+// tcgen05 3xTF32 version for weight GEMMs (w_hi / w_lo: [N][K] tf32-exact planes); returns false if declined
+bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms);
 // (B,C,N) channel-major <-> token-major [B][N][ld] (first C columns)
 void launch_bcn_to_tokens(LaunchCtx& ctx, const float* in, int B, int C, int N, float* out, int Np, int ld);
 void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float* out, int B, int C, int N);

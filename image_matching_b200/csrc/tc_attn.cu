@@ -61,9 +61,10 @@ struct TcAttnSmem {
   static constexpr int KV_STAGE = 4 * KV_PLANE;          // K hi, K lo, V hi, V lo
   static constexpr int P_PLANE = kTaQ * KT * 4;
   static constexpr int OFF_KV = 2 * Q_PLANE;
-  static constexpr int OFF_P = OFF_KV + 2 * KV_STAGE;
+  static constexpr int NKV = 3;                           // K/V ring depth (TMA latency ~ 2-3 tiles of work)
+  static constexpr int OFF_P = OFF_KV + NKV * KV_STAGE;
   static constexpr int OFF_BAR = OFF_P + 2 * P_PLANE;
-  static constexpr int N_BARS = 1 + 2 + 2 + 2 + 2 + 1 + 1 + 2 + 2;
+  static constexpr int N_BARS = 1 + 3 + 3 + 2 + 2 + 1 + 1 + 2 + 2;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;   // 1024: SWIZZLE_128B tiles need 1 KB alignment
   static constexpr int TMEM_COLS = (2 * KT + 2 * HD) <= 128 ? 128 : 256;
   static constexpr int NH = HD / 32;                      // 128-byte column halves per row
@@ -96,8 +97,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + 2;
-  uint64_t* s_full = kv_empty + 2;
+  uint64_t* kv_empty = kv_full + SM::NKV;
+  uint64_t* s_full = kv_empty + SM::NKV;
   uint64_t* s_empty = s_full + 2;
   uint64_t* p_full = s_empty + 2;
   uint64_t* p_empty = p_full + 1;
@@ -118,8 +119,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
+    for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
       mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
     }
@@ -148,7 +149,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       }
     }
     for (int j = 0; j < T; ++j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
+      const int st = j % SM::NKV, ph = (j / SM::NKV) & 1;
       mbar_wait(&kv_empty[st], ph ^ 1);
       mbar_expect_tx(&kv_full[st], SM::KV_STAGE);
       uint8_t* dst = sKV + st * SM::KV_STAGE;
@@ -164,15 +165,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         tma_load_2d(dst + 3 * SM::KV_PLANE + kc * SM::VT_CHUNK, &tm_vt_lo, &kv_full[st], j * KT + kc * 32, vt_row0);
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp)
     if (T > 0) {
       const uint32_t idesc_s = instr_desc(2, 128, KT);                    // A, B K-major
       const uint32_t idesc_o = instr_desc(2, 128, HD);                    // A = P, B = V^T, both K-major
       const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
       auto issue_S = [&](int j) {
         const int st = j & 1;
-        const uint32_t k_base = smem_u32(sKV + st * SM::KV_STAGE);
+        const uint32_t k_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE);
+        if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks) {
           // K-major SWIZZLE_128B: 8-channel step = +32 B inside the 128 B row, next 32 channels = next half
@@ -186,6 +188,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
           mma_tf32(tS + st * KT, ql, kh, idesc_s, 1);
         }
         tc_commit(&s_full[st]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -195,7 +199,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         const int st = j & 1, ph = (j >> 1) & 1;
         if (j + 1 < T) {
           const int sn = (j + 1) & 1, pn = ((j + 1) >> 1) & 1;
-          mbar_wait(&kv_full[sn], pn);
+          mbar_wait(&kv_full[(j + 1) % SM::NKV], ((j + 1) / SM::NKV) & 1);
           mbar_wait(&s_empty[sn], pn ^ 1);
           tc_fence_after();
           issue_S(j + 1);
@@ -203,7 +207,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         mbar_wait(p_full, j & 1);
         mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t v_base = smem_u32(sKV + st * SM::KV_STAGE + 2 * SM::KV_PLANE);
+        const uint32_t v_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE + 2 * SM::KV_PLANE);
+        if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < KT / 8; ++ks) {
           const uint64_t ph_ = smem_desc_nosw(p_base + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
@@ -216,9 +221,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
           mma_tf32(tO + st * HD, ph_, vl, idesc_o, 1);
           mma_tf32(tO + st * HD, pl_, vh, idesc_o, 1);
         }
-        tc_commit(&kv_empty[st]);
+        tc_commit(&kv_empty[j % SM::NKV]);
         tc_commit(p_empty);
         tc_commit(&o_full[st]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 2) {

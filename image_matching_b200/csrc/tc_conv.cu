@@ -33,15 +33,17 @@ constexpr int kTcKbGroups = 4;                    // channel groups (of 4) per K
 constexpr int kTcAPlane = kTcKbGroups * kTcPlaneB;   // 20736: hi (or lo) part of an A stage
 constexpr int kTcAStage = 2 * kTcAPlane;          // 41472
 constexpr int kTcNA = 3;                          // A stages
-constexpr int kTcNB = 4;                          // B (weight slab) ring slots
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;
 
 template <int NB>
 struct TcConvSmem {
   static constexpr int B_PLANE = kTcKbGroups * NB * 16;
   static constexpr int B_SLOT = 2 * B_PLANE;
-  static constexpr int BAR_OFF = kTcNA * kTcAStage + kTcNB * B_SLOT;
-  static constexpr int N_BARS = 2 * kTcNA + 2 * kTcNB + 4;
+  // weight-slab ring: a slab is consumed in 12 MMAs (~400-800 cycles) while an L2 fetch takes ~2-4k cycles, so the
+  // ring must hold ~96 KB of slabs in flight (measured: 4 slots left the tensor pipe 60% idle waiting on B)
+  static constexpr int NBS = 98304 / B_SLOT;
+  static constexpr int BAR_OFF = kTcNA * kTcAStage + NBS * B_SLOT;
+  static constexpr int N_BARS = 2 * kTcNA + 2 * NBS + 4;
   static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
   static constexpr size_t BYTES = 128 /*align slack*/ + BAR_OFF + N_BARS * 8 + 16;
 };
@@ -50,6 +52,7 @@ template <int NB, bool POOL>
 __global__ void __launch_bounds__(192, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
   using SM = TcConvSmem<NB>;
+  constexpr int kTcNB = SM::NBS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sA = smem;
@@ -121,8 +124,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
     const uint32_t idesc = instr_desc(2 /*tf32*/, 128, NB);
     const uint64_t a_hi32 = (smem_desc_nosw(0, kTcPlaneB, kTcHalo * 16) >> 32) << 32;
     const uint32_t a_lo16 = (uint32_t)((kTcPlaneB >> 4) << 16);
@@ -144,6 +147,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
           tc_fence_after();
           const uint32_t b_base = smem_u32(sB + sb * SM::B_SLOT);
           const int ky = tap / 3, kx = tap - 3 * ky;
+          if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t b_off = b_base + ks * 2 * NB * 16;
@@ -162,12 +166,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             }
           }
           tc_commit(&b_empty[sb]);
+          if (tap == 8) tc_commit(&a_empty[sa]);
+          if (tap == 8 && kb == nkb - 1) tc_commit(&acc_full[buf]);
+          }
+          __syncwarp();
           if (++sb == kTcNB) { sb = 0; pb ^= 1; }
         }
-        tc_commit(&a_empty[sa]);
         if (++sa == kTcNA) { sa = 0; pa ^= 1; }
       }
-      tc_commit(&acc_full[buf]);
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)

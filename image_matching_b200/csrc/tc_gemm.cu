@@ -1,0 +1,249 @@
+// SuperGlue per-token linear layers (Conv1d k=1) on tcgen05 tensor cores, 3xTF32 (fp32-class accuracy).
+// Reference: superglue/models/superglue_test.py:49-60 (MLP), :98-107 (proj / merge), :110-119 (propagation MLP),
+// :214-216 (final_proj).
+//
+//   C[M,N] (+)= A[M,K] * W[N,K]^T + bias   (optional ReLU, residual accumulate, tf32 hi/lo output planes, V^T copy)
+//
+// Persistent CTA per SM, 320 threads:
+//   warp 0      TMA producer  : per 32-column K block the raw fp32 A tile (128 rows x 128 B) and the pre-split
+//                               weight tiles W_hi / W_lo (NT rows x 128 B), all SWIZZLE_128B K-major.
+//   warps 2..5  splitter      : A is produced by other kernels in full fp32, so it is split HERE, in shared memory
+//                               (hi in place, lo into a second tile; element-wise, hence swizzle-agnostic) --
+//                               each A element feeds NT columns, so the split costs ~1% of the MMA time and no
+//                               producer kernel has to write doubled activation planes.
+//   warp 1      MMA issuer    : 4 K steps x (Ahi*Whi + Ahi*Wlo + Alo*Whi), M=128, N=NT=128; main and cross terms in
+//                               separate TMEM accumulators (the tensor core truncates on accumulate, see tc_conv.cu),
+//                               double-buffered (2 x 2 x 128 = 512 columns) so the epilogue of tile i overlaps the
+//                               MMAs of tile i+1.
+//   warps 6..9  epilogue      : tcgen05.ld -> alpha/bias/ReLU/residual -> stores (row-contiguous float4; the V^T
+//                               copy is written column-wise so a warp stores 128 contiguous bytes).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace b200m {
+
+using namespace tc;
+
+constexpr int kGemmNT = 128;                 // output columns per tile
+constexpr int kGemmStages = 3;
+constexpr int kGemmATile = 128 * 128;        // bytes: 128 rows x 32 fp32
+constexpr int kGemmBTile = kGemmNT * 128;
+constexpr int kGemmStage = 2 * kGemmATile + 2 * kGemmBTile;   // A hi(raw), A lo, W hi, W lo
+constexpr int kGemmBarOff = kGemmStages * kGemmStage;
+constexpr size_t kGemmSmem = 1024 + kGemmBarOff + (3 * kGemmStages + 4) * 8 + 16;
+
+__global__ void __launch_bounds__(320, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w_hi,
+               const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmBarOff);
+  uint64_t* full = bars;                       // TMA bytes landed
+  uint64_t* split = full + kGemmStages;        // A split into hi / lo
+  uint64_t* empty = split + kGemmStages;       // MMAs of the stage retired
+  uint64_t* acc_full = empty + kGemmStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = cdiv(p.M, 128), n_tiles = cdiv(p.N, kGemmNT);
+  const int total = m_tiles * n_tiles;
+  const int nkb = cdiv(p.K, 32);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&split[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * kGemmNT;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kGemmATile + 2 * kGemmBTile);
+        uint8_t* st = smem + s * kGemmStage;
+        tma_load_2d(st, &tm_a, &full[s], kb * 32, m0);
+        tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * 32, n0);
+        tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * 32, n0);
+        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = instr_desc(2, 128, kGemmNT);
+    int s = 0, ph = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * (2 * kGemmNT);   // main accumulator; cross terms at d + NT
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&split[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kGemmStage), a_lo = a_hi + kGemmATile;
+        const uint32_t w_hi = a_hi + 2 * kGemmATile, w_lo = w_hi + kGemmBTile;
+        if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ah = smem_desc_sw128(a_hi + ks * 32), al = smem_desc_sw128(a_lo + ks * 32);
+          const uint64_t wh = smem_desc_sw128(w_hi + ks * 32), wl = smem_desc_sw128(w_lo + ks * 32);
+          mma_tf32(d, ah, wh, idesc, (kb | ks) != 0);
+          mma_tf32(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
+          mma_tf32(d + kGemmNT, al, wh, idesc, 1);
+        }
+        tc_commit(&empty[s]);
+        if (kb == nkb - 1) tc_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // ------------------------------------------------------------------ splitter: raw fp32 A -> tf32 hi / lo
+    const int t = threadIdx.x - 64;    // 0..127
+    int s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(smem + s * kGemmStage);
+        float4* lo = reinterpret_cast<float4*>(smem + s * kGemmStage + kGemmATile);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 128 + t;
+          float4 a = hi[idx], h, l;
+          h.x = __uint_as_float((__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u);
+          h.y = __uint_as_float((__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u);
+          h.z = __uint_as_float((__float_as_uint(a.z) + 0x1000u) & 0xFFFFE000u);
+          h.w = __uint_as_float((__float_as_uint(a.w) + 0x1000u) & 0xFFFFE000u);
+          l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[s]);
+        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ epilogue (thread = output row)
+    const int w4 = warp & 3;
+    const int mrow = w4 * 32 + lane;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * kGemmNT;
+      const int buf = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const int r = m0 + mrow;
+      const bool rok = r < p.M;
+      float* crow = p.C + (size_t)r * p.ldc;
+      float* lrow = p.C_lo ? p.C_lo + (size_t)r * p.ldc : nullptr;
+      const int blk = p.VT ? r / p.vt_np : 0, rr = p.VT ? r - blk * p.vt_np : 0;
+#pragma unroll 1
+      for (int ch = 0; ch < kGemmNT / 32; ++ch) {
+        float v[32], vc[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(w4 * 32) << 16) + buf * (2 * kGemmNT) + ch * 32;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + kGemmNT, vc);
+        const int c0 = n0 + ch * 32;
+        if (c0 >= p.N) continue;           // uniform per warp
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = p.alpha * (v[j] + vc[j]) + (p.bias ? __ldg(p.bias + min(c0 + j, p.N - 1)) : 0.f);
+          if (p.relu) t = fmaxf(t, 0.f);
+          v[j] = t;
+        }
+        if (rok) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int c = c0 + 4 * g;
+            if (c >= p.N) break;
+            float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + c);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (lrow) {
+              float4 h, l;
+              h.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
+              h.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+              h.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
+              h.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
+              l.x = __uint_as_float((__float_as_uint(o.x - h.x) + 0x1000u) & 0xFFFFE000u);
+              l.y = __uint_as_float((__float_as_uint(o.y - h.y) + 0x1000u) & 0xFFFFE000u);
+              l.z = __uint_as_float((__float_as_uint(o.z - h.z) + 0x1000u) & 0xFFFFE000u);
+              l.w = __uint_as_float((__float_as_uint(o.w - h.w) + 0x1000u) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(crow + c) = h;
+              *reinterpret_cast<float4*>(lrow + c) = l;
+              v[4 * g] = h.x; v[4 * g + 1] = h.y; v[4 * g + 2] = h.z; v[4 * g + 3] = h.w;
+              if (p.VT && c >= p.vt_col0) {
+                const size_t o0 = ((size_t)blk * (p.N - p.vt_col0) + (c - p.vt_col0)) * p.vt_np + rr;
+                p.VT[o0] = h.x; p.VT[o0 + p.vt_np] = h.y; p.VT[o0 + 2 * (size_t)p.vt_np] = h.z;
+                p.VT[o0 + 3 * (size_t)p.vt_np] = h.w;
+                p.VT_lo[o0] = l.x; p.VT_lo[o0 + p.vt_np] = l.y; p.VT_lo[o0 + 2 * (size_t)p.vt_np] = l.z;
+                p.VT_lo[o0 + 3 * (size_t)p.vt_np] = l.w;
+              }
+            } else {
+              *reinterpret_cast<float4*>(crow + c) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static bool make_sw128_map2(CUtensorMap* m, const float* base, size_t rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// W_hi / W_lo: [N][K] row-major tf32-exact planes (split at pack time).  Requirements: batch == 1, K % 4 == 0,
+// lda % 4 == 0, N % 4 == 0 and 16-byte aligned bases; anything else is declined (caller uses the CUDA-core GEMM).
+bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms) {
+  if (p.batch != 1 || p.K % 4 || p.lda % 4 || p.ldc % 4 || p.N % 4 || p.K < 32 || p.M <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(w_hi)) & 15) return false;
+  ProfScope prof__(ctx, "tc_gemm");
+  CUtensorMap ma, mh, ml;
+  if (!make_sw128_map2(&ma, p.A, (size_t)p.M, p.K, p.lda, 128) || !make_sw128_map2(&mh, w_hi, (size_t)p.N, p.K, p.K, kGemmNT) ||
+      !make_sw128_map2(&ml, w_lo, (size_t)p.N, p.K, p.K, kGemmNT))
+    return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) != cudaSuccess)
+      return false;
+    attr_set = true;
+  }
+  const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT);
+  const int grid = total < num_sms ? total : num_sms;
+  tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);
+  B200M_LAUNCH_CHECK(ctx, "tc_gemm");
+  return true;
+}
+
+}  // namespace b200m

@@ -130,3 +130,30 @@ def test_gather_matches_world2_gloo(n_pairs):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_gather_worker, args=(2, port, n_pairs, 16), nprocs=2, join=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present")
+def test_reference_script_resolves_to_the_shim(tmp_path):
+    """superpoint_glue_test.py runs UNCHANGED up to its first matching(...) call, which on this GPU-less box
+    must be OUR module refusing to run on CPU (proves the import redirection + config/weights plumbing)."""
+    import subprocess
+    import cv2
+    from image_matching_b200 import synth
+    ds = tmp_path / "ds"
+    (ds / "source1").mkdir(parents=True)
+    (ds / "template1").mkdir()
+    a, b = synth.make_pair(1, 480, 640)
+    cv2.imwrite(str(ds / "source1" / "s.png"), (a * 255).astype(np.uint8))
+    cv2.imwrite(str(ds / "template1" / "t.png"), (b * 255).astype(np.uint8))
+    sg = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.superglue_weights(0, 128).items()}
+    torch.save({"epoch": 0, "net": sg}, tmp_path / "sg.pth")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "image_matching_b200.run_reference_script", "/root/reference",
+                        "superpoint_glue_test.py", "--img_dir", str(ds) + "/", "--resize_scale", "0.25",
+                        "--Result_dir", str(tmp_path / "out") + "/", "--superglue_weights", str(tmp_path / "sg.pth"),
+                        "--superpoint_weights", "superpoint/models/weights/superPointNet_allss_descriptor_128.pth.tar"],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    assert "Loaded SuperPoint model" in out and "Loaded SuperGlue model weights" in out, out[-2000:]
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in out, out[-2000:]

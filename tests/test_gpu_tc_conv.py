@@ -37,10 +37,15 @@ def _torch_ref(sp, layer, x):
         wa, ba = fold_bn(sp["convPa.weight"], sp["convPa.bias"], sp, "bnPa")
         wd, bd = fold_bn(sp["convDa.weight"], sp["convDa.bias"], sp, "bnDa")
         w, b = np.concatenate([wa, wd]), np.concatenate([ba, bd])
-    y = torch.relu(torch.nn.functional.conv2d(x.double(), torch.from_numpy(w).to(DEV).double(),
-                                              torch.from_numpy(b).to(DEV).double(), padding=1))
+    # float64 reference without cuDNN (its first fp64 call can stall for minutes on a cold box):
+    # unfold + one matmul
+    xd = x.double()
+    n, c, H, W = xd.shape
+    cols = torch.nn.functional.unfold(xd, 3, padding=1)                        # (n, c*9, H*W)
+    wd = torch.from_numpy(w).to(DEV).double().reshape(w.shape[0], -1)
+    y = torch.relu(wd @ cols + torch.from_numpy(b).to(DEV).double()[None, :, None]).reshape(n, -1, H, W)
     if layer in (0, 2, 4):
-        y = torch.nn.functional.max_pool2d(y, 2)
+        y = y[:, :, :H // 2 * 2, :W // 2 * 2].reshape(n, -1, H // 2, 2, W // 2, 2).amax((3, 5))
     return y
 
 
