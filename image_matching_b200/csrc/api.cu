@@ -356,6 +356,7 @@ SpDims sp_dims(const b200m_handle* h, int H, int W) {
 struct SpWs {
   float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat;
   unsigned long long* keys;
+  unsigned char* nms_scratch;
   int *cand_counts, *overflow;
   size_t p0_img, p1_img, semi_img, draw_img, dn_img, heat_img;
 };
@@ -376,6 +377,7 @@ bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w)
   w.dn = A.take<float>(w.dn_img * mb);
   w.heat = A.take<float>(w.heat_img * mb);
   w.keys = A.take<unsigned long long>((size_t)d.cand_cap * mb);
+  w.nms_scratch = A.take<unsigned char>(nms_scratch_bytes(mb, d.H8, d.W8));
   w.cand_counts = A.take<int>(mb + 1);
   w.overflow = w.cand_counts ? w.cand_counts + mb : nullptr;
   return A.ok;
@@ -456,7 +458,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_im
       launch_softmax_heat(ctx, w.semi, 32, w.heat, n, d.hc, d.wc);
       cudaMemsetAsync(w.cand_counts, 0, sizeof(int) * (mb + 1), ctx.stream);
       launch_nms_candidates(ctx, w.heat, nullptr, n, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
-                            h->cfg.remove_borders, w.keys, w.cand_counts, d.cand_cap, w.overflow);
+                            h->cfg.remove_borders, w.keys, w.cand_counts, d.cand_cap, w.overflow, w.nms_scratch);
       launch_select_keypoints(ctx, w.keys, w.cand_counts, d.cand_cap, n, d.W8, h->cfg.max_keypoints,
                               keypoints + (size_t)i0 * cap * 2, scores + (size_t)i0 * cap, counts + i0, cap);
       launch_c4_l2_normalize(ctx, w.draw, d.dpad / 4, 0, w.dn, D / 4, D, n, d.hc, d.wc);
@@ -831,6 +833,7 @@ int b200m_detector_post(b200m_handle* h, const float* semi, int n_images, int hc
   float* heat_ws = A.take<float>((size_t)n_images * d.H8 * d.W8);
   unsigned long long* keys = A.take<unsigned long long>((size_t)n_images * d.cand_cap);
   int* cc = A.take<int>(n_images + 1);
+  unsigned char* nms_scr = A.take<unsigned char>(nms_scratch_bytes(n_images, d.H8, d.W8));
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "detector_post workspace too small: need %zu bytes", A.off);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_nchw_to_c4(ctx, semi, 65, semi_c4, 32, n_images, hc, wc);
@@ -838,7 +841,7 @@ int b200m_detector_post(b200m_handle* h, const float* semi, int n_images, int hc
   launch_softmax_heat(ctx, semi_c4, 32, hp, n_images, hc, wc);
   cudaMemsetAsync(cc, 0, sizeof(int) * (n_images + 1), ctx.stream);
   launch_nms_candidates(ctx, hp, nms, n_images, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
-                        h->cfg.remove_borders, keypoints ? keys : nullptr, cc, d.cand_cap, cc + n_images);
+                        h->cfg.remove_borders, keypoints ? keys : nullptr, cc, d.cand_cap, cc + n_images, nms_scr);
   if (keypoints)
     launch_select_keypoints(ctx, keys, cc, d.cand_cap, n_images, d.W8, h->cfg.max_keypoints, keypoints, scores,
                             counts, cap);

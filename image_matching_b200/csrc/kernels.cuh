@@ -56,9 +56,10 @@ void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, in
 // semi C4-planar (>= 17 groups) -> heat (n, 8h, 8w)
 void launch_softmax_heat(LaunchCtx& ctx, const float* semi_c4, int c4_total, float* heat, int n, int hc, int wc);
 // heat -> optional dense nms map + candidate list (score, linear index) per image
+size_t nms_scratch_bytes(int n, int H8, int W8);
 void launch_nms_candidates(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8,
                            int radius, float thr, int border, unsigned long long* cand_keys,
-                           int* cand_counts, int cand_cap, int* overflow_flag);
+                           int* cand_counts, int cand_cap, int* overflow_flag, void* scratch);
 // candidate list -> keypoints (x,y), scores, counts; descending-score top-k or row-major order
 void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, const int* cand_counts,
                              int cand_cap, int n, int W8, int max_kp, float* keypoints, float* scores,

@@ -77,31 +77,28 @@ __global__ void __launch_bounds__(256) ot_col_kernel(OtParams p) {
   const float* S = p.S + (size_t)b * p.strideS;
   const bool active = j <= d.m;
   const bool bin_col = (j == d.m);
-  float mx = -INFINITY;
+  // one streaming pass with a running (max, sum) pair per column -- halves the L2 traffic of the column sweep;
+  // the partial pairs of the 8 warps are merged exactly like a flash-softmax split
+  float mx = -INFINITY, sum = 0.f;
   if (active)
     for (int i = w; i <= d.n; i += 8) {
-      float c = (bin_col || i == d.n) ? p.alpha : S[(size_t)i * p.ldS + j];
-      mx = fmaxf(mx, c + u[i]);
+      const float c = (bin_col || i == d.n) ? p.alpha : S[(size_t)i * p.ldS + j];
+      const float x = c + u[i];
+      if (x > mx) { sum = sum * expf(mx - x) + 1.f; mx = x; }
+      else sum += expf(x - mx);
     }
+  __shared__ float reds[8][33];
   red[w][lane] = mx;
-  __syncthreads();
-  mx = red[0][lane];
-#pragma unroll
-  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k][lane]);
-  __syncthreads();
-  float sum = 0.f;
-  if (active)
-    for (int i = w; i <= d.n; i += 8) {
-      float c = (bin_col || i == d.n) ? p.alpha : S[(size_t)i * p.ldS + j];
-      sum += expf((c + u[i]) - mx);
-    }
-  red[w][lane] = sum;
+  reds[w][lane] = sum;
   __syncthreads();
   if (w == 0 && active) {
-    sum = red[0][lane];
+    float M = red[0][lane];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) sum += red[k][lane];
-    p.v[(size_t)b * p.ld_uv + j] = (bin_col ? d.nu_bin : d.norm) - (logf(sum) + mx);
+    for (int k = 1; k < 8; ++k) M = fmaxf(M, red[k][lane]);
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][lane] == -INFINITY ? 0.f : reds[k][lane] * expf(red[k][lane] - M);
+    p.v[(size_t)b * p.ld_uv + j] = (bin_col ? d.nu_bin : d.norm) - (logf(tot) + M);
   }
 }
 

@@ -52,135 +52,124 @@ void launch_softmax_heat(LaunchCtx& ctx, const float* semi_c4, int c4_total, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// simple_nms (:7-22) + threshold (:135-138) + remove_borders (:25-30), tile-local and exact.
-// Five chained (2r+1)^2 max-pools give a 5r-pixel dependency halo; a block evaluates a 32x32 output
-// tile on a (32+10r)^2 working window held in shared memory (r <= 4 -> 72x72).  Pools are separable
-// (row pass then column pass); positions outside the image act as -inf padding (scores) / 0 (masks),
-// positions outside the window are never consumed by a valid output (shrinking-validity argument:
-// each pool consumes r pixels of margin, 5 pools consume the 5r halo).
+// simple_nms (:7-22) + threshold (:135-138) + remove_borders (:25-30), exact (compare-only).
+// The reference chains five (2r+1)^2 max-pools.  Evaluating all five inside one tile needs a 5r-pixel halo
+// (25x redundant work at 32x32 tiles, measured 12.8 ms / 128 images); instead each pool is its own pass over
+// the L2-resident maps with an r-pixel halo (1.56x), separable row / column max in shared memory:
+//   pass A  (MODE 0): m      = (s == P(s))
+//   pass B  (MODE 1): supp   = P(m) > 0 ;  ss = supp ? 0 : s
+//   pass C  (MODE 2): m     |= (ss == P(ss)) & ~supp          (B, C run twice)
+//   the last pass C also emits where(m, s, 0), the threshold / border test and the candidate list.
+// Out-of-image positions act as -inf padding exactly like torch's max_pool2d.
 constexpr int kNmsTile = 32;
 
-template <typename T>
-__device__ __forceinline__ void pool_pass(const T* __restrict__ src, T* __restrict__ tmp, T* __restrict__ dst,
-                                          int Wd, int r, T lowest) {
-  const int N = Wd * Wd;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    int y = i / Wd, x = i - y * Wd;
-    int lo = max(x - r, 0), hi = min(x + r, Wd - 1);
-    T m = lowest;
-    for (int k = lo; k <= hi; ++k) { T c = src[y * Wd + k]; m = c > m ? c : m; }
-    tmp[i] = m;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    int y = i / Wd, x = i - y * Wd;
-    int lo = max(y - r, 0), hi = min(y + r, Wd - 1);
-    T m = lowest;
-    for (int k = lo; k <= hi; ++k) { T c = tmp[k * Wd + x]; m = c > m ? c : m; }
-    dst[i] = m;
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ heat, float* __restrict__ nms_dense,
-                                                  int H8, int W8, int r, float thr, int border,
-                                                  unsigned long long* __restrict__ cand_keys,
-                                                  int* __restrict__ cand_counts, int cand_cap,
-                                                  int* __restrict__ overflow_flag) {
-  extern __shared__ unsigned char smraw[];
-  const int halo = 5 * r;
-  const int Wd = kNmsTile + 2 * halo;
-  const int N = Wd * Wd;
-  float* S = reinterpret_cast<float*>(smraw);   // scores (-inf outside the image)
-  float* A = S + N;                             // pooled / suppressed scores
-  float* T = A + N;                             // row-pass scratch
-  unsigned char* M = reinterpret_cast<unsigned char*>(T + N);   // max_mask
-  unsigned char* SP = M + N;                                    // supp_mask
-  unsigned char* TB = SP + N;                                   // byte scratch
-  unsigned char* IN = TB + N;                                   // inside-image flag
+template <int R, int MODE, bool LAST>
+__global__ void __launch_bounds__(256) nms_pass_kernel(const float* __restrict__ heat, float* __restrict__ ss,
+                                                       unsigned char* __restrict__ m, unsigned char* __restrict__ supp,
+                                                       float* __restrict__ nms_dense, int H8, int W8, float thr,
+                                                       int border, unsigned long long* __restrict__ cand_keys,
+                                                       int* __restrict__ cand_counts, int cand_cap,
+                                                       int* __restrict__ overflow_flag) {
+  constexpr int Wd = kNmsTile + 2 * R;
+  __shared__ float in[Wd][Wd + 1];
+  __shared__ float tmp[Wd][kNmsTile + 1];
   const int n = blockIdx.z;
-  const int x0 = blockIdx.x * kNmsTile - halo, y0 = blockIdx.y * kNmsTile - halo;
-  const float* hm = heat + (size_t)n * H8 * W8;
+  const size_t img = (size_t)n * H8 * W8;
+  const int x0 = blockIdx.x * kNmsTile - R, y0 = blockIdx.y * kNmsTile - R;
   const float NEG = -INFINITY;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    int y = i / Wd, x = i - y * Wd;
-    int gy = y0 + y, gx = x0 + x;
-    bool in = gy >= 0 && gy < H8 && gx >= 0 && gx < W8;
-    S[i] = in ? hm[(size_t)gy * W8 + gx] : NEG;
-    IN[i] = in;
+  // pooled input: scores (A), mask as 0/1 (B), suppressed scores (C)
+  for (int i = threadIdx.x; i < Wd * Wd; i += 256) {
+    const int y = i / Wd, x = i - y * Wd;
+    const int gy = y0 + y, gx = x0 + x;
+    float v = NEG;
+    if (gy >= 0 && gy < H8 && gx >= 0 && gx < W8) {
+      const size_t o = img + (size_t)gy * W8 + gx;
+      v = MODE == 0 ? heat[o] : (MODE == 1 ? (float)m[o] : ss[o]);
+    }
+    in[y][x] = v;
   }
   __syncthreads();
-  // max_mask = scores == max_pool(scores)
-  pool_pass<float>(S, T, A, Wd, r, NEG);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) M[i] = IN[i] && (S[i] == A[i]);
-  __syncthreads();
-  for (int it = 0; it < 2; ++it) {
-    // supp_mask = max_pool(max_mask) > 0
-    pool_pass<unsigned char>(M, TB, SP, Wd, r, (unsigned char)0);
-    // supp_scores = where(supp_mask, 0, scores)   (padding of the next pool stays -inf)
-    for (int i = threadIdx.x; i < N; i += blockDim.x) A[i] = IN[i] ? (SP[i] ? 0.f : S[i]) : NEG;
-    __syncthreads();
-    // new_max_mask = supp_scores == max_pool(supp_scores): row pass A -> T, column pass fused with the
-    // mask update (reads T and the thread's own A[i] only)
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      int y = i / Wd, x = i - y * Wd;
-      int lo = max(x - r, 0), hi = min(x + r, Wd - 1);
-      float m = NEG;
-      for (int k = lo; k <= hi; ++k) m = fmaxf(m, A[y * Wd + k]);
-      T[i] = m;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      int y = i / Wd, x = i - y * Wd;
-      int lo = max(y - r, 0), hi = min(y + r, Wd - 1);
-      float m = NEG;
-      for (int k = lo; k <= hi; ++k) m = fmaxf(m, T[k * Wd + x]);
-      // max_mask |= new_max_mask & ~supp_mask
-      if (IN[i] && !SP[i] && A[i] == m) M[i] = 1;
-    }
-    __syncthreads();
+  for (int i = threadIdx.x; i < Wd * kNmsTile; i += 256) {     // row pass
+    const int y = i / kNmsTile, x = i - y * kNmsTile;
+    float v = in[y][x];
+#pragma unroll
+    for (int d = 1; d <= 2 * R; ++d) v = fmaxf(v, in[y][x + d]);
+    tmp[y][x] = v;
   }
-  // where(max_mask, scores, 0) -> threshold -> border -> candidate list
-  for (int i = threadIdx.x; i < kNmsTile * kNmsTile; i += blockDim.x) {
-    int ty = i / kNmsTile, tx = i - ty * kNmsTile;
-    int gy = blockIdx.y * kNmsTile + ty, gx = blockIdx.x * kNmsTile + tx;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNmsTile * kNmsTile; i += 256) {   // column pass + combine
+    const int y = i / kNmsTile, x = i - y * kNmsTile;
+    const int gy = blockIdx.y * kNmsTile + y, gx = blockIdx.x * kNmsTile + x;
     if (gy >= H8 || gx >= W8) continue;
-    int w = (ty + halo) * Wd + tx + halo;
-    float sc = M[w] ? S[w] : 0.f;
-    if (nms_dense) nms_dense[(size_t)n * H8 * W8 + (size_t)gy * W8 + gx] = sc;
-    if (cand_keys && sc > thr && gy >= border && gy < H8 - border && gx >= border && gx < W8 - border) {
-      int slot = atomicAdd(&cand_counts[n], 1);
-      if (slot < cand_cap) {
-        unsigned int lin = (unsigned int)(gy * W8 + gx);
-        // descending sort key: larger score first, then smaller linear index first
-        cand_keys[(size_t)n * cand_cap + slot] =
-            ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+    float v = tmp[y][x];
+#pragma unroll
+    for (int d = 1; d <= 2 * R; ++d) v = fmaxf(v, tmp[y + d][x]);
+    const size_t o = img + (size_t)gy * W8 + gx;
+    const float c = in[y + R][x + R];          // the pooled map's own value at this pixel
+    if (MODE == 0) {
+      m[o] = (c == v);
+    } else if (MODE == 1) {
+      const bool sp = v > 0.f;
+      supp[o] = sp;
+      ss[o] = sp ? 0.f : heat[o];
+    } else {
+      bool mk = m[o] != 0;
+      if (!mk && !supp[o] && c == v) mk = true;
+      if (!LAST) {
+        m[o] = mk;
       } else {
-        *overflow_flag = 1;
+        const float sc = mk ? heat[o] : 0.f;
+        if (nms_dense) nms_dense[o] = sc;
+        if (cand_keys && sc > thr && gy >= border && gy < H8 - border && gx >= border && gx < W8 - border) {
+          const int slot = atomicAdd(&cand_counts[n], 1);
+          if (slot < cand_cap) {
+            const unsigned int lin = (unsigned int)(gy * W8 + gx);
+            // descending sort key: larger score first, then smaller linear index first
+            cand_keys[(size_t)n * cand_cap + slot] =
+                ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+          } else {
+            *overflow_flag = 1;
+          }
+        }
       }
     }
   }
 }
 
-static size_t nms_smem_bytes(int r) {
-  int Wd = kNmsTile + 10 * r;
-  return (size_t)Wd * Wd * (3 * sizeof(float) + 4);
+template <int R>
+static void launch_nms_r(LaunchCtx& ctx, const float* heat, float* ss, unsigned char* m, unsigned char* supp,
+                         float* nms_dense, int n, int H8, int W8, float thr, int border,
+                         unsigned long long* cand_keys, int* cand_counts, int cand_cap, int* overflow_flag) {
+  dim3 grid(cdiv(W8, kNmsTile), cdiv(H8, kNmsTile), n);
+#define B200M_NMS_PASS(MODE, LAST)                                                                               \
+  nms_pass_kernel<R, MODE, LAST><<<grid, 256, 0, ctx.stream>>>(heat, ss, m, supp, nms_dense, H8, W8, thr, border, \
+                                                               cand_keys, cand_counts, cand_cap, overflow_flag);  \
+  B200M_LAUNCH_CHECK(ctx, "nms_pass")
+  B200M_NMS_PASS(0, false);
+  B200M_NMS_PASS(1, false);
+  B200M_NMS_PASS(2, false);
+  B200M_NMS_PASS(1, false);
+  B200M_NMS_PASS(2, true);
+#undef B200M_NMS_PASS
 }
+
+size_t nms_scratch_bytes(int n, int H8, int W8) { return (size_t)n * H8 * W8 * 6 + 1024; }
 
 void launch_nms_candidates(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8,
                            int radius, float thr, int border, unsigned long long* cand_keys,
-                           int* cand_counts, int cand_cap, int* overflow_flag) {
+                           int* cand_counts, int cand_cap, int* overflow_flag, void* scratch) {
   ProfScope prof__(ctx, "nms_candidates");
-  static size_t attr_bytes = 0;
-  size_t bytes = nms_smem_bytes(radius);
-  if (bytes > attr_bytes) {
-    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    attr_bytes = bytes;
+  const size_t px = (size_t)n * H8 * W8;
+  float* ss = reinterpret_cast<float*>(scratch);
+  unsigned char* m = reinterpret_cast<unsigned char*>(ss + px);
+  unsigned char* supp = m + px;
+  switch (radius) {
+    case 0: launch_nms_r<0>(ctx, heat, ss, m, supp, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag); break;
+    case 1: launch_nms_r<1>(ctx, heat, ss, m, supp, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag); break;
+    case 2: launch_nms_r<2>(ctx, heat, ss, m, supp, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag); break;
+    case 3: launch_nms_r<3>(ctx, heat, ss, m, supp, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag); break;
+    default: launch_nms_r<4>(ctx, heat, ss, m, supp, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag); break;
   }
-  dim3 grid(cdiv(W8, kNmsTile), cdiv(H8, kNmsTile), n);
-  nms_kernel<<<grid, 256, bytes, ctx.stream>>>(heat, nms_dense, H8, W8, radius, thr, border, cand_keys,
-                                              cand_counts, cand_cap, overflow_flag);
-  B200M_LAUNCH_CHECK(ctx, "nms");
 }
 
 // ------------------------------------------------------------------------------------------------
