@@ -30,7 +30,10 @@ KENC = [32, 64, 128]
 SINKHORN = 30
 GF_PAIR_TOTAL = 135.43        # algorithmic GFLOP per pair (C1/C2/C4)
 GF_PAIR_QK = 9.664            # attention QK^T only
-GF_IMG_CONV_C4 = 51.79 - 0.354  # convs executed by the conv*_c4 kernels (everything but the Cin=1 stencil)
+# dram__bytes_read+write per tc_conv3x3 launch from profiles/r01_ncu_tc_conv.csv (mean of the 3 captured launches,
+# 16-image micro-batch); the kernel's algorithmic input+output is read/written exactly once
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 798.6e6
+GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers (tc_conv3x3): all but the Cin=1 stencil and the two 1x1 heads
 
 
 def make_cfg():
@@ -284,17 +287,22 @@ def run_b200(args):
         e2e = total_pairs * args.steps / (e2e_ms / 1e3)
         dom = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
         roof = None
-        if "conv3x3_c4" in prof:
-            conv_ms = prof["conv3x3_c4"]["ms_per_step"] + prof.get("conv1x1_c4", {"ms_per_step": 0})["ms_per_step"]
-            n_launch = prof["conv3x3_c4"]["launches_per_step"] + prof.get("conv1x1_c4", {"launches_per_step": 0})["launches_per_step"]
-            flops_step = GF_IMG_CONV_C4 * 1e9 * 2 * B
+        ck = "tc_conv3x3" if "tc_conv3x3" in prof else ("conv3x3_c4" if "conv3x3_c4" in prof else None)
+        if ck:
+            conv_ms = prof[ck]["ms_per_step"]
+            n_launch = prof[ck]["launches_per_step"]
+            flops_step = GF_IMG_CONV3 * 1e9 * 2 * B                    # algorithmic FLOPs (NOT x3 for 3xTF32)
             ach = flops_step / (conv_ms / 1e3) / 1e12
-            roof = {"kernel": "conv3x3_c4+conv1x1_c4 (SuperPoint encoder + heads)", "bound": "tensor",
+            roof = {"kernel": ck + " (SuperPoint 3x3 convs, implicit GEMM, 3xTF32 on tcgen05)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
+                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
+                    "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
                     "flops_per_launch": flops_step / max(n_launch, 1), "avg_launch_ms": conv_ms / max(n_launch, 1),
                     "share_of_step": conv_ms / sum(p["ms_per_step"] for p in prof.values()),
-                    "dominant_by_time": dom}
+                    "dominant_by_time": dom,
+                    "note": "achieved counts algorithmic FLOPs once; the kernel issues 3 tf32 MMAs per product "
+                            "(fp32-class accuracy), i.e. %.0f TFLOP/s of tf32 MMA work against a tf32 pipe peak "
+                            "of half the bf16 figure" % (3 * ach)}
         line = {"metric": "image-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -326,3 +326,51 @@ def test_full_size_batch_runs_and_is_consistent():
         assert np.array_equal(m1[i][m0[i][v]], np.nonzero(v)[0])      # mutual consistency
         s = out["scores0"][i].cpu().numpy()
         assert np.all(np.diff(s) <= 0)                                # sortedness of top-k
+
+
+def test_config5_external_features_vs_oracle():
+    """BASELINE config 5 shape (SuperGlue fed with external 128-d descriptors, keypoints0/1 supplied so
+    SuperPoint is skipped, 100 Sinkhorn iterations) at N=M=2048 against the numpy oracle."""
+    from image_matching_b200 import synth
+    from oracle import matching_oracle as O
+    cfg = golden_cfg(max_kp=-1, iters=100)
+    sp, sg = synth.superpoint_weights(0, 128), synth.superglue_weights(5, 128)
+    m = _matching(cfg, sp, sg)
+    H, W, N = 480, 640, 2048
+    kp0, sc0, de0 = synth.random_features(1, 1, N, 128, H, W)
+    kp1, sc1, de1 = synth.random_features(2, 1, N, 128, H, W)
+    de1 = (0.6 * de0[:, :, np.random.default_rng(0).permutation(N)] + 0.4 * de1).astype(np.float32)
+    de1 /= np.linalg.norm(de1, axis=1, keepdims=True)
+    data = {"image0": torch.empty(1, 1, H, W, device=DEV), "image1": torch.empty(1, 1, H, W, device=DEV),
+            "keypoints0": _t(kp0), "scores0": _t(sc0), "descriptors0": _t(de0),
+            "keypoints1": _t(kp1), "scores1": _t(sc1), "descriptors1": _t(de1)}
+    pred = m(data)
+    r = O.superglue_forward(kp0[0], sc0[0], de0[0], kp1[0], sc1[0], de1[0], H, W, sg, cfg["superglue"])
+    m0 = pred["matches0"][0].cpu().numpy()
+    agree = (m0 == r["matches0"]).mean()
+    nvalid = int((r["matches0"] > -1).sum())
+    print(f"config5: {nvalid} oracle matches, agreement {agree:.4f}")
+    assert nvalid > 200 and agree >= 0.995
+    both = (m0 > -1) & (r["matches0"] > -1)
+    assert np.abs(pred["matching_scores0"][0].cpu().numpy() - r["matching_scores0"])[both].max() < 1e-3
+
+
+def test_config3_shape_runs():
+    """BASELINE config 3 model (D=256, kenc [32,64,128,256], 2048 keypoints, 1280x960) at batch 2:
+    size-independent properties (counts, sortedness, mutual consistency, batch == single)."""
+    from image_matching_b200 import synth
+    cfg = golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=2048, iters=30)
+    m = _matching(cfg, synth.superpoint_weights(1, 256), synth.superglue_weights(1, 256, (32, 64, 128, 256)))
+    a, b = synth.make_pair_batch([31, 32], 960, 1280)
+    out = m.forward_device(_t(a), _t(b))
+    out = {k: v.clone() for k, v in out.items()}
+    cnt = out["counts"].cpu().numpy()
+    assert (cnt == 2048).all()
+    m0, m1 = out["matches0"].cpu().numpy(), out["matches1"].cpu().numpy()
+    for i in range(2):
+        v = m0[i] > -1
+        assert np.array_equal(m1[i][m0[i][v]], np.nonzero(v)[0])
+        assert np.all(np.diff(out["scores0"][i].cpu().numpy()) <= 0)
+    o1 = m.forward_device(_t(a[1:]), _t(b[1:]))
+    assert torch.equal(o1["matches0"][0], out["matches0"][1])
+    assert torch.equal(o1["keypoints1"][0], out["keypoints1"][1])
