@@ -85,7 +85,7 @@ struct b200m_handle {
   const char* err_where = nullptr;
   Profiler prof;
   std::vector<ProfRecord> prof_recs;
-  bool use_tc = true;            // tcgen05 3xTF32 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
+  bool use_tc = true;            // tcgen05 fp16x3 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
   bool use_tc_attn = true;       // tcgen05 flash attention (B200M_ATTN_IMPL=simt selects the fp32 CUDA-core kernel)
   bool use_tc_gemm = true;       // tcgen05 linear layers (B200M_GEMM_IMPL=simt selects the fp32 CUDA-core GEMM)
   int num_sms = 148;
@@ -357,7 +357,7 @@ struct SpWs {
   float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat;
   unsigned long long* keys;
   unsigned char* nms_scratch;
-  int *cand_counts, *overflow;
+  int *cand_counts, *overflow;      // overflow[0]: candidate list overflow, overflow[1]: fp16 activation overflow
   size_t p0_img, p1_img, semi_img, draw_img, dn_img, heat_img;
 };
 bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w) {
@@ -378,7 +378,7 @@ bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w)
   w.heat = A.take<float>(w.heat_img * mb);
   w.keys = A.take<unsigned long long>((size_t)d.cand_cap * mb);
   w.nms_scratch = A.take<unsigned char>(nms_scratch_bytes(mb, d.H8, d.W8));
-  w.cand_counts = A.take<int>(mb + 1);
+  w.cand_counts = A.take<int>(mb + 2);
   w.overflow = w.cand_counts ? w.cand_counts + mb : nullptr;
   return A.ok;
 }
@@ -396,10 +396,10 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
 // One 3x3 layer on the tensor cores; falls back to the fp32 CUDA-core kernel if the launch is refused.
 // in/out are (hi, lo) plane pairs; out_lo == nullptr -> full-precision output in out_hi.
 void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
-                 float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool) {
+                 float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow) {
   TcConvParams p;
   p.in_hi = in_hi; p.in_lo = in_lo; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
-  p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0;
+  p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.overflow = overflow;
   p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = 1; p.pool = pool ? 1 : 0;
   launch_tc_conv3x3(ctx, p, h->num_sms);
 }
@@ -409,15 +409,17 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
   // the C4 buffers are addressed per image with each layer's own channel-group count, so the ping-pong
   // buffers are simply re-interpreted per layer
   if (h->use_tc) {
+    int* ovf = w.overflow ? w.overflow + 1 : nullptr;
+    // fp16 hi/lo planes, C8-planar: channel units per image = C / 8
     launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, w.p0_lo, n, d.H, d.W);
-    run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H, d.W, true);      // -> 64 x H2 x W2
-    run_conv_tc(h, ctx, h->c2a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.H2, d.W2, false);
-    run_conv_tc(h, ctx, h->c2b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H2, d.W2, true);    // -> 64 x H3 x W3
-    run_conv_tc(h, ctx, h->c3a, w.p1, w.p1_lo, w.p0, w.p0_lo, 32, n, d.H3, d.W3, false);   // 128 ch
-    run_conv_tc(h, ctx, h->c3b, w.p0, w.p0_lo, w.p1, w.p1_lo, 32, n, d.H3, d.W3, true);    // -> 128 x hc x wc
-    run_conv_tc(h, ctx, h->c4a, w.p1, w.p1_lo, w.p0, w.p0_lo, 32, n, d.hc, d.wc, false);
-    run_conv_tc(h, ctx, h->c4b, w.p0, w.p0_lo, w.p1, w.p1_lo, 32, n, d.hc, d.wc, false);   // x4
-    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, nullptr, 128, n, d.hc, d.wc, false); // cPa | cDa, full fp32
+    run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H, d.W, true, ovf);        // -> 64 x H2 x W2
+    run_conv_tc(h, ctx, h->c2a, w.p1, w.p1_lo, w.p0, w.p0_lo, 8, n, d.H2, d.W2, false, ovf);
+    run_conv_tc(h, ctx, h->c2b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H2, d.W2, true, ovf);      // -> 64 x H3 x W3
+    run_conv_tc(h, ctx, h->c3a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.H3, d.W3, false, ovf);    // 128 ch
+    run_conv_tc(h, ctx, h->c3b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H3, d.W3, true, ovf);     // -> 128 x hc x wc
+    run_conv_tc(h, ctx, h->c4a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.hc, d.wc, false, ovf);
+    run_conv_tc(h, ctx, h->c4b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.hc, d.wc, false, ovf);    // x4
+    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, nullptr, 128, n, d.hc, d.wc, false, ovf); // cPa | cDa, full fp32
   } else {
     launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, nullptr, n, d.H, d.W);
     run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
@@ -447,6 +449,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_im
   SpWs w;
   if (!sp_carve(h, d, mb, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperPoint workspace too small: need %zu bytes", A.off);
   LaunchCtx ctx = make_ctx(h, stream);
+  cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), ctx.stream);
   for (int i0 = 0; i0 < n_images; i0 += mb) {
     const int n = std::min(mb, n_images - i0);
     sp_dense(h, ctx, d, w, images + (size_t)i0 * H * W, n);
@@ -456,7 +459,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_im
       launch_c4_to_nchw(ctx, w.draw, d.dpad / 4, 0, D, desc_out + (size_t)i0 * D * d.hc * d.wc, n, d.hc, d.wc, true);
     if (keypoints) {
       launch_softmax_heat(ctx, w.semi, 32, w.heat, n, d.hc, d.wc);
-      cudaMemsetAsync(w.cand_counts, 0, sizeof(int) * (mb + 1), ctx.stream);
+      cudaMemsetAsync(w.cand_counts, 0, sizeof(int) * mb, ctx.stream);
       launch_nms_candidates(ctx, w.heat, nullptr, n, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
                             h->cfg.remove_borders, w.keys, w.cand_counts, d.cand_cap, w.overflow, w.nms_scratch);
       launch_select_keypoints(ctx, w.keys, w.cand_counts, d.cand_cap, n, d.W8, h->cfg.max_keypoints,
@@ -467,6 +470,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_im
                                 tok_out ? tok_out + (size_t)i0 * tok_img_stride : nullptr, tok_ld, tok_img_stride);
     }
   }
+  if (keypoints) launch_apply_flags(ctx, w.overflow, counts, n_images);
   return finish(h, ctx);
 }
 
@@ -711,13 +715,15 @@ int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* 
     return fail(B200M_ERR_CUDA, "scratch allocation failed");
   float *a = buf, *a_hi = a + in_f, *a_lo = a_hi + in_f, *o_hi = a_lo + in_f, *o_lo = o_hi + out_f;
   LaunchCtx ctx = make_ctx(h, stream);
-  launch_nchw_to_c4(ctx, in, L.cin, a, L.cin / 4, n, H, W);
   if (use_tc) {
-    launch_c4_split(ctx, a, a_hi, a_lo, in_f / 4);
+    launch_nchw_to_c8_split(ctx, in, L.cin, a_hi, a_lo, n, H, W);
     const bool split_out = layer != 7;
-    run_conv_tc(h, ctx, L, a_hi, a_lo, o_hi, split_out ? o_lo : nullptr, L.cout_pad / 4, n, H, W, pool);
-    launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false, split_out ? o_lo : nullptr);
+    run_conv_tc(h, ctx, L, a_hi, a_lo, o_hi, split_out ? o_lo : nullptr, split_out ? L.cout_pad / 8 : L.cout_pad / 4, n,
+                H, W, pool, nullptr);
+    if (split_out) launch_c8_to_nchw(ctx, o_hi, o_lo, L.cout_pad / 8, L.cout, out, n, Ho, Wo);
+    else launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false);
   } else {
+    launch_nchw_to_c4(ctx, in, L.cin, a, L.cin / 4, n, H, W);
     run_conv(h, ctx, L, a, L.cin / 4, 0, o_hi, L.cout_pad / 4, n, H, W, true, pool);
     launch_c4_to_nchw(ctx, o_hi, L.cout_pad / 4, 0, L.cout, out, n, Ho, Wo, false);
   }
@@ -832,19 +838,20 @@ int b200m_detector_post(b200m_handle* h, const float* semi, int n_images, int hc
   float* semi_c4 = A.take<float>((size_t)n_images * 128 * hc * wc);
   float* heat_ws = A.take<float>((size_t)n_images * d.H8 * d.W8);
   unsigned long long* keys = A.take<unsigned long long>((size_t)n_images * d.cand_cap);
-  int* cc = A.take<int>(n_images + 1);
+  int* cc = A.take<int>(n_images + 2);
   unsigned char* nms_scr = A.take<unsigned char>(nms_scratch_bytes(n_images, d.H8, d.W8));
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "detector_post workspace too small: need %zu bytes", A.off);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_nchw_to_c4(ctx, semi, 65, semi_c4, 32, n_images, hc, wc);
   float* hp = heat ? heat : heat_ws;
   launch_softmax_heat(ctx, semi_c4, 32, hp, n_images, hc, wc);
-  cudaMemsetAsync(cc, 0, sizeof(int) * (n_images + 1), ctx.stream);
+  cudaMemsetAsync(cc, 0, sizeof(int) * (n_images + 2), ctx.stream);
   launch_nms_candidates(ctx, hp, nms, n_images, d.H8, d.W8, h->cfg.nms_radius, h->cfg.keypoint_threshold,
                         h->cfg.remove_borders, keypoints ? keys : nullptr, cc, d.cand_cap, cc + n_images, nms_scr);
   if (keypoints)
     launch_select_keypoints(ctx, keys, cc, d.cand_cap, n_images, d.W8, h->cfg.max_keypoints, keypoints, scores,
                             counts, cap);
+  if (keypoints) launch_apply_flags(ctx, cc + n_images, counts, n_images);
   return finish(h, ctx);
 }
 

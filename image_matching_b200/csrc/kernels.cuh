@@ -25,22 +25,27 @@ struct ConvParams {
   int n, H, W;         // input spatial size (output = H,W or H/2,W/2 when pooled)
   int relu;
 };
-// out_lo != null: write tf32-exact hi / lo planes (3xTF32 operand split for the tensor-core convs)
+// out_lo != null: write fp16 hi / lo planes, C8-planar [image][C/8][H][W][8] (operand split of the tensor-core convs:
+// v = hi + lo / 2048); otherwise full fp32 C4-planar
 void launch_conv1_direct(LaunchCtx& ctx, const float* img, const float* w9x64, const float* bias,
                          float* out, float* out_lo, int n, int H, int W);
 void launch_conv(LaunchCtx& ctx, const ConvParams& p, int ksize, bool pool);
 void launch_c4_to_nchw(LaunchCtx& ctx, const float* in, int c4_total, int c4_off, int C, float* out,
                        int n, int H, int W, bool l2_normalize, const float* in_lo = nullptr);
-// full-precision C4-planar -> tf32-exact hi / lo planes
+// full-precision fp32 -> tf32-exact hi / lo planes (element-wise; attention test hook)
 void launch_c4_split(LaunchCtx& ctx, const float* in, float* hi, float* lo, size_t n_float4);
+// (n,C,H,W) fp32 <-> fp16 hi/lo C8-planar planes (conv layer test hook)
+void launch_nchw_to_c8_split(LaunchCtx& ctx, const float* in, int C, void* hi, void* lo, int n, int H, int W);
+void launch_c8_to_nchw(LaunchCtx& ctx, const void* hi, const void* lo, int c8_total, int C, float* out, int n, int H, int W);
 
 // ------------------------------------------------------------------ tensor-core 3x3 conv (tc_conv.cu)
 struct TcConvParams {
-  const float* in_hi; const float* in_lo;   // C4-planar activation planes, cin/4 groups per image
+  const float* in_hi; const float* in_lo;   // fp16 C8-planar activation planes (hi, lo*2048), cin/8 units per image
   const float* wpk;                         // tc_conv_pack_weights layout
   const float* bias;                        // [cout_pad]
-  float* out_hi; float* out_lo;             // out_lo == null: out_hi receives the full fp32 value
-  int out_c4_total, out_c4_off;
+  float* out_hi; float* out_lo;             // fp16 C8-planar planes; out_lo == null: out_hi = full fp32, C4-planar
+  int out_c4_total, out_c4_off;             // channel units per image in the output buffer (8-ch units, or 4-ch if fp32)
+  int* overflow;                            // sticky flag: an activation left the fp16 range
   int cin, cout_pad, nb;                    // nb = output channels per CTA tile (64 or 128)
   int n, H, W;
   int relu, pool;
@@ -64,6 +69,7 @@ void launch_nms_candidates(LaunchCtx& ctx, const float* heat, float* nms_dense, 
 void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, const int* cand_counts,
                              int cand_cap, int n, int W8, int max_kp, float* keypoints, float* scores,
                              int* counts, int cap);
+void launch_apply_flags(LaunchCtx& ctx, const int* flags, int* counts, int n);
 // normalised C4-planar descriptor map + keypoints -> descriptors (n,D,cap) and/or token-major rows
 void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_total, int D, int n, int hc, int wc,
                                const float* keypoints, const int* counts, int cap, int align_corners,

@@ -1,6 +1,7 @@
 // SuperPoint encoder / head convolutions, fp32 CUDA-core path (exact-fp32 accumulate).
 // Reference: superpoint/models/unet_parts.py:10-48, superpoint/models/superpoint_test.py:113-126.
 // BatchNorm is folded into (w, b) at pack time; ReLU and the 2x2 max-pool are fused in the epilogue.
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 
 namespace b200m {
@@ -40,7 +41,11 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = tile[threadIdx.y + ky][threadIdx.x + kx];
-  float4* o = reinterpret_cast<float4*>(out) + (size_t)n * 16 * H * W + (size_t)y * W + x;
+  const size_t plane = (size_t)H * W;
+  float4* o = reinterpret_cast<float4*>(out) + (size_t)n * 16 * plane + (size_t)y * W + x;
+  uint4* oh = reinterpret_cast<uint4*>(out) + (size_t)n * 8 * plane + (size_t)y * W + x;      // fp16 C8-planar
+  uint4* ol = reinterpret_cast<uint4*>(out_lo) + (size_t)n * 8 * plane + (size_t)y * W + x;
+  float prev[4];
 #pragma unroll 4
   for (int g = 0; g < 16; ++g) {
     float4 a = sb[g];
@@ -54,13 +59,23 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
     }
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     if (out_lo) {
-      float4 hi, lo;
-      hi.x = tf32_hi(a.x); hi.y = tf32_hi(a.y); hi.z = tf32_hi(a.z); hi.w = tf32_hi(a.w);
-      lo.x = tf32_hi(a.x - hi.x); lo.y = tf32_hi(a.y - hi.y); lo.z = tf32_hi(a.z - hi.z); lo.w = tf32_hi(a.w - hi.w);
-      o[(size_t)g * H * W] = hi;
-      (reinterpret_cast<float4*>(out_lo) + (size_t)n * 16 * H * W + (size_t)y * W + x)[(size_t)g * H * W] = lo;
+      if ((g & 1) == 0) {
+        prev[0] = a.x; prev[1] = a.y; prev[2] = a.z; prev[3] = a.w;
+      } else {
+        const float e[8] = {prev[0], prev[1], prev[2], prev[3], a.x, a.y, a.z, a.w};
+        __half2 h2[4], l2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half ha = __float2half_rn(e[2 * j]), hb = __float2half_rn(e[2 * j + 1]);
+          h2[j] = __halves2half2(ha, hb);
+          l2[j] = __halves2half2(__float2half_rn((e[2 * j] - __half2float(ha)) * 2048.f),
+                                 __float2half_rn((e[2 * j + 1] - __half2float(hb)) * 2048.f));
+        }
+        oh[(size_t)(g >> 1) * plane] = *reinterpret_cast<uint4*>(h2);
+        ol[(size_t)(g >> 1) * plane] = *reinterpret_cast<uint4*>(l2);
+      }
     } else {
-      o[(size_t)g * H * W] = a;
+      o[(size_t)g * plane] = a;
     }
   }
 }
@@ -344,6 +359,57 @@ void launch_nchw_to_c4(LaunchCtx& ctx, const float* in, int C, float* out, int c
   dim3 grid(cdiv(HW, 128), n);
   nchw_to_c4_kernel<<<grid, 128, 0, ctx.stream>>>(in, C, reinterpret_cast<float4*>(out), c4_total, HW);
   B200M_LAUNCH_CHECK(ctx, "nchw_to_c4");
+}
+
+__global__ void nchw_to_c8_split_kernel(const float* __restrict__ in, int C, uint4* __restrict__ hi, uint4* __restrict__ lo,
+                                        int HW) {
+  const int n = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= HW) return;
+  const float* src = in + (size_t)n * C * HW + px;
+  const int U = C / 8;
+  for (int u = 0; u < U; ++u) {
+    __half2 h2[4], l2[4];
+    for (int j = 0; j < 4; ++j) {
+      const float a = src[(size_t)(u * 8 + 2 * j) * HW], b = src[(size_t)(u * 8 + 2 * j + 1) * HW];
+      const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+      h2[j] = __halves2half2(ha, hb);
+      l2[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * 2048.f),
+                             __float2half_rn((b - __half2float(hb)) * 2048.f));
+    }
+    hi[((size_t)n * U + u) * HW + px] = *reinterpret_cast<uint4*>(h2);
+    lo[((size_t)n * U + u) * HW + px] = *reinterpret_cast<uint4*>(l2);
+  }
+}
+
+void launch_nchw_to_c8_split(LaunchCtx& ctx, const float* in, int C, void* hi, void* lo, int n, int H, int W) {
+  ProfScope prof__(ctx, "nchw_to_c8_split");
+  dim3 grid(cdiv(H * W, 128), n);
+  nchw_to_c8_split_kernel<<<grid, 128, 0, ctx.stream>>>(in, C, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo), H * W);
+  B200M_LAUNCH_CHECK(ctx, "nchw_to_c8_split");
+}
+
+__global__ void c8_to_nchw_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo, int c8_total, int C,
+                                  float* __restrict__ out, int HW) {
+  const int n = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= HW) return;
+  for (int u = 0; u < cdiv(C, 8); ++u) {
+    uint4 h = hi[((size_t)n * c8_total + u) * HW + px], l = lo[((size_t)n * c8_total + u) * HW + px];
+    const __half* hh = reinterpret_cast<const __half*>(&h);
+    const __half* ll = reinterpret_cast<const __half*>(&l);
+    for (int j = 0; j < 8; ++j)
+      if (u * 8 + j < C)
+        out[((size_t)n * C + u * 8 + j) * HW + px] = __half2float(hh[j]) + __half2float(ll[j]) * (1.f / 2048.f);
+  }
+}
+
+void launch_c8_to_nchw(LaunchCtx& ctx, const void* hi, const void* lo, int c8_total, int C, float* out, int n, int H, int W) {
+  ProfScope prof__(ctx, "c8_to_nchw");
+  dim3 grid(cdiv(H * W, 128), n);
+  c8_to_nchw_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const uint4*>(hi), reinterpret_cast<const uint4*>(lo),
+                                                   c8_total, C, out, H * W);
+  B200M_LAUNCH_CHECK(ctx, "c8_to_nchw");
 }
 
 // desc / ||desc||_2 over channels, no eps (superpoint_test.py:125-126)

@@ -256,6 +256,21 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
   B200M_LAUNCH_CHECK(ctx, "select_keypoints");
 }
 
+// Sticky error flags (candidate-list overflow, fp16 activation overflow) are surfaced through the per-image counts
+// the caller reads back anyway: counts[i] = -1 / -2, so no extra host synchronisation is needed.
+__global__ void apply_flags_kernel(const int* __restrict__ flags, int* __restrict__ counts, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[1]) counts[i] = -2;
+  else if (flags[0]) counts[i] = -1;
+}
+
+void launch_apply_flags(LaunchCtx& ctx, const int* flags, int* counts, int n) {
+  ProfScope prof__(ctx, "apply_flags");
+  apply_flags_kernel<<<cdiv(n, 128), 128, 0, ctx.stream>>>(flags, counts, n);
+  B200M_LAUNCH_CHECK(ctx, "apply_flags");
+}
+
 // ------------------------------------------------------------------------------------------------
 // sample_descriptors (:40-52): bilinear grid_sample (zeros padding) of the normalised descriptor map at
 // the keypoints, then L2 normalise (eps 1e-12).  One warp per keypoint, lane = channel group (float4).

@@ -1,16 +1,21 @@
-// SuperPoint 3x3 convolutions on the 5th-generation tensor cores (tcgen05), fp32-class accuracy via 3xTF32.
+// SuperPoint 3x3 convolutions on the 5th-generation tensor cores (tcgen05), fp32-class accuracy via a 2-term fp16
+// split ("fp16x3"): v = hi + lo/2048 with hi = fp16(v), lo = fp16((v - hi) * 2048)  (representation error 2^-24 |v|,
+// every fp16 x fp16 product is exact in the fp32 accumulator).  Compared with 3xTF32 (first version of this kernel)
+// the operands are half as wide, so the shared-memory-bound MMA stream runs twice as fast, and the split is MORE
+// accurate (tf32 hi/lo keeps 2^-22).  Range: activations must stay below the fp16 maximum (65504); the epilogue
+// raises a sticky overflow flag that the host checks.
 // Reference: superpoint/models/unet_parts.py:10-48, superpoint/models/superpoint_test.py:113-126.
 //
 // Implicit GEMM, one persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer   - per 16-channel K block ONE halo tile (18x18 pixels x 16 ch, hi and lo planes) is
+//   warp 0      TMA producer   - per 32-channel K block ONE halo tile (18x18 pixels x 32 ch fp16, hi and lo planes) is
 //                                fetched with cp.async.bulk.tensor (out-of-bounds = zero = the conv's zero padding);
 //                                the nine taps are NOT re-fetched: a tap is just a +16 B / +288 B shift of the UMMA
 //                                shared-memory descriptor's start address inside that tile (no-swizzle K-major
 //                                canonical layout == the C4-planar activation layout).  Weight slabs [tap][kblock]
 //                                arrive pre-laid-out with 1-D bulk copies.
-//   warp 1      MMA issuer     - one thread issues tcgen05.mma.kind::tf32, M=128 (16 rows x 8 px), N=NB, K=8;
+//   warp 1      MMA issuer     - one thread issues tcgen05.mma.kind::f16, M=128 (16 rows x 8 px), N=NB, K=16;
 //                                two accumulators (left / right 8-px half of the 16x16 tile) share every weight slab;
-//                                D = Ahi*Bhi + (Ahi*Blo + Alo*Bhi)  (3xTF32: fp32-class accuracy, keeps the detector
+//                                D = Ahi*Bhi + (Ahi*Blo + Alo*Bhi)/2048  (fp32-class accuracy, keeps the detector
 //                                logits stable enough for keypoint equality).  The tensor core truncates (RZ) when
 //                                it adds a K=8 dot product into the fp32 accumulator, so the error grows with the
 //                                number of accumulation steps: the small cross terms get their OWN accumulator
@@ -18,7 +23,8 @@
 //                                summed with a rounded fp32 add in the epilogue.  NB=64: 2 x (2 px-halves x
 //                                {main, cross} x 64) = 512 TMEM columns, double-buffered; NB=128: single-buffered.
 //   warps 2..5  epilogue       - tcgen05.ld accumulators -> +bias, ReLU, optional 2x2 max-pool (warp shuffles),
-//                                split into tf32-exact hi/lo planes for the next layer, coalesced float4 stores.
+//                                split into fp16 hi/lo planes for the next layer, coalesced 16-byte stores.
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -29,11 +35,12 @@ using namespace tc;
 constexpr int kTcTile = 16;                       // output tile is 16 x 16 pixels
 constexpr int kTcHalo = kTcTile + 2;              // 18
 constexpr int kTcPlaneB = kTcHalo * kTcHalo * 16; // bytes of one channel-group plane of the halo tile (5184)
-constexpr int kTcKbGroups = 4;                    // channel groups (of 4) per K block -> 16 channels
+constexpr int kTcKbGroups = 4;                    // 16-byte channel groups (8 fp16 channels) per K block -> 32 channels
+constexpr int kTcUnitCh = 8;                      // channels per 16-byte unit
+constexpr float kLoScale = 2048.f;                // lo planes / weights carry (v - hi) * 2^11
 constexpr int kTcAPlane = kTcKbGroups * kTcPlaneB;   // 20736: hi (or lo) part of an A stage
 constexpr int kTcAStage = 2 * kTcAPlane;          // 41472
 constexpr int kTcNA = 3;                          // A stages
-constexpr uint32_t kTf32Mask = 0xFFFFE000u;
 
 template <int NB>
 struct TcConvSmem {
@@ -69,7 +76,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = cdiv(p.W, kTcTile), tiles_y = cdiv(p.H, kTcTile);
   const int ncb = p.cout_pad / NB;
-  const int nkb = p.cin / 16;
+  const int nkb = p.cin / (kTcKbGroups * kTcUnitCh);
   const int total = p.n * tiles_y * tiles_x * ncb;
 
   if (threadIdx.x == 0) {
@@ -104,8 +111,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       mbar_wait(&a_empty[sa], pa ^ 1);
       mbar_expect_tx(&a_full[sa], kTcAStage);
       uint8_t* dst = sA + sa * kTcAStage;
-      tma_load_4d(dst, &tm_hi, &a_full[sa], 4 * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
-      tma_load_4d(dst + kTcAPlane, &tm_lo, &a_full[sa], 4 * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
+      tma_load_4d(dst, &tm_hi, &a_full[sa], kTcUnitCh * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
+      tma_load_4d(dst + kTcAPlane, &tm_lo, &a_full[sa], kTcUnitCh * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
       if (++sa == kTcNA) { sa = 0; pa ^= 1; }
     };
     if ((int)blockIdx.x < total) issue_A(blockIdx.x, 0);
@@ -115,18 +122,18 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         // keep the activation halo one K block ahead of the weight slabs
         if (kb + 1 < nkb) issue_A(tile, kb + 1);
         else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
-        const float* wsrc = p.wpk + (size_t)(cb * nkb + kb) * 9 * (SM::B_SLOT / 4);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)(cb * nkb + kb) * 9 * SM::B_SLOT;
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           mbar_expect_tx(&b_full[sb], SM::B_SLOT);
-          bulk_load(sB + sb * SM::B_SLOT, wsrc + (size_t)tap * (SM::B_SLOT / 4), SM::B_SLOT, &b_full[sb]);
+          bulk_load(sB + sb * SM::B_SLOT, wsrc + (size_t)tap * SM::B_SLOT, SM::B_SLOT, &b_full[sb]);
           if (++sb == kTcNB) { sb = 0; pb ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    const uint32_t idesc = instr_desc(2 /*tf32*/, 128, NB);
+    const uint32_t idesc = instr_desc(0 /*f16*/, 128, NB);
     const uint64_t a_hi32 = (smem_desc_nosw(0, kTcPlaneB, kTcHalo * 16) >> 32) << 32;
     const uint32_t a_lo16 = (uint32_t)((kTcPlaneB >> 4) << 16);
     const uint64_t b_hi32 = (smem_desc_nosw(0, NB * 16, 128) >> 32) << 32;
@@ -160,9 +167,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
               const uint64_t al = a_hi32 | (uint64_t)(a_lo16 | (((a_off + kTcAPlane) >> 4) & 0x3FFF));
               const uint32_t d = d0 + sub * (2 * NB);      // main accumulator; cross accumulator at d + NB
               const uint32_t acc = (kb | tap | ks) != 0;
-              mma_tf32(d, ah, bh, idesc, acc);
-              mma_tf32(d + NB, ah, bl, idesc, acc);
-              mma_tf32(d + NB, al, bh, idesc, 1);
+              mma_bf16(d, ah, bh, idesc, acc);          // kind::f16 (format selected by idesc = fp16)
+              mma_bf16(d + NB, ah, bl, idesc, acc);
+              mma_bf16(d + NB, al, bh, idesc, 1);
             }
           }
           tc_commit(&b_empty[sb]);
@@ -211,7 +218,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
           const int c0 = cb * NB + ch * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = (v[j] + vc[j]) + __ldg(p.bias + c0 + j);
+            float t = fmaf(vc[j], 1.f / kLoScale, v[j]) + __ldg(p.bias + c0 + j);
             if (p.relu) t = fmaxf(t, 0.f);
             if (POOL) {
               t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
@@ -220,22 +227,32 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             v[j] = t;
           }
           if (writer) {
-            const size_t g0 = (size_t)img * p.out_c4_total + p.out_c4_off + (c0 >> 2);
-            float4* oh = reinterpret_cast<float4*>(p.out_hi) + g0 * oplane + (size_t)Y * Wo + X;
             if (p.out_lo) {
-              float4* ol = reinterpret_cast<float4*>(p.out_lo) + g0 * oplane + (size_t)Y * Wo + X;
+              // fp16 hi / lo planes, C8-planar: 4 units of 8 channels per 32-column chunk
+              const size_t g0 = (size_t)img * p.out_c4_total + p.out_c4_off + (c0 >> 3);
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi) + g0 * oplane + (size_t)Y * Wo + X;
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo) + g0 * oplane + (size_t)Y * Wo + X;
+              bool ovf = false;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float h[4], l[4];
+              for (int g = 0; g < 4; ++g) {
+                __half2 h2[4], l2[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  h[j] = __uint_as_float((__float_as_uint(v[4 * g + j]) + 0x1000u) & kTf32Mask);
-                  l[j] = __uint_as_float((__float_as_uint(v[4 * g + j] - h[j]) + 0x1000u) & kTf32Mask);
+                  const float a = v[8 * g + 2 * j], b = v[8 * g + 2 * j + 1];
+                  ovf |= (fabsf(a) > 65000.f) | (fabsf(b) > 65000.f);
+                  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+                  h2[j] = __halves2half2(ha, hb);
+                  l2[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * kLoScale),
+                                         __float2half_rn((b - __half2float(hb)) * kLoScale));
                 }
-                oh[(size_t)g * oplane] = make_float4(h[0], h[1], h[2], h[3]);
-                ol[(size_t)g * oplane] = make_float4(l[0], l[1], l[2], l[3]);
+                oh[(size_t)g * oplane] = *reinterpret_cast<uint4*>(h2);
+                ol[(size_t)g * oplane] = *reinterpret_cast<uint4*>(l2);
               }
+              if (ovf && p.overflow) *p.overflow = 1;
             } else {
+              // full fp32, C4-planar (consumed by the CUDA-core 1x1 heads)
+              const size_t g0 = (size_t)img * p.out_c4_total + p.out_c4_off + (c0 >> 2);
+              float4* oh = reinterpret_cast<float4*>(p.out_hi) + g0 * oplane + (size_t)Y * Wo + X;
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 oh[(size_t)g * oplane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -256,14 +273,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   }
 }
 
-static bool make_act_map(CUtensorMap* m, const float* base, int n, int c4, int H, int W) {
+static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H, int W) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint64_t dims[4] = {(cuuint64_t)4 * W, (cuuint64_t)H, (cuuint64_t)c4, (cuuint64_t)n};
+  cuuint64_t dims[4] = {(cuuint64_t)kTcUnitCh * W, (cuuint64_t)H, (cuuint64_t)c4, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)c4 * H * W * 16};
-  cuuint32_t box[4] = {4 * kTcHalo, kTcHalo, kTcKbGroups, 1};
+  cuuint32_t box[4] = {kTcUnitCh * kTcHalo, kTcHalo, kTcKbGroups, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -273,8 +290,8 @@ template <int NB, bool POOL>
 static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   ProfScope prof__(ctx, "tc_conv3x3");
   CUtensorMap tm_hi, tm_lo;
-  if (!make_act_map(&tm_hi, p.in_hi, p.n, p.cin / 4, p.H, p.W)) return false;
-  if (!make_act_map(&tm_lo, p.in_lo, p.n, p.cin / 4, p.H, p.W)) return false;
+  if (!make_act_map(&tm_hi, p.in_hi, p.n, p.cin / kTcUnitCh, p.H, p.W)) return false;
+  if (!make_act_map(&tm_lo, p.in_lo, p.n, p.cin / kTcUnitCh, p.H, p.W)) return false;
   static bool attr_set = false;
   auto kern = tc_conv3x3_kernel<NB, POOL>;
   if (!attr_set) {
@@ -290,41 +307,36 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
 }
 
 bool launch_tc_conv3x3(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
-  if (p.cin % 16 || p.cout_pad % p.nb || (p.nb != 64 && p.nb != 128)) return false;
+  if (p.cin % 32 || p.cout_pad % p.nb || (p.nb != 64 && p.nb != 128)) return false;
   if (p.nb == 64) return p.pool ? launch_tc_t<64, true>(ctx, p, num_sms) : launch_tc_t<64, false>(ctx, p, num_sms);
   return p.pool ? launch_tc_t<128, true>(ctx, p, num_sms) : launch_tc_t<128, false>(ctx, p, num_sms);
 }
 
+// size of the packed weights in floats (the arena is float-typed; the content is fp16)
 size_t tc_conv_weight_floats(int cin, int cout_pad, int nb) {
-  return (size_t)(cout_pad / nb) * (cin / 16) * 9 * 2 * kTcKbGroups * nb * 4;
+  return (size_t)(cout_pad / nb) * (cin / 32) * 9 * 2 * kTcKbGroups * nb * 4;
 }
 
-// Host-side weight packing: w[cout][cin][3][3] (BatchNorm already folded, fp32) ->
-// [cout_blk][kblock][tap][plane hi/lo][chunk of 4 ch][n][4], i.e. the exact shared-memory image of a B slab.
-void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst) {
-  const int ncb = cout_pad / nb, nkb = cin / 16;
+// Host-side weight packing: w[cout][cin][3][3] (BatchNorm already folded) ->
+// [cout_blk][kblock(32 ch)][tap][plane hi/lo][unit of 8 ch][n][8 halves], i.e. the exact shared-memory image of a
+// B slab; hi = fp16(w), lo = fp16((w - hi) * 2048).
+void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst_f) {
+  __half* dst = reinterpret_cast<__half*>(dst_f);
+  const int ncb = cout_pad / nb, nkb = cin / 32;
   for (int cb = 0; cb < ncb; ++cb)
     for (int kb = 0; kb < nkb; ++kb)
       for (int tap = 0; tap < 9; ++tap)
         for (int kc = 0; kc < kTcKbGroups; ++kc)
           for (int n = 0; n < nb; ++n)
-            for (int j = 0; j < 4; ++j) {
-              const int o = cb * nb + n, ci = kb * 16 + kc * 4 + j;
-              float v = o < cout ? (float)w[((size_t)o * cin + ci) * 9 + tap] : 0.f;
-              uint32_t bits;                       // round-to-nearest tf32 split: v = hi + lo (+ O(2^-22 |v|))
-              memcpy(&bits, &v, 4);
-              bits = (bits + 0x1000u) & kTf32Mask;
-              float hi;
-              memcpy(&hi, &bits, 4);
-              float lo = v - hi;
-              memcpy(&bits, &lo, 4);
-              bits = (bits + 0x1000u) & kTf32Mask;
-              memcpy(&lo, &bits, 4);
-              size_t slab = ((size_t)(cb * nkb + kb) * 9 + tap) * 2;
-              size_t idx_hi = ((slab + 0) * kTcKbGroups + kc) * nb * 4 + (size_t)n * 4 + j;
-              size_t idx_lo = ((slab + 1) * kTcKbGroups + kc) * nb * 4 + (size_t)n * 4 + j;
-              dst[idx_hi] = hi;
-              dst[idx_lo] = lo;
+            for (int j = 0; j < kTcUnitCh; ++j) {
+              const int o = cb * nb + n, ci = kb * 32 + kc * kTcUnitCh + j;
+              const float v = o < cout ? (float)w[((size_t)o * cin + ci) * 9 + tap] : 0.f;
+              const __half hi = __float2half_rn(v);
+              const __half lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+              const size_t slab = ((size_t)(cb * nkb + kb) * 9 + tap) * 2;
+              const size_t per_plane = (size_t)kTcKbGroups * nb * kTcUnitCh;
+              dst[(slab + 0) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = hi;
+              dst[(slab + 1) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = lo;
             }
 }
 

@@ -215,7 +215,17 @@ class SuperPoint(_B200Module):
         return kp, sc, de, cnt
 
     @staticmethod
+    def _check_counts(cnt_host):
+        """Negative counts are the library's sticky device-side error flags (read back with the counts)."""
+        if any(c == -2 for c in cnt_host):
+            raise RuntimeError("SuperPoint activation left the fp16 range of the tensor-core convolution "
+                               "(|x| > 65504); set B200M_CONV_IMPL=simt for the fp32 CUDA-core path")
+        if any(c == -1 for c in cnt_host):
+            raise RuntimeError("keypoint candidate list overflowed (degenerate heat-map with massive ties)")
+
+    @staticmethod
     def _to_lists(kp, sc, de, cnt_host):
+        SuperPoint._check_counts(cnt_host)
         keypoints = [kp[i, :n] for i, n in enumerate(cnt_host)]
         scores = tuple(sc[i, :n] for i, n in enumerate(cnt_host))
         descriptors = [de[i, :, :n] for i, n in enumerate(cnt_host)]

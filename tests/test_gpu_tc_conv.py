@@ -64,6 +64,6 @@ def test_tc_conv_matches_fp32(model, layer, shape):
     e_simt = float((simt.double() - ref).abs().max()) / scale
     e_tc = float((tc.double() - ref).abs().max()) / scale
     bias = float((tc.double() - ref).mean()) / scale
-    print(f"layer {layer} {shape}: rel err simt {e_simt:.2e}  tc(3xTF32) {e_tc:.2e} (mean signed {bias:+.2e})")
+    print(f"layer {layer} {shape}: rel err simt {e_simt:.2e}  tc(fp16x3) {e_tc:.2e} (mean signed {bias:+.2e})")
     assert e_simt < 2e-6
-    assert e_tc < 6e-6          # fp32-class: 3xTF32 keeps ~21 mantissa bits per product (plain TF32: ~5e-4)
+    assert e_tc < 6e-6          # fp32-class: the fp16 2-term split keeps ~24 mantissa bits per operand (plain TF32: ~5e-4)
