@@ -191,17 +191,10 @@ struct Packer {
       }
       host[L.b_off + r] = (float)b[sr];
     }
-    L.w_hi_off = alloc((size_t)N * Kpad);
-    L.w_lo_off = alloc((size_t)N * Kpad);
-    for (size_t i = 0; i < (size_t)N * Kpad; ++i) {
-      float v = host[L.w_off + i], hi, lo;
-      uint32_t bits;
-      memcpy(&bits, &v, 4); bits = (bits + 0x1000u) & 0xFFFFE000u; memcpy(&hi, &bits, 4);
-      lo = v - hi;
-      memcpy(&bits, &lo, 4); bits = (bits + 0x1000u) & 0xFFFFE000u; memcpy(&lo, &bits, 4);
-      host[L.w_hi_off + i] = hi;
-      host[L.w_lo_off + i] = lo;
-    }
+    // fp16 hi / lo*2048 planes of the same matrix for the tensor-core GEMM (halves stored in the float arena)
+    L.w_hi_off = alloc(((size_t)N * Kpad + 1) / 2);
+    L.w_lo_off = alloc(((size_t)N * Kpad + 1) / 2);
+    gemm_pack_fp16_planes(host.data() + L.w_off, (size_t)N * Kpad, host.data() + L.w_hi_off, host.data() + L.w_lo_off);
     return L;
   }
 };

@@ -91,8 +91,9 @@ struct GemmParams {
   float* VT = nullptr; float* VT_lo = nullptr; int vt_col0 = 0; int vt_np = 1;
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
-// tcgen05 3xTF32 version for weight GEMMs (w_hi / w_lo: [N][K] tf32-exact planes); returns false if declined
+// tcgen05 fp16x3 version for weight GEMMs (w_hi / w_lo: [N][K] fp16 planes, lo scaled by 2048); false if declined
 bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms);
+void gemm_pack_fp16_planes(const float* w, size_t n, float* hi_as_float, float* lo_as_float);   // host
 // (B,C,N) channel-major <-> token-major [B][N][ld] (first C columns)
 void launch_bcn_to_tokens(LaunchCtx& ctx, const float* in, int B, int C, int N, float* out, int Np, int ld);
 void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float* out, int B, int C, int N);

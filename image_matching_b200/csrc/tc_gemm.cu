@@ -1,22 +1,25 @@
-// SuperGlue per-token linear layers (Conv1d k=1) on tcgen05 tensor cores, 3xTF32 (fp32-class accuracy).
+// SuperGlue per-token linear layers (Conv1d k=1) on tcgen05 tensor cores, fp32-class accuracy via the 2-term fp16
+// split of tc_conv.cu (v = hi + lo/2048; "fp16x3": Ahi*Whi + (Ahi*Wlo + Alo*Whi)/2048).
 // Reference: superglue/models/superglue_test.py:49-60 (MLP), :98-107 (proj / merge), :110-119 (propagation MLP),
 // :214-216 (final_proj).
 //
 //   C[M,N] (+)= A[M,K] * W[N,K]^T + bias   (optional ReLU, residual accumulate, tf32 hi/lo output planes, V^T copy)
 //
 // Persistent CTA per SM, 320 threads:
-//   warp 0      TMA producer  : per 32-column K block the raw fp32 A tile (128 rows x 128 B) and the pre-split
-//                               weight tiles W_hi / W_lo (NT rows x 128 B), all SWIZZLE_128B K-major.
-//   warps 2..5  splitter      : A is produced by other kernels in full fp32, so it is split HERE, in shared memory
-//                               (hi in place, lo into a second tile; element-wise, hence swizzle-agnostic) --
-//                               each A element feeds NT columns, so the split costs ~1% of the MMA time and no
-//                               producer kernel has to write doubled activation planes.
-//   warp 1      MMA issuer    : 4 K steps x (Ahi*Whi + Ahi*Wlo + Alo*Whi), M=128, N=NT=128; main and cross terms in
+//   warp 0      TMA producer  : per 64-column K block the raw fp32 A tile (two 128 rows x 128 B boxes) and the
+//                               pre-split fp16 weight tiles W_hi / W_lo (NT rows x 128 B), all SWIZZLE_128B K-major.
+//   warps 2..5  splitter      : A is produced by other kernels in full fp32, so it is split HERE, in shared memory:
+//                               thread = row; the 64 fp32 of a row (2 x 128 B) become 64 fp16 hi (128 B, written
+//                               over box 0's copy of that row) + 64 fp16 lo (over box 1's) -- in place, no cross-
+//                               thread hazard, same swizzle phase.  Each A element feeds NT columns, so the split
+//                               costs a few % of the MMA time and no producer writes doubled activation planes.
+//   warp 1      MMA issuer    : 4 K steps x (Ahi*Whi, Ahi*Wlo + Alo*Whi), M=128, N=NT=128, K=16; main and cross terms in
 //                               separate TMEM accumulators (the tensor core truncates on accumulate, see tc_conv.cu),
 //                               double-buffered (2 x 2 x 128 = 512 columns) so the epilogue of tile i overlaps the
 //                               MMAs of tile i+1.
 //   warps 6..9  epilogue      : tcgen05.ld -> alpha/bias/ReLU/residual -> stores (row-contiguous float4; the V^T
 //                               copy is written column-wise so a warp stores 128 contiguous bytes).
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -26,9 +29,10 @@ using namespace tc;
 
 constexpr int kGemmNT = 128;                 // output columns per tile
 constexpr int kGemmStages = 3;
-constexpr int kGemmATile = 128 * 128;        // bytes: 128 rows x 32 fp32
-constexpr int kGemmBTile = kGemmNT * 128;
-constexpr int kGemmStage = 2 * kGemmATile + 2 * kGemmBTile;   // A hi(raw), A lo, W hi, W lo
+constexpr int kGemmKB = 64;                  // K columns per pipeline stage
+constexpr int kGemmATile = 128 * 128;        // bytes: 128 rows x 128 B (32 fp32 raw, or 64 fp16 after the split)
+constexpr int kGemmBTile = kGemmNT * 128;    // NT rows x 64 fp16
+constexpr int kGemmStage = 2 * kGemmATile + 2 * kGemmBTile;   // A box0 -> hi, A box1 -> lo, W hi, W lo
 constexpr int kGemmBarOff = kGemmStages * kGemmStage;
 constexpr size_t kGemmSmem = 1024 + kGemmBarOff + (3 * kGemmStages + 4) * 8 + 16;
 
@@ -48,7 +52,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = cdiv(p.M, 128), n_tiles = cdiv(p.N, kGemmNT);
   const int total = m_tiles * n_tiles;
-  const int nkb = cdiv(p.K, 32);
+  const int nkb = cdiv(p.K, kGemmKB);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&split[i], 4); mbar_init(&empty[i], 1); }
@@ -68,16 +72,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * kGemmNT;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], kGemmATile + 2 * kGemmBTile);
+        mbar_expect_tx(&full[s], 2 * kGemmATile + 2 * kGemmBTile);
         uint8_t* st = smem + s * kGemmStage;
-        tma_load_2d(st, &tm_a, &full[s], kb * 32, m0);
-        tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * 32, n0);
-        tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * 32, n0);
+        tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, m0);
+        tma_load_2d(st + kGemmATile, &tm_a, &full[s], kb * kGemmKB + 32, m0);
+        tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * kGemmKB, n0);
+        tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * kGemmKB, n0);
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = instr_desc(2, 128, kGemmNT);
+    const uint32_t idesc = instr_desc(0 /*f16*/, 128, kGemmNT);
     int s = 0, ph = 0, lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int buf = lt & 1, aph = (lt >> 1) & 1;
@@ -94,9 +99,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ah = smem_desc_sw128(a_hi + ks * 32), al = smem_desc_sw128(a_lo + ks * 32);
           const uint64_t wh = smem_desc_sw128(w_hi + ks * 32), wl = smem_desc_sw128(w_lo + ks * 32);
-          mma_tf32(d, ah, wh, idesc, (kb | ks) != 0);
-          mma_tf32(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
-          mma_tf32(d + kGemmNT, al, wh, idesc, 1);
+          mma_bf16(d, ah, wh, idesc, (kb | ks) != 0);             // kind::f16, fp16 operands (idesc)
+          mma_bf16(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
+          mma_bf16(d + kGemmNT, al, wh, idesc, 1);
         }
         tc_commit(&empty[s]);
         if (kb == nkb - 1) tc_commit(&acc_full[buf]);
@@ -112,19 +117,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + s * kGemmStage);
-        float4* lo = reinterpret_cast<float4*>(smem + s * kGemmStage + kGemmATile);
+        uint8_t* st = smem + s * kGemmStage;
+        const int r = t, sw = r & 7;                      // this thread's row and its swizzle phase
+        float e[64];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = i * 128 + t;
-          float4 a = hi[idx], h, l;
-          h.x = __uint_as_float((__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u);
-          h.y = __uint_as_float((__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u);
-          h.z = __uint_as_float((__float_as_uint(a.z) + 0x1000u) & 0xFFFFE000u);
-          h.w = __uint_as_float((__float_as_uint(a.w) + 0x1000u) & 0xFFFFE000u);
-          l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-          hi[idx] = h;
-          lo[idx] = l;
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(st + b * kGemmATile + r * 128 + ((q ^ sw) << 4));
+            e[b * 32 + q * 4 + 0] = v.x; e[b * 32 + q * 4 + 1] = v.y;
+            e[b * 32 + q * 4 + 2] = v.z; e[b * 32 + q * 4 + 3] = v.w;
+          }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                     // 8 fp16 (16 B) per chunk
+          __half2 h2[4], l2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = e[q * 8 + 2 * j], b = e[q * 8 + 2 * j + 1];
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            h2[j] = __halves2half2(ha, hb);
+            l2[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * 2048.f),
+                                   __float2half_rn((b - __half2float(hb)) * 2048.f));
+          }
+          *reinterpret_cast<uint4*>(st + r * 128 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(h2);
+          *reinterpret_cast<uint4*>(st + kGemmATile + r * 128 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(l2);
         }
         fence_proxy_async();
         __syncwarp();
@@ -157,7 +173,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (c0 >= p.N) continue;           // uniform per warp
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = p.alpha * (v[j] + vc[j]) + (p.bias ? __ldg(p.bias + min(c0 + j, p.N - 1)) : 0.f);
+          float t = p.alpha * fmaf(vc[j], 1.f / 2048.f, v[j]) + (p.bias ? __ldg(p.bias + min(c0 + j, p.N - 1)) : 0.f);
           if (p.relu) t = fmaxf(t, 0.f);
           v[j] = t;
         }
@@ -210,6 +226,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
 }
 
+static bool make_sw128_map_f16(CUtensorMap* m, const void* base, size_t rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static bool make_sw128_map2(CUtensorMap* m, const float* base, size_t rows, int cols, int ld, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
@@ -223,15 +252,15 @@ static bool make_sw128_map2(CUtensorMap* m, const float* base, size_t rows, int 
   return r == CUDA_SUCCESS;
 }
 
-// W_hi / W_lo: [N][K] row-major tf32-exact planes (split at pack time).  Requirements: batch == 1, K % 4 == 0,
+// W_hi / W_lo: [N][K] row-major fp16 planes (hi, lo*2048; split at pack time).  Requirements: batch == 1, K % 8 == 0,
 // lda % 4 == 0, N % 4 == 0 and 16-byte aligned bases; anything else is declined (caller uses the CUDA-core GEMM).
 bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms) {
-  if (p.batch != 1 || p.K % 4 || p.lda % 4 || p.ldc % 4 || p.N % 4 || p.K < 32 || p.M <= 0) return false;
+  if (p.batch != 1 || p.K % 8 || p.lda % 4 || p.ldc % 4 || p.N % 4 || p.K < 32 || p.M <= 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(w_hi)) & 15) return false;
   ProfScope prof__(ctx, "tc_gemm");
   CUtensorMap ma, mh, ml;
-  if (!make_sw128_map2(&ma, p.A, (size_t)p.M, p.K, p.lda, 128) || !make_sw128_map2(&mh, w_hi, (size_t)p.N, p.K, p.K, kGemmNT) ||
-      !make_sw128_map2(&ml, w_lo, (size_t)p.N, p.K, p.K, kGemmNT))
+  if (!make_sw128_map2(&ma, p.A, (size_t)p.M, p.K, p.lda, 128) ||
+      !make_sw128_map_f16(&mh, w_hi, (size_t)p.N, p.K, p.K, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, (size_t)p.N, p.K, p.K, kGemmNT))
     return false;
   static bool attr_set = false;
   if (!attr_set) {
@@ -244,6 +273,16 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
   return true;
+}
+
+void gemm_pack_fp16_planes(const float* w, size_t n, float* hi_as_float, float* lo_as_float) {
+  __half* hi = reinterpret_cast<__half*>(hi_as_float);
+  __half* lo = reinterpret_cast<__half*>(lo_as_float);
+  for (size_t i = 0; i < n; ++i) {
+    const __half h = __float2half_rn(w[i]);
+    hi[i] = h;
+    lo[i] = __float2half_rn((w[i] - __half2float(h)) * 2048.f);
+  }
 }
 
 }  // namespace b200m
