@@ -507,7 +507,7 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
 
 void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A, int lda, float* C, int ldc,
                 size_t M, bool relu, bool accumulate, float* C_lo = nullptr, float* VT = nullptr,
-                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1) {
+                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1) {   // C_lo set => fp16 plane outputs
   GemmParams p;
   p.A = A; p.lda = lda; p.strideA = 0;
   p.Bw = h->d_w + L.w_off; p.ldb = L.K; p.strideB = 0;
@@ -515,7 +515,7 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.bias = h->d_w + L.b_off;
   p.M = (int)M; p.N = L.N; p.K = L.K; p.batch = 1;
   p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
-  p.C_lo = C_lo;
+  p.C_lo = C_lo; p.out_f16 = C_lo ? 1 : 0;
   p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np;
   if (h->use_tc_gemm && launch_tc_gemm(ctx, p, h->d_w + L.w_hi_off, h->d_w + L.w_lo_off, h->num_sms)) return;
   launch_gemm(ctx, p);
@@ -731,14 +731,13 @@ int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, 
   const size_t rows = (size_t)2 * B * Np, n = rows * 3 * D;
   LaunchCtx ctx = make_ctx(h, stream);
   if (use_tc) {
-    float* planes = nullptr;
+    float* planes = nullptr;      // fp16 planes: hi, lo (rows x 3D) and V^T hi, lo (rows x D), stored in a float buffer
     const size_t nv = rows * D;
-    if (cudaMallocAsync(&planes, (2 * n + 2 * nv) * sizeof(float), ctx.stream) != cudaSuccess)
+    if (cudaMallocAsync(&planes, (n + nv) * sizeof(float), ctx.stream) != cudaSuccess)
       return fail(B200M_ERR_CUDA, "scratch allocation failed");
-    float *vt_hi = planes + 2 * n, *vt_lo = vt_hi + nv;
-    launch_c4_split(ctx, qkv, planes, planes + n, n / 4);
-    launch_vt_from_qkv(ctx, planes, planes + n, vt_hi, vt_lo, 2 * B, Np, D);
-    bool ok = launch_tc_attention(ctx, planes, planes + n, vt_hi, vt_lo, msg, B, Np, D, kHeads, nullptr, nullptr, n0, n1,
+    float *q_hi = planes, *q_lo = planes + n / 2, *vt_hi = planes + n, *vt_lo = planes + n + nv / 2;
+    launch_qkv_to_f16_planes(ctx, qkv, q_hi, q_lo, vt_hi, vt_lo, 2 * B, Np, D);
+    bool ok = launch_tc_attention(ctx, q_hi, q_lo, vt_hi, vt_lo, msg, B, Np, D, kHeads, nullptr, nullptr, n0, n1,
                                   cross != 0);
     cudaFreeAsync(planes, ctx.stream);
     if (!ok) return fail(B200M_ERR_CUDA, "tcgen05 attention launch refused");

@@ -86,8 +86,10 @@ struct GemmParams {
   float alpha;       // C = alpha * (A B^T) + bias
   int relu;
   int accumulate;    // C += ...
-  float* C_lo = nullptr;   // if set: C receives the tf32-rounded value, C_lo the residual (3xTF32 operand planes)
-  // if set (with C_lo): columns >= vt_col0 are ALSO written transposed, VT[row / vt_np][col - vt_col0][row % vt_np]
+  // out_f16: C / C_lo / VT / VT_lo are fp16 planes (same element indexing): C = fp16(v), C_lo = fp16(v - C);
+  // with VT set, columns >= vt_col0 are ALSO written transposed, VT[row / vt_np][col - vt_col0][row % vt_np]
+  int out_f16 = 0;
+  float* C_lo = nullptr;
   float* VT = nullptr; float* VT_lo = nullptr; int vt_col0 = 0; int vt_np = 1;
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
@@ -107,13 +109,14 @@ void launch_attention(LaunchCtx& ctx, const float* qkv, float* msg, int B, int N
                       const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross);
 
 // tcgen05 flash attention on tf32 hi/lo planes of the fused q|k|v projection (tc_attn.cu)
-// vt_*: transposed value planes [2*B blocks][D][Np] (keys contiguous), written by the q|k|v projection's epilogue
-bool launch_tc_attention(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, const float* vt_hi,
-                         const float* vt_lo, float* msg, int B, int Np, int D,
+// qkv_*: fp16 planes [2*B*Np][3D] (hi = fp16(x), lo = fp16(x - hi)); vt_*: transposed value planes, fp16,
+// [2*B blocks][D][Np] (keys contiguous) -- all written by the q|k|v projection's epilogue (GemmParams::out_f16)
+bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
+                         const void* vt_lo, float* msg, int B, int Np, int D,
                          int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross);
-// (rows, 3D) q|k|v plane pair -> V^T plane pair (test hook path; the GEMM epilogue does this in the product path)
-void launch_vt_from_qkv(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, float* vt_hi, float* vt_lo,
-                        int blocks, int Np, int D);
+// fp32 (rows, 3D) q|k|v buffer -> the fp16 plane set above (test hook; the GEMM epilogue does this in the product path)
+void launch_qkv_to_f16_planes(LaunchCtx& ctx, const float* qkv, void* hi, void* lo, void* vt_hi, void* vt_lo,
+                              int blocks, int Np, int D);
 
 // ------------------------------------------------------------------ optimal transport (sg_ot.cu)
 struct OtParams {

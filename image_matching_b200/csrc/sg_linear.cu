@@ -1,6 +1,7 @@
 // SuperGlue linear layers (Conv1d k=1 == per-token GEMM) and layout helpers, fp32 CUDA-core path.
 // Reference: superglue/models/superglue_test.py:49-60 (MLP), :73-82 (KeypointEncoder), :98-107 (proj/merge),
 // :110-119 (AttentionalPropagation.mlp), :256-260 (final_proj + score einsum).
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 
 namespace b200m {
@@ -94,16 +95,17 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(GemmParams p) {
       float v = p.alpha * acc[i][j] + bz4[j];
       if (p.relu) v = fmaxf(v, 0.f);
       if (p.accumulate) v += crow[c];
-      if (p.C_lo) {
-        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-        const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
-        crow[c] = hi;
-        p.C_lo[(size_t)bz * p.strideC + (size_t)r * p.ldc + c] = lo;
+      if (p.out_f16) {
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t o = (size_t)bz * p.strideC + (size_t)r * p.ldc + c;
+        reinterpret_cast<__half*>(p.C)[o] = hi;
+        reinterpret_cast<__half*>(p.C_lo)[o] = lo;
         if (p.VT && c >= p.vt_col0) {
           const int blk = r / p.vt_np, rr = r - blk * p.vt_np;
-          const size_t o = ((size_t)blk * (p.N - p.vt_col0) + (c - p.vt_col0)) * p.vt_np + rr;
-          p.VT[o] = hi;
-          p.VT_lo[o] = lo;
+          const size_t ov = ((size_t)blk * (p.N - p.vt_col0) + (c - p.vt_col0)) * p.vt_np + rr;
+          reinterpret_cast<__half*>(p.VT)[ov] = hi;
+          reinterpret_cast<__half*>(p.VT_lo)[ov] = lo;
         }
       } else {
         crow[c] = v;
@@ -173,34 +175,32 @@ void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float
   B200M_LAUNCH_CHECK(ctx, "tokens_to_bcn");
 }
 
-__global__ void vt_from_qkv_kernel(const float* __restrict__ qh, const float* __restrict__ ql, float* __restrict__ vh,
-                                   float* __restrict__ vl, int Np, int D) {
-  __shared__ float th[32][33], tl[32][33];
-  const int blk = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int nn = n0 + i, c = c0 + threadIdx.x;
-    bool ok = nn < Np && c < D;
-    size_t src = ((size_t)blk * Np + nn) * 3 * D + 2 * D + c;
-    th[i][threadIdx.x] = ok ? qh[src] : 0.f;
-    tl[i][threadIdx.x] = ok ? ql[src] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int c = c0 + i, nn = n0 + threadIdx.x;
-    if (c < D && nn < Np) {
-      size_t dst = ((size_t)blk * D + c) * Np + nn;
-      vh[dst] = th[threadIdx.x][i];
-      vl[dst] = tl[threadIdx.x][i];
-    }
+// fp32 q|k|v rows -> fp16 hi/lo planes + transposed V planes (test hook for the attention kernel)
+__global__ void qkv_to_f16_planes_kernel(const float* __restrict__ qkv, __half* __restrict__ hi, __half* __restrict__ lo,
+                                         __half* __restrict__ vh, __half* __restrict__ vl, int Np, int D) {
+  const int blk = blockIdx.z, row = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 3 * D) return;
+  const size_t o = ((size_t)blk * Np + row) * 3 * D + c;
+  const float v = qkv[o];
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  hi[o] = h;
+  lo[o] = l;
+  if (c >= 2 * D) {
+    const size_t ov = ((size_t)blk * D + (c - 2 * D)) * Np + row;
+    vh[ov] = h;
+    vl[ov] = l;
   }
 }
 
-void launch_vt_from_qkv(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, float* vt_hi, float* vt_lo,
-                        int blocks, int Np, int D) {
-  ProfScope prof__(ctx, "vt_from_qkv");
-  dim3 grid(cdiv(Np, 32), cdiv(D, 32), blocks), block(32, 8);
-  vt_from_qkv_kernel<<<grid, block, 0, ctx.stream>>>(qkv_hi, qkv_lo, vt_hi, vt_lo, Np, D);
-  B200M_LAUNCH_CHECK(ctx, "vt_from_qkv");
+void launch_qkv_to_f16_planes(LaunchCtx& ctx, const float* qkv, void* hi, void* lo, void* vt_hi, void* vt_lo,
+                              int blocks, int Np, int D) {
+  ProfScope prof__(ctx, "qkv_to_f16_planes");
+  dim3 grid(cdiv(3 * D, 128), Np, blocks);
+  qkv_to_f16_planes_kernel<<<grid, 128, 0, ctx.stream>>>(qkv, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo),
+                                                         reinterpret_cast<__half*>(vt_hi), reinterpret_cast<__half*>(vt_lo), Np, D);
+  B200M_LAUNCH_CHECK(ctx, "qkv_to_f16_planes");
 }
 
 // normalize_keypoints (:63-70) fused with the cat([kpts^T, scores]) of KeypointEncoder.forward (:80-82):

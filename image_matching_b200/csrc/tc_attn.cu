@@ -1,32 +1,35 @@
 // SuperGlue multi-head attention on tcgen05 tensor cores: flash-style (online softmax, the (B,4,N,M)
-// probability tensor of the reference is never materialised), fp32-class accuracy via 3xTF32.
+// probability tensor of the reference is never materialised), fp32-class accuracy via a 2-term fp16 split
+// (x = hi + lo, hi = fp16(x), lo = fp16(x - hi); every product is hi*hi + hi*lo + lo*hi, exact in the fp32
+// accumulator; |q|,|k|,|v| = O(1) and p in [0,1], so the unscaled lo term costs < 3e-8 absolute).
 // Reference: superglue/models/superglue_test.py:85-89 (attention), :92-107 (MultiHeadedAttention).
 //
-// One CTA per (side, pair, head, 128-query tile); key tiles of KT keys stream through a 2-stage ring.
-//   warp 0      TMA producer : Q tile once, then K / V^T tiles (hi and lo planes): 2-D tensor maps with 128-byte
-//                              swizzle, box = 128 B x rows, i.e. the canonical K-major SWIZZLE_128B UMMA layout.
-//                              K tiles are [keys][32 ch]; V is read from the transposed copy V^T [ch][keys] that the
-//                              q|k|v projection's epilogue writes next to it, so both MMAs take K-major operands
-//                              (kind::tf32 returned zeros for an MN-major B operand on this part).
+// The first (3xTF32) version of this kernel measured 2.9k cycles per 128x64 tile with the softmax warps idle 41% of
+// the time on `s_full` / `p_empty`: shared-memory bandwidth (~290 KB of operand reads + P writes + TMA fills per tile
+// at 128 B/clk) was the limit, not the tensor pipe (17% active) or the MUFU.  fp16 operands halve every one of those
+// streams and shrink the CTA to 96 KB of shared memory, so two CTAs share an SM and hide each other's pipeline fill.
+//
+// One CTA per (side, pair, head, 128-query tile); key tiles of KT keys stream through a 3-stage TMA ring.
+//   warp 0      TMA producer : Q tile once, then K / V^T tiles (hi and lo planes), 2-D tensor maps, 128- or 64-byte
+//                              swizzle (= row length), i.e. the canonical K-major swizzled UMMA layouts.  K tiles are
+//                              [keys][d]; V is read from the transposed copy V^T [d][keys] that the q|k|v projection's
+//                              epilogue writes, so both MMAs take K-major operands (an MN-major B operand returned
+//                              zeros for kind::tf32 on this part).
 //   warp 1      MMA issuer   : S_j = Q K_j^T (M=128, N=KT, K=d) into a double-buffered TMEM tile, then
-//                              OT_j = P_j V_j (M=128, N=d, K=KT); each product is hi*hi + hi*lo + lo*hi.
-//   warps 2..5  softmax      : thread = query row.  tcgen05.ld S_j, running max / sum (exp2 with the 1/sqrt(d)
-//                              scale folded into one FFMA), P_j split into tf32 hi/lo and stored to shared memory
-//                              as the next MMA's A operand, OT_{j-1} pulled from TMEM and folded into the
-//                              register accumulator with the usual exp(m_old - m_new) correction.
+//                              OT_j = P_j V_j (M=128, N=d, K=KT), one accumulator per key half.
+//   warps 2..9  softmax      : thread = (query row, key half).  tcgen05.ld S_j, running max / sum (ex2.approx with
+//                              the 1/sqrt(d) scale folded into one FFMA), P_j split into fp16 hi/lo and stored to
+//                              shared memory as the next MMA's A operand (no-swizzle K-major, 8 keys per 16-byte
+//                              unit), OT_{j-1} pulled from TMEM and folded into the register accumulator with the
+//                              usual exp(m_old - m_new) correction; the two key halves keep independent statistics
+//                              (2-way split-KV) and are merged once at the end.
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
 namespace b200m {
 
 using namespace tc;
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -52,25 +55,46 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
   }
 }
 
+// ex2.approx.ftz: 1 MUFU op, max relative error 2^-22 (the accurate exp2f expands to ~4 extra instructions)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// K-major swizzled descriptor for rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); 8-row groups are
+// 8*ROWB bytes apart
+template <int ROWB>
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr) {
+  static_assert(ROWB == 128 || ROWB == 64, "row length must be 64 or 128 bytes");
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
+  return d;
+}
+
 constexpr int kTaQ = 128;   // queries per CTA
 
 template <int HD, int KT>
 struct TcAttnSmem {
-  static constexpr int Q_PLANE = kTaQ * HD * 4;          // bytes, one (hi or lo) plane
-  static constexpr int KV_PLANE = KT * HD * 4;
-  static constexpr int KV_STAGE = 4 * KV_PLANE;          // K hi, K lo, V hi, V lo
-  static constexpr int P_PLANE = kTaQ * KT * 4;
+  static constexpr int QROW = HD * 2;                     // bytes per Q / K row (fp16)
+  static constexpr int VROW = KT * 2;                     // bytes per V^T row
+  static constexpr int Q_PLANE = kTaQ * QROW;
+  static constexpr int K_PLANE = KT * QROW;
+  static constexpr int V_PLANE = HD * VROW;               // == K_PLANE
+  static constexpr int KV_STAGE = 2 * K_PLANE + 2 * V_PLANE;
+  static constexpr int NKV = 3;                           // K/V ring depth
+  static constexpr int P_PLANE = kTaQ * KT * 2;           // [KT/8 chunks][128 rows][8 halves]
   static constexpr int OFF_KV = 2 * Q_PLANE;
-  static constexpr int NKV = 3;                           // K/V ring depth (TMA latency ~ 2-3 tiles of work)
   static constexpr int OFF_P = OFF_KV + NKV * KV_STAGE;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_PLANE;
+  static constexpr int OFF_X = OFF_P + 2 * P_PLANE;       // half-merge exchange: 128 rows x (HD + 2) floats
+  static constexpr int OFF_BAR = OFF_X + kTaQ * (HD + 2) * 4;
   static constexpr int N_BARS = 1 + 3 + 3 + 2 + 2 + 1 + 1 + 2 + 2;
-  static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;   // 1024: SWIZZLE_128B tiles need 1 KB alignment
-  static constexpr int TMEM_COLS = (2 * KT + 2 * HD) <= 128 ? 128 : 256;
-  static constexpr int NH = HD / 32;                      // 128-byte column halves per row
-  static constexpr int Q_HALF = kTaQ * 128;               // bytes of one 32-channel half of a Q plane
-  static constexpr int KV_HALF = KT * 128;
-  static constexpr int VT_CHUNK = HD * 128;               // bytes of one 32-key chunk of a V^T plane
+  static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
+  static constexpr int TMEM_COLS = (2 * KT + 4 * HD) <= 256 ? 256 : 512;
 };
 
 struct TcAttnParams {
@@ -83,7 +107,7 @@ struct TcAttnParams {
 };
 
 template <int HD, int KT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                     const __grid_constant__ CUtensorMap tm_kv_hi, const __grid_constant__ CUtensorMap tm_kv_lo,
                     const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo,
@@ -94,6 +118,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + SM::OFF_KV;
   uint8_t* sP = smem + SM::OFF_P;
+  float* sX = reinterpret_cast<float*>(smem + SM::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = q_full + 1;
@@ -121,10 +146,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     mbar_init(q_full, 1);
     for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q_hi); tma_prefetch_desc(&tm_q_lo);
@@ -142,52 +167,40 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     // ------------------------------------------------------------------ TMA producer
     if (T > 0) {
       mbar_expect_tx(q_full, 2 * SM::Q_PLANE);
-#pragma unroll
-      for (int hf = 0; hf < SM::NH; ++hf) {
-        tma_load_2d(sQ + hf * SM::Q_HALF, &tm_q_hi, q_full, cq + hf * 32, q_row0);
-        tma_load_2d(sQ + SM::Q_PLANE + hf * SM::Q_HALF, &tm_q_lo, q_full, cq + hf * 32, q_row0);
-      }
+      tma_load_2d(sQ, &tm_q_hi, q_full, cq, q_row0);
+      tma_load_2d(sQ + SM::Q_PLANE, &tm_q_lo, q_full, cq, q_row0);
     }
     for (int j = 0; j < T; ++j) {
       const int st = j % SM::NKV, ph = (j / SM::NKV) & 1;
       mbar_wait(&kv_empty[st], ph ^ 1);
       mbar_expect_tx(&kv_full[st], SM::KV_STAGE);
       uint8_t* dst = sKV + st * SM::KV_STAGE;
-      const int r = k_row0 + j * KT;
-#pragma unroll
-      for (int hf = 0; hf < SM::NH; ++hf) {
-        tma_load_2d(dst + hf * SM::KV_HALF, &tm_kv_hi, &kv_full[st], ck + hf * 32, r);
-        tma_load_2d(dst + SM::KV_PLANE + hf * SM::KV_HALF, &tm_kv_lo, &kv_full[st], ck + hf * 32, r);
-      }
-#pragma unroll
-      for (int kc = 0; kc < KT / 32; ++kc) {   // V^T: [HD channel rows][32 keys] per chunk
-        tma_load_2d(dst + 2 * SM::KV_PLANE + kc * SM::VT_CHUNK, &tm_vt_hi, &kv_full[st], j * KT + kc * 32, vt_row0);
-        tma_load_2d(dst + 3 * SM::KV_PLANE + kc * SM::VT_CHUNK, &tm_vt_lo, &kv_full[st], j * KT + kc * 32, vt_row0);
-      }
+      tma_load_2d(dst, &tm_kv_hi, &kv_full[st], ck, k_row0 + j * KT);
+      tma_load_2d(dst + SM::K_PLANE, &tm_kv_lo, &kv_full[st], ck, k_row0 + j * KT);
+      tma_load_2d(dst + 2 * SM::K_PLANE, &tm_vt_hi, &kv_full[st], j * KT, vt_row0);
+      tma_load_2d(dst + 2 * SM::K_PLANE + SM::V_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp)
     if (T > 0) {
-      const uint32_t idesc_s = instr_desc(2, 128, KT);                    // A, B K-major
-      const uint32_t idesc_o = instr_desc(2, 128, HD);                    // A = P, B = V^T, both K-major
+      const uint32_t idesc_s = instr_desc(0, 128, KT);                    // fp16, A and B K-major
+      const uint32_t idesc_o = instr_desc(0, 128, HD);
       const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
       auto issue_S = [&](int j) {
         const int st = j & 1;
         const uint32_t k_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE);
         if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 8; ++ks) {
-          // K-major SWIZZLE_128B: 8-channel step = +32 B inside the 128 B row, next 32 channels = next half
-          const uint32_t qo = (ks >> 2) * SM::Q_HALF + (ks & 3) * 32, ko = (ks >> 2) * SM::KV_HALF + (ks & 3) * 32;
-          const uint64_t qh = smem_desc_sw128(q_base + qo);
-          const uint64_t ql = smem_desc_sw128(q_base + SM::Q_PLANE + qo);
-          const uint64_t kh = smem_desc_sw128(k_base + ko);
-          const uint64_t kl = smem_desc_sw128(k_base + SM::KV_PLANE + ko);
-          mma_tf32(tS + st * KT, qh, kh, idesc_s, ks != 0);
-          mma_tf32(tS + st * KT, qh, kl, idesc_s, 1);
-          mma_tf32(tS + st * KT, ql, kh, idesc_s, 1);
-        }
-        tc_commit(&s_full[st]);
+          for (int ks = 0; ks < HD / 16; ++ks) {          // 16 channels = 32 B inside the swizzled row
+            const uint64_t qh = smem_desc_sw<SM::QROW>(q_base + ks * 32);
+            const uint64_t ql = smem_desc_sw<SM::QROW>(q_base + SM::Q_PLANE + ks * 32);
+            const uint64_t kh = smem_desc_sw<SM::QROW>(k_base + ks * 32);
+            const uint64_t kl = smem_desc_sw<SM::QROW>(k_base + SM::K_PLANE + ks * 32);
+            mma_bf16(tS + st * KT, qh, kh, idesc_s, ks != 0);
+            mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
+            mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
+          }
+          tc_commit(&s_full[st]);
         }
         __syncwarp();
       };
@@ -207,29 +220,31 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         mbar_wait(p_full, j & 1);
         mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t v_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE + 2 * SM::KV_PLANE);
+        const uint32_t v_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE + 2 * SM::K_PLANE);
         if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < KT / 8; ++ks) {
-          const uint64_t ph_ = smem_desc_nosw(p_base + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
-          const uint64_t pl_ = smem_desc_nosw(p_base + SM::P_PLANE + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
-          // V^T, K-major SWIZZLE_128B: rows = channels, 32 keys (128 B) per row; 8-key step = +32 B
-          const uint32_t vo = (ks >> 2) * SM::VT_CHUNK + (ks & 3) * 32;
-          const uint64_t vh = smem_desc_sw128(v_base + vo);
-          const uint64_t vl = smem_desc_sw128(v_base + SM::KV_PLANE + vo);
-          mma_tf32(tO + st * HD, ph_, vh, idesc_o, ks != 0);
-          mma_tf32(tO + st * HD, ph_, vl, idesc_o, 1);
-          mma_tf32(tO + st * HD, pl_, vh, idesc_o, 1);
-        }
-        tc_commit(&kv_empty[j % SM::NKV]);
-        tc_commit(p_empty);
-        tc_commit(&o_full[st]);
+          for (int ks = 0; ks < KT / 16; ++ks) {           // 16 keys per MMA = two 8-key units of P
+            const uint64_t ph_ = smem_desc_nosw(p_base + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
+            const uint64_t pl_ = smem_desc_nosw(p_base + SM::P_PLANE + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
+            const uint64_t vh = smem_desc_sw<SM::VROW>(v_base + ks * 32);
+            const uint64_t vl = smem_desc_sw<SM::VROW>(v_base + SM::V_PLANE + ks * 32);
+            // keys [0, KT/2) accumulate into OT[st][0], keys [KT/2, KT) into OT[st][1] (independent softmax halves)
+            const uint32_t dO = tO + st * (2 * HD) + (ks / (KT / 32)) * HD;
+            mma_bf16(dO, ph_, vh, idesc_o, (ks % (KT / 32)) != 0);
+            mma_bf16(dO, ph_, vl, idesc_o, 1);
+            mma_bf16(dO, pl_, vh, idesc_o, 1);
+          }
+          tc_commit(&kv_empty[j % SM::NKV]);
+          tc_commit(p_empty);
+          tc_commit(&o_full[st]);
         }
         __syncwarp();
       }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------------ softmax / accumulate (thread = query row)
+    // ------------------------------------------------------------------ softmax / accumulate
+    constexpr int KH = KT / 2;
+    const int half = (warp - 2) >> 2;
     const int w4 = warp & 3;
     const int m = w4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
@@ -238,18 +253,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, m_o = -INFINITY, m_prev = -INFINITY;
-    float4* Ph = reinterpret_cast<float4*>(sP) + m;                       // [key chunk][row][4]
-    float4* Pl = reinterpret_cast<float4*>(sP + SM::P_PLANE) + m;
+    uint4* Ph = reinterpret_cast<uint4*>(sP) + (half * (KH / 8)) * kTaQ + m;        // [8-key chunk][row][8 halves]
+    uint4* Pl = reinterpret_cast<uint4*>(sP + SM::P_PLANE) + (half * (KH / 8)) * kTaQ + m;
     auto fold_O = [&](int j, float m_tile) {
       const int st = j & 1, ph = (j >> 1) & 1;
       mbar_wait(&o_full[st], ph);
       tc_fence_after();
       float ot[HD];
-      tmem_ld_n<HD>(tO + lane_base + st * HD, ot);
+      tmem_ld_n<HD>(tO + lane_base + st * (2 * HD) + half * HD, ot);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[st]);
-      const float corr = exp2f((m_o - m_tile) * c);                      // exp2(-inf) = 0 on the first tile
+      const float corr = fast_exp2((m_o - m_tile) * c);                   // exp2(-inf) = 0 on the first tile
 #pragma unroll
       for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr, ot[i]);
       m_o = m_tile;
@@ -258,57 +273,78 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       const int st = j & 1, ph = (j >> 1) & 1;
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
-      float s[KT];
-      tmem_ld_n<KT>(tS + lane_base + st * KT, s);
+      float s[KH];
+      tmem_ld_n<KH>(tS + lane_base + st * KT + half * KH, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
-      const int kbase = j * KT;
-      if (kbase + KT > n_k) {
+      const int kbase = j * KT + half * KH;
+      if (kbase + KH > n_k) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
+        for (int i = 0; i < KH; ++i)
           if (kbase + i >= n_k) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float mx4[4] = {s[0], s[1], s[2], s[3]};                             // 4 independent chains
 #pragma unroll
-      for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < KH; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
-      const float neg = -m_new * c;
-      float sum = 0.f;
+      const float m_safe = m_new == -INFINITY ? 0.f : m_new;              // nothing valid seen yet: stay finite
+      const float neg = -m_safe * c;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < KT; ++i) {
-        s[i] = exp2f(fmaf(s[i], c, neg));
-        sum += s[i];
+      for (int i = 0; i < KH; ++i) {
+        s[i] = fast_exp2(fmaf(s[i], c, neg));
+        sum4[i & 3] += s[i];
       }
-      l_run = l_run * exp2f((m_run - m_new) * c) + sum;
+      l_run = l_run * fast_exp2((m_run - m_safe) * c) + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m_run = m_new;
-      // P_j -> shared memory (A operand of the PV MMA), tf32 hi / lo planes
+      // P_j -> shared memory (A operand of the PV MMA), fp16 hi / lo planes
       mbar_wait(p_empty, (j & 1) ^ 1);
 #pragma unroll
-      for (int g = 0; g < KT / 4; ++g) {
-        float h[4], l[4];
+      for (int g = 0; g < KH / 8; ++g) {
+        __half2 h2[4], l2[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          h[t] = __uint_as_float((__float_as_uint(s[4 * g + t]) + 0x1000u) & 0xFFFFE000u);
-          l[t] = s[4 * g + t] - h[t];
+          const float a = s[8 * g + 2 * t], bb = s[8 * g + 2 * t + 1];
+          h2[t] = __floats2half2_rn(a, bb);
+          const float2 back = __half22float2(h2[t]);
+          l2[t] = __floats2half2_rn(a - back.x, bb - back.y);
         }
-        Ph[g * kTaQ] = make_float4(h[0], h[1], h[2], h[3]);
-        Pl[g * kTaQ] = make_float4(l[0], l[1], l[2], l[3]);
+        Ph[g * kTaQ] = *reinterpret_cast<uint4*>(h2);
+        Pl[g * kTaQ] = *reinterpret_cast<uint4*>(l2);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (j > 0) fold_O(j - 1, m_prev);
-      m_prev = m_new;
+      m_prev = m_safe;
     }
     if (T > 0) fold_O(T - 1, m_prev);
+    // ---- merge the two key halves
+    float* xch = sX + (size_t)m * (HD + 2);
+    if (half == 1) {
+      xch[0] = m_run; xch[1] = l_run;
+#pragma unroll
+      for (int i = 0; i < HD; ++i) xch[2 + i] = o[i];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int row = blockIdx.x * kTaQ + m;
-    if (row < p.Np) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    if (half == 0 && row < p.Np) {
+      const float mb = xch[0], lb = xch[1];
+      const float mm = fmaxf(m_run, mb);
+      const float ca = m_run == -INFINITY ? 0.f : fast_exp2((m_run - mm) * c);
+      const float cb = mb == -INFINITY ? 0.f : fast_exp2((mb - mm) * c);
+      const float l = l_run * ca + lb * cb;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
       float4* dst = reinterpret_cast<float4*>(p.msg + ((size_t)(side * p.B + b) * p.Np + row) * p.D + head * HD);
 #pragma unroll
-      for (int g = 0; g < HD / 4; ++g)
-        dst[g] = make_float4(o[4 * g] * inv, o[4 * g + 1] * inv, o[4 * g + 2] * inv, o[4 * g + 3] * inv);
+      for (int g = 0; g < HD / 4; ++g) {
+        float r4[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r4[t] = (o[4 * g + t] * ca + xch[2 + 4 * g + t] * cb) * inv;
+        dst[g] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+      }
     }
   }
   tc_fence_before();
@@ -319,30 +355,31 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   }
 }
 
-// 2-D view of a [rows][ld] fp32 plane; box = 32 columns (128 B) x box_rows, 128-byte swizzle
-static bool make_sw128_map(CUtensorMap* m, const float* base, size_t rows, int ld, int box_rows) {
+// 2-D view of a [rows][ld] fp16 plane; box = box_cols x box_rows with the swizzle that matches the row length
+static bool make_f16_map(CUtensorMap* m, const void* base, size_t rows, size_t cols, size_t ld, int box_cols, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 template <int HD, int KT>
-static bool launch_tc_attn_t(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, const float* vt_hi,
-                             const float* vt_lo, float* msg, int B, int Np,
+static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
+                             const void* vt_lo, float* msg, int B, int Np,
                              int D, int heads, const int* c0, const int* c1, int nf0, int nf1, bool cross) {
   ProfScope prof__(ctx, "tc_attention");
   const size_t rows = (size_t)2 * B * Np;
   CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
-  if (!make_sw128_map(&mq_hi, qkv_hi, rows, 3 * D, kTaQ) || !make_sw128_map(&mq_lo, qkv_lo, rows, 3 * D, kTaQ) ||
-      !make_sw128_map(&mk_hi, qkv_hi, rows, 3 * D, KT) || !make_sw128_map(&mk_lo, qkv_lo, rows, 3 * D, KT) ||
-      !make_sw128_map(&mv_hi, vt_hi, (size_t)2 * B * D, Np, HD) || !make_sw128_map(&mv_lo, vt_lo, (size_t)2 * B * D, Np, HD))
+  if (!make_f16_map(&mq_hi, qkv_hi, rows, 3 * D, 3 * D, HD, kTaQ) || !make_f16_map(&mq_lo, qkv_lo, rows, 3 * D, 3 * D, HD, kTaQ) ||
+      !make_f16_map(&mk_hi, qkv_hi, rows, 3 * D, 3 * D, HD, KT) || !make_f16_map(&mk_lo, qkv_lo, rows, 3 * D, 3 * D, HD, KT) ||
+      !make_f16_map(&mv_hi, vt_hi, (size_t)2 * B * D, Np, Np, KT, HD) || !make_f16_map(&mv_lo, vt_lo, (size_t)2 * B * D, Np, Np, KT, HD))
     return false;
   using SM = TcAttnSmem<HD, KT>;
   static bool attr_set = false;
@@ -356,16 +393,18 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const float* qkv_hi, const float* q
   p.cross = cross ? 1 : 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   dim3 grid(cdiv(Np, kTaQ), heads, 2 * B);
-  kern<<<grid, 192, SM::BYTES, ctx.stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
+  kern<<<grid, 320, SM::BYTES, ctx.stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_attention");
   return true;
 }
 
-bool launch_tc_attention(LaunchCtx& ctx, const float* qkv_hi, const float* qkv_lo, const float* vt_hi,
-                         const float* vt_lo, float* msg, int B, int Np, int D,
+// qkv_*: fp16 planes [2*B*Np][3D] (hi, lo = x - hi, unscaled); vt_*: fp16 planes [2*B][D][Np]
+bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
+                         const void* vt_lo, float* msg, int B, int Np, int D,
                          int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross) {
   const int hd = D / heads;
-  // hd = 16 (D = 64) rows are 64 B -- would need the 64-byte swizzle variant; the fp32 CUDA-core kernel handles it
+  if (Np % 8) return false;   // V^T rows must be 16-byte multiples for TMA
+  // hd = 16 (D = 64) rows would be 32 B; the fp32 CUDA-core kernel handles that model
   if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross);
   if (hd == 64) return launch_tc_attn_t<64, 32>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross);
   return false;

@@ -161,7 +161,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int r = m0 + mrow;
       const bool rok = r < p.M;
       float* crow = p.C + (size_t)r * p.ldc;
-      float* lrow = p.C_lo ? p.C_lo + (size_t)r * p.ldc : nullptr;
       const int blk = p.VT ? r / p.vt_np : 0, rr = p.VT ? r - blk * p.vt_np : 0;
 #pragma unroll 1
       for (int ch = 0; ch < kGemmNT / 32; ++ch) {
@@ -187,25 +186,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const float4 old = *reinterpret_cast<const float4*>(crow + c);
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
-            if (lrow) {
-              float4 h, l;
-              h.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
-              h.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
-              h.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
-              h.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
-              l.x = __uint_as_float((__float_as_uint(o.x - h.x) + 0x1000u) & 0xFFFFE000u);
-              l.y = __uint_as_float((__float_as_uint(o.y - h.y) + 0x1000u) & 0xFFFFE000u);
-              l.z = __uint_as_float((__float_as_uint(o.z - h.z) + 0x1000u) & 0xFFFFE000u);
-              l.w = __uint_as_float((__float_as_uint(o.w - h.w) + 0x1000u) & 0xFFFFE000u);
-              *reinterpret_cast<float4*>(crow + c) = h;
-              *reinterpret_cast<float4*>(lrow + c) = l;
-              v[4 * g] = h.x; v[4 * g + 1] = h.y; v[4 * g + 2] = h.z; v[4 * g + 3] = h.w;
+            if (p.out_f16) {
+              // fp16 hi / lo planes (+ transposed V planes): consumed by the attention kernel
+              const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+              const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+              const __half2 l01 = __floats2half2_rn(o.x - b01.x, o.y - b01.y);
+              const __half2 l23 = __floats2half2_rn(o.z - b23.x, o.w - b23.y);
+              __half* ch = reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c;
+              __half* cl = reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c;
+              *reinterpret_cast<__half2*>(ch) = h01; *reinterpret_cast<__half2*>(ch + 2) = h23;
+              *reinterpret_cast<__half2*>(cl) = l01; *reinterpret_cast<__half2*>(cl + 2) = l23;
               if (p.VT && c >= p.vt_col0) {
+                __half* vh = reinterpret_cast<__half*>(p.VT);
+                __half* vl = reinterpret_cast<__half*>(p.VT_lo);
                 const size_t o0 = ((size_t)blk * (p.N - p.vt_col0) + (c - p.vt_col0)) * p.vt_np + rr;
-                p.VT[o0] = h.x; p.VT[o0 + p.vt_np] = h.y; p.VT[o0 + 2 * (size_t)p.vt_np] = h.z;
-                p.VT[o0 + 3 * (size_t)p.vt_np] = h.w;
-                p.VT_lo[o0] = l.x; p.VT_lo[o0 + p.vt_np] = l.y; p.VT_lo[o0 + 2 * (size_t)p.vt_np] = l.z;
-                p.VT_lo[o0 + 3 * (size_t)p.vt_np] = l.w;
+                const size_t np = (size_t)p.vt_np;
+                vh[o0] = __low2half(h01); vh[o0 + np] = __high2half(h01);
+                vh[o0 + 2 * np] = __low2half(h23); vh[o0 + 3 * np] = __high2half(h23);
+                vl[o0] = __low2half(l01); vl[o0 + np] = __high2half(l01);
+                vl[o0 + 2 * np] = __low2half(l23); vl[o0 + 3 * np] = __high2half(l23);
               }
             } else {
               *reinterpret_cast<float4*>(crow + c) = o;
