@@ -172,10 +172,10 @@ struct Packer {
     for (int o = 0; o < cout; ++o) host[L.b_off + o] = (float)b[o];
     return L;
   }
-  void pack_tc(ConvLayer& L, const std::vector<double>& w) {   // 3x3 layers with cin % 16 == 0
+  void pack_tc(ConvLayer& L, const std::vector<double>& w) {   // 3x3 / 1x1 layers with cin % 32 == 0
     L.nb = L.cout_pad >= 128 ? 128 : 64;
-    L.tc_w_off = alloc(tc_conv_weight_floats(L.cin, L.cout_pad, L.nb));
-    tc_conv_pack_weights(w.data(), L.cout, L.cin, L.cout_pad, L.nb, host.data() + L.tc_w_off);
+    L.tc_w_off = alloc(tc_conv_weight_floats(L.cin, L.cout_pad, L.nb, L.ks));
+    tc_conv_pack_weights(w.data(), L.cout, L.cin, L.cout_pad, L.nb, L.ks, host.data() + L.tc_w_off);
   }
   Linear pack_linear(const std::vector<double>& w, const std::vector<double>& b, int N, int K, int Kpad,
                      const int* row_perm = nullptr, const int* col_perm = nullptr) {
@@ -243,9 +243,11 @@ int pack_superpoint(b200m_handle* h, Packer& P) {
   if (!P.folded(sp + "convPb", sp + "bnPb", 65, 256, w, b, {65, 256, 1, 1}))
     return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
   h->pb = P.pack_conv(w, b, 65, 256, 1);
+  P.pack_tc(h->pb, w);
   if (!P.folded(sp + "convDb", sp + "bnDb", D, 256, w, b, {D, 256, 1, 1}))
     return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
   h->db = P.pack_conv(w, b, D, 256, 1);
+  P.pack_tc(h->db, w);
   return B200M_OK;
 }
 
@@ -389,12 +391,14 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
 // One 3x3 layer on the tensor cores; falls back to the fp32 CUDA-core kernel if the launch is refused.
 // in/out are (hi, lo) plane pairs; out_lo == nullptr -> full-precision output in out_hi.
 void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
-                 float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow) {
+                 float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow,
+                 bool relu = true, int in_c8_total = 0, int in_c8_off = 0) {
   TcConvParams p;
   p.in_hi = in_hi; p.in_lo = in_lo; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
   p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.overflow = overflow;
-  p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = 1; p.pool = pool ? 1 : 0;
-  launch_tc_conv3x3(ctx, p, h->num_sms);
+  p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = relu ? 1 : 0;
+  p.pool = pool ? 1 : 0; p.ks = L.ks; p.in_c8_total = in_c8_total; p.in_c8_off = in_c8_off;
+  launch_tc_conv(ctx, p, h->num_sms);
 }
 
 // encoder + heads for `n` images (n <= micro-batch): fills w.semi (C4, 32 groups) and w.draw (C4, dpad/4 groups)
@@ -412,7 +416,11 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
     run_conv_tc(h, ctx, h->c3b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H3, d.W3, true, ovf);     // -> 128 x hc x wc
     run_conv_tc(h, ctx, h->c4a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.hc, d.wc, false, ovf);
     run_conv_tc(h, ctx, h->c4b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.hc, d.wc, false, ovf);    // x4
-    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, nullptr, 128, n, d.hc, d.wc, false, ovf); // cPa | cDa, full fp32
+    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, w.p0_lo, 64, n, d.hc, d.wc, false, ovf);  // cPa | cDa (512 ch)
+    // 1x1 heads on the same pipeline (one tap per K block), full fp32 C4-planar outputs
+    run_conv_tc(h, ctx, h->pb, w.p0, w.p0_lo, w.semi, nullptr, 32, n, d.hc, d.wc, false, ovf, false, 64, 0);
+    run_conv_tc(h, ctx, h->db, w.p0, w.p0_lo, w.draw, nullptr, d.dpad / 4, n, d.hc, d.wc, false, ovf, false, 64, 32);
+    return;
   } else {
     launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, nullptr, n, d.H, d.W);
     run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
@@ -479,9 +487,18 @@ size_t sp_ws_bytes(const b200m_handle* h, int n_images, int H, int W) {
 struct SgWs {
   int Np, ldS, ld_uv;
   size_t rows;           // 2 * B * Np
-  float *X, *QKV, *QKV_lo, *VT, *VT_lo, *MSG, *HID, *IN4, *S, *u, *v, *max0;
+  float *X, *QKV, *QKV_lo, *VT, *VT_lo, *MSG, *HID, *IN4, *S, *u, *v, *max0, *ot_part;
   int *idx0, *idx1;
 };
+// pairs per Sinkhorn micro-batch: their score matrices share the L2
+int ot_chunk_pairs(int B, int N, int ldS) {
+  const size_t pair_bytes = (size_t)std::max(N, 1) * ldS * sizeof(float);
+  return std::max(1, std::min(B, (int)((size_t)(64u << 20) / std::max<size_t>(pair_bytes, 1))));
+}
+size_t ot_part_floats(int B, int N, int M, int ldS) {
+  return ot_fused_scratch_floats(ot_chunk_pairs(B, N, ldS), N, M);
+}
+
 bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
   const int D = h->cfg.descriptor_dim;
   w.Np = round_up(std::max(std::max(N, M), 1), 64);
@@ -500,6 +517,7 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
   w.u = A.take<float>((size_t)B * w.ld_uv);
   w.v = A.take<float>((size_t)B * w.ld_uv);
   w.max0 = A.take<float>((size_t)B * w.ld_uv);
+  w.ot_part = A.take<float>(ot_part_floats(B, N, M, w.ldS));
   w.idx0 = A.take<int>((size_t)B * w.ld_uv);
   w.idx1 = A.take<int>((size_t)B * w.ld_uv);
   return A.ok;
@@ -592,9 +610,9 @@ OtParams ot_params(b200m_handle* h, const SgWs& w, const float* S, int ldS, long
 }
 
 // Sinkhorn sweeps in micro-batches of pairs whose score matrices fit the L2 together
-void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters) {
-  const size_t pair_bytes = (size_t)std::max(all.N, 1) * all.ldS * sizeof(float);
-  int chunk = (int)std::max<size_t>(1, (size_t)(64u << 20) / std::max<size_t>(pair_bytes, 1));
+void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters, float* partials) {
+  const int chunk = ot_chunk_pairs(all.B, all.N, all.ldS);
+  const bool fused = partials && ot_fused_supported(all);
   launch_ot_init(ctx, all);
   for (int b0 = 0; b0 < all.B; b0 += chunk) {
     OtParams p = all;
@@ -604,6 +622,10 @@ void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters
     p.v = all.v + (size_t)b0 * all.ld_uv;
     if (p.counts0) p.counts0 += b0;
     if (p.counts1) p.counts1 += b0;
+    if (fused) {
+      launch_ot_sinkhorn_fused(ctx, p, iters, partials);
+      continue;
+    }
     for (int it = 0; it < iters; ++it) {
       launch_ot_row_update(ctx, p);
       launch_ot_col_update(ctx, p);
@@ -619,7 +641,7 @@ int sg_core(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, const float* kpts0, 
   sg_gnn(h, ctx, w, B, c0, c1, N, M, 0, h->cfg.n_gnn_layers);
   sg_scores(h, ctx, w, B, N, M);
   OtParams p = ot_params(h, w, w.S, w.ldS, (long long)N * w.ldS, B, N, M, c0, c1);
-  sg_sinkhorn(h, ctx, p, h->cfg.sinkhorn_iterations);
+  sg_sinkhorn(h, ctx, p, h->cfg.sinkhorn_iterations, w.ot_part);
   launch_ot_argmax(ctx, p, w.idx0, w.max0, w.idx1);
   launch_match_select(ctx, w.idx0, w.max0, w.idx1, w.ld_uv, c0, c1, B, N, M, h->cfg.match_threshold,
                       (long long*)matches0, (long long*)matches1, ms0, ms1);
@@ -958,10 +980,11 @@ int b200m_sinkhorn(b200m_handle* h, const float* S, int B, int N, int M, int ite
   w.ld_uv = round_up(std::max(N, M) + 1, 4);
   w.u = A.take<float>((size_t)B * w.ld_uv);
   w.v = A.take<float>((size_t)B * w.ld_uv);
+  w.ot_part = A.take<float>(ot_part_floats(B, N, M, M));
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
   LaunchCtx ctx = make_ctx(h, stream);
   OtParams p = ot_params(h, w, S, M, (long long)N * M, B, N, M, nullptr, nullptr);
-  sg_sinkhorn(h, ctx, p, iters);
+  sg_sinkhorn(h, ctx, p, iters, w.ot_part);
   launch_ot_write_Z(ctx, p, Z);
   return finish(h, ctx);
 }

@@ -49,10 +49,12 @@ struct TcConvParams {
   int cin, cout_pad, nb;                    // nb = output channels per CTA tile (64 or 128)
   int n, H, W;
   int relu, pool;
+  int ks = 3;                               // 3 (3x3, zero pad 1) or 1 (1x1 heads)
+  int in_c8_total = 0, in_c8_off = 0;       // 8-channel units per image in the input buffer (0 = cin/8) / first unit read
 };
-bool launch_tc_conv3x3(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
-size_t tc_conv_weight_floats(int cin, int cout_pad, int nb);
-void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst);
+bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
+size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks);
+void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, int ks, float* dst);
 void launch_nchw_to_c4(LaunchCtx& ctx, const float* in, int C, float* out, int c4_total, int n, int H, int W);
 void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* out,
                             int out_c4_total, int C, int n, int H, int W);
@@ -130,6 +132,10 @@ struct OtParams {
 void launch_ot_init(LaunchCtx& ctx, const OtParams& p);
 void launch_ot_row_update(LaunchCtx& ctx, const OtParams& p);
 void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p);
+// fused iterations for M <= 1024 (one launch per iteration, S read once per iteration); starts from u = v = 0
+bool ot_fused_supported(const OtParams& p);
+size_t ot_fused_scratch_floats(int pairs, int N, int M);
+void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch);
 void launch_ot_write_Z(LaunchCtx& ctx, const OtParams& p, float* Z);   // dense (B,N+1,M+1), full sizes only
 // argmax over rows / columns of the final Z (computed on the fly from S,u,v)
 void launch_ot_argmax(LaunchCtx& ctx, const OtParams& p, int* idx0, float* max0, int* idx1);

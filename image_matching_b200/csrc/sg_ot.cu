@@ -109,6 +109,209 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
   B200M_LAUNCH_CHECK(ctx, "ot_col");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused Sinkhorn iteration for M <= 1024 columns: ONE launch per iteration, S is read once per iteration (the
+// unfused pair of kernels above reads it three times), two exps per element.
+//   A CTA (8 warps) owns 64 consecutive rows of one pair.
+//   prologue : v of the previous iteration is rebuilt from the per-CTA column partials the previous launch wrote
+//              (<= 17 partial rows per pair, flash-softmax style merge), so no separate combine launch is needed.
+//   rows     : a warp owns 8 rows.  A row (<= 1024 floats) lives in 32 registers per lane (8 coalesced float4 loads):
+//              row LSE with v (two-pass in registers, one exp per element) -> u_i; then y = c + u_i is folded into the
+//              warp's running per-column (max, sum) state, also in registers (branch-free online LSE: one exp per
+//              element, exp(-|y - m|), because one of the two rescale factors is always 1).
+//   epilogue : the 8 warps' column states are tree-merged through shared memory and written as ONE partial row.
+// ot_finish_kernel turns the last partials into v for the match selection.
+constexpr int kOtRowsPerWarp = 8;
+constexpr int kOtRowsPerCta = 8 * kOtRowsPerWarp;
+constexpr int kOtFusedMaxM = 1024;
+
+int ot_fused_parts(int N) { return cdiv(N + 1, kOtRowsPerCta); }
+
+// (m, s) <- (m, s) (+) y : running logsumexp state, branch-free, one exp
+__device__ __forceinline__ void lse_push(float& m, float& s, float y) {
+  const float dlt = y - m;
+  const float e = __expf(-fabsf(dlt));
+  s = dlt > 0.f ? fmaf(s, e, 1.f) : s + e;
+  m = fmaxf(m, y);
+}
+// (m, s) <- (m, s) (+) (m2, s2); an empty state is (-inf, 0)
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float M = fmaxf(m, m2);
+  const float a = m == -INFINITY ? 0.f : __expf(m - M);
+  const float b = m2 == -INFINITY ? 0.f : __expf(m2 - M);
+  s = s * a + s2 * b;
+  m = M;
+}
+
+__global__ void __launch_bounds__(256, 2) ot_iter_kernel(OtParams p, const float2* __restrict__ part_in,
+                                                        float2* __restrict__ part_out, int max_parts, int ld_part,
+                                                        int first) {
+  __shared__ __align__(16) float v_s[kOtFusedMaxM + 4];
+  __shared__ __align__(16) float2 xch[4][kOtFusedMaxM + 4];      // warp-state exchange of the tree merge (32 KB)
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PairDims d = pair_dims(p, b);
+  if (d.n == 0 || d.m == 0) return;                       // uniform per block
+  const int parts = cdiv(d.n + 1, kOtRowsPerCta);
+  if ((int)blockIdx.x >= parts) return;                   // uniform per block
+  // ---- prologue: v_j = log_nu_j - logsumexp_i(c_ij + u_i) from the previous launch's partials (v = 0 at the start)
+  for (int j = threadIdx.x; j < kOtFusedMaxM + 4; j += 256) {
+    float vj = 0.f;
+    if (!first && j <= d.m) {
+      const float2* col = part_in + (size_t)b * max_parts * ld_part + j;
+      float mm = -INFINITY, ss = 0.f;
+      for (int q = 0; q < parts; ++q) {
+        const float2 t = __ldg(col + (size_t)q * ld_part);
+        lse_merge(mm, ss, t.x, t.y);
+      }
+      vj = (j == d.m ? d.nu_bin : d.norm) - (logf(ss) + mm);
+    }
+    v_s[j] = vj;
+  }
+  __syncthreads();
+  const int row0 = blockIdx.x * kOtRowsPerCta + warp * kOtRowsPerWarp;
+  const float vbin = v_s[d.m];
+  float cm[32], cs[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) { cm[q] = -INFINITY; cs[q] = 0.f; }
+  float bm = -INFINITY, bs = 0.f;                         // dustbin column state (same in every lane)
+  const float* S = p.S + (size_t)b * p.strideS;
+  float* u = p.u + (size_t)b * p.ld_uv;
+  const int row_end = min(row0 + kOtRowsPerWarp, d.n + 1);
+  for (int i = row0; i < row_end; ++i) {
+    const bool bin_row = (i == d.n);
+    float c[32];                         // masked columns (j >= m) hold -inf: they drop out of every sum
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = 4 * lane + 128 * k;
+      float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+      if (!bin_row && j < d.m)           // rows are padded to ldS (multiple of 4)
+        t = __ldg(reinterpret_cast<const float4*>(S + (size_t)i * p.ldS + j));
+      c[4 * k] = j < d.m ? t.x : -INFINITY;
+      c[4 * k + 1] = j + 1 < d.m ? t.y : -INFINITY;
+      c[4 * k + 2] = j + 2 < d.m ? t.z : -INFINITY;
+      c[4 * k + 3] = j + 3 < d.m ? t.w : -INFINITY;
+    }
+    // ---- u_i = log_mu_i - logsumexp_j(c_ij + v_j), dustbin column included
+    float mx = p.alpha + vbin;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
+      mx = fmaxf(mx, fmaxf(fmaxf(c[4 * k] + vv.x, c[4 * k + 1] + vv.y), fmaxf(c[4 * k + 2] + vv.z, c[4 * k + 3] + vv.w)));
+    }
+    mx = warp_max(mx);
+    float sum = lane == 0 ? __expf((p.alpha + vbin) - mx) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
+      sum += __expf((c[4 * k] + vv.x) - mx) + __expf((c[4 * k + 1] + vv.y) - mx);
+      sum += __expf((c[4 * k + 2] + vv.z) - mx) + __expf((c[4 * k + 3] + vv.w) - mx);
+    }
+    sum = warp_sum(sum);
+    const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) + mx);
+    if (lane == 0) u[i] = ui;
+    // ---- fold this row into the column states: y_ij = c_ij + u_i (masked columns keep the empty state)
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      float m2 = cm[q], s2 = cs[q];
+      lse_push(m2, s2, c[q] + ui);
+      const bool valid = c[q] > -INFINITY;
+      cm[q] = valid ? m2 : cm[q];
+      cs[q] = valid ? s2 : cs[q];
+    }
+    lse_push(bm, bs, p.alpha + ui);
+  }
+  // ---- tree merge of the 8 warps' column states: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0
+#pragma unroll 1
+  for (int span = 4; span >= 1; span >>= 1) {
+    if (warp >= span && warp < 2 * span) {
+      float2* dst = xch[warp - span];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float4* d4 = reinterpret_cast<float4*>(dst + 4 * lane + 128 * k);
+        d4[0] = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+        d4[1] = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+      }
+      if (lane == 0) dst[kOtFusedMaxM] = make_float2(bm, bs);
+    }
+    __syncthreads();
+    if (warp < span) {
+      const float2* src = xch[warp];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + 4 * lane + 128 * k);
+        const float4 a = s4[0], bq = s4[1];
+        lse_merge(cm[4 * k], cs[4 * k], a.x, a.y);
+        lse_merge(cm[4 * k + 1], cs[4 * k + 1], a.z, a.w);
+        lse_merge(cm[4 * k + 2], cs[4 * k + 2], bq.x, bq.y);
+        lse_merge(cm[4 * k + 3], cs[4 * k + 3], bq.z, bq.w);
+      }
+      const float2 bb = src[kOtFusedMaxM];
+      lse_merge(bm, bs, bb.x, bb.y);
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    float2* prow = part_out + ((size_t)b * max_parts + blockIdx.x) * ld_part;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = 4 * lane + 128 * k;
+      if (j < d.m) {     // ld_part is a multiple of 4 and > m, so the 4-wide store stays inside the row
+        float4* dst = reinterpret_cast<float4*>(prow + j);
+        dst[0] = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+        dst[1] = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) prow[d.m] = make_float2(bm, bs);
+  }
+}
+
+// v from the partials of the last iteration
+__global__ void __launch_bounds__(256) ot_finish_kernel(OtParams p, const float2* __restrict__ partials,
+                                                        int max_parts, int ld_part) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const PairDims d = pair_dims(p, b);
+  if (d.n == 0 || d.m == 0 || j > d.m) return;
+  const int parts = cdiv(d.n + 1, kOtRowsPerCta);
+  const float2* col = partials + (size_t)b * max_parts * ld_part + j;
+  float mm = -INFINITY, ss = 0.f;
+  for (int q = 0; q < parts; ++q) {
+    const float2 t = __ldg(col + (size_t)q * ld_part);
+    lse_merge(mm, ss, t.x, t.y);
+  }
+  p.v[(size_t)b * p.ld_uv + j] = (j == d.m ? d.nu_bin : d.norm) - (logf(ss) + mm);
+}
+
+bool ot_fused_supported(const OtParams& p) {
+  return p.M <= kOtFusedMaxM && p.ldS % 4 == 0 && p.strideS % 4 == 0 && (reinterpret_cast<uintptr_t>(p.S) & 15) == 0;
+}
+
+// floats of scratch for `pairs` pairs: two ping-pong sets of partial rows
+size_t ot_fused_scratch_floats(int pairs, int N, int M) {
+  return (size_t)2 * pairs * ot_fused_parts(N) * round_up(M + 1, 4) * 2;
+}
+
+// `iters` full Sinkhorn iterations (u update then v update) starting from u = v = 0; leaves u and v in p.u / p.v
+void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch) {
+  if (iters <= 0) return;
+  const int max_parts = ot_fused_parts(p.N), ld_part = round_up(p.M + 1, 4);
+  float2* part[2];
+  part[0] = reinterpret_cast<float2*>(scratch);
+  part[1] = part[0] + (size_t)p.B * max_parts * ld_part;
+  for (int it = 0; it < iters; ++it) {
+    ProfScope prof__(ctx, "ot_iter_fused");
+    dim3 grid(max_parts, p.B);
+    ot_iter_kernel<<<grid, 256, 0, ctx.stream>>>(p, part[(it + 1) & 1], part[it & 1], max_parts, ld_part, it == 0);
+    B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
+  }
+  ProfScope prof__(ctx, "ot_finish");
+  dim3 grid(cdiv(p.M + 1, 256), p.B);
+  ot_finish_kernel<<<grid, 256, 0, ctx.stream>>>(p, part[(iters - 1) & 1], max_parts, ld_part);
+  B200M_LAUNCH_CHECK(ctx, "ot_finish");
+}
+
 // Z = couplings + u + v - norm, dense (stage API; full sizes)
 __global__ void ot_write_Z_kernel(OtParams p, float* __restrict__ Z) {
   const int b = blockIdx.z, i = blockIdx.y;

@@ -33,33 +33,38 @@ namespace b200m {
 using namespace tc;
 
 constexpr int kTcTile = 16;                       // output tile is 16 x 16 pixels
-constexpr int kTcHalo = kTcTile + 2;              // 18
-constexpr int kTcPlaneB = kTcHalo * kTcHalo * 16; // bytes of one channel-group plane of the halo tile (5184)
 constexpr int kTcKbGroups = 4;                    // 16-byte channel groups (8 fp16 channels) per K block -> 32 channels
 constexpr int kTcUnitCh = 8;                      // channels per 16-byte unit
 constexpr float kLoScale = 2048.f;                // lo planes / weights carry (v - hi) * 2^11
-constexpr int kTcAPlane = kTcKbGroups * kTcPlaneB;   // 20736: hi (or lo) part of an A stage
-constexpr int kTcAStage = 2 * kTcAPlane;          // 41472
 constexpr int kTcNA = 3;                          // A stages
 
-template <int NB>
+// KS = 3: 3x3 conv, 18x18 halo tile, nine taps by descriptor shifts.  KS = 1: the 1x1 heads (convPb / convDb),
+// the same pipeline with a 16x16 tile and one tap per K block.
+template <int NB, int KS>
 struct TcConvSmem {
+  static constexpr int HALO = kTcTile + KS - 1;
+  static constexpr int TAPS = KS * KS;
+  static constexpr int PLANE_B = HALO * HALO * 16;        // bytes of one channel-group plane of the halo tile
+  static constexpr int A_PLANE = kTcKbGroups * PLANE_B;   // hi (or lo) part of an A stage
+  static constexpr int A_STAGE = 2 * A_PLANE;
   static constexpr int B_PLANE = kTcKbGroups * NB * 16;
   static constexpr int B_SLOT = 2 * B_PLANE;
   // weight-slab ring: a slab is consumed in 12 MMAs (~400-800 cycles) while an L2 fetch takes ~2-4k cycles, so the
   // ring must hold ~96 KB of slabs in flight (measured: 4 slots left the tensor pipe 60% idle waiting on B)
   static constexpr int NBS = 98304 / B_SLOT;
-  static constexpr int BAR_OFF = kTcNA * kTcAStage + NBS * B_SLOT;
+  static constexpr int BAR_OFF = kTcNA * A_STAGE + NBS * B_SLOT;
   static constexpr int N_BARS = 2 * kTcNA + 2 * NBS + 4;
   static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
   static constexpr size_t BYTES = 128 /*align slack*/ + BAR_OFF + N_BARS * 8 + 16;
 };
 
-template <int NB, bool POOL>
+template <int NB, bool POOL, int KS>
 __global__ void __launch_bounds__(192, 1)
-tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
-  using SM = TcConvSmem<NB>;
+tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
+  using SM = TcConvSmem<NB, KS>;
   constexpr int kTcNB = SM::NBS;
+  constexpr int kTcHalo = SM::HALO, kTcPlaneB = SM::PLANE_B, kTcAPlane = SM::A_PLANE, kTcAStage = SM::A_STAGE;
+  constexpr int kTaps = SM::TAPS, kPad = KS / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sA = smem;
@@ -111,8 +116,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       mbar_wait(&a_empty[sa], pa ^ 1);
       mbar_expect_tx(&a_full[sa], kTcAStage);
       uint8_t* dst = sA + sa * kTcAStage;
-      tma_load_4d(dst, &tm_hi, &a_full[sa], kTcUnitCh * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
-      tma_load_4d(dst + kTcAPlane, &tm_lo, &a_full[sa], kTcUnitCh * (x0 - 1), y0 - 1, kb * kTcKbGroups, img);
+      tma_load_4d(dst, &tm_hi, &a_full[sa], kTcUnitCh * (x0 - kPad), y0 - kPad, p.in_c8_off + kb * kTcKbGroups, img);
+      tma_load_4d(dst + kTcAPlane, &tm_lo, &a_full[sa], kTcUnitCh * (x0 - kPad), y0 - kPad,
+                  p.in_c8_off + kb * kTcKbGroups, img);
       if (++sa == kTcNA) { sa = 0; pa ^= 1; }
     };
     if ((int)blockIdx.x < total) issue_A(blockIdx.x, 0);
@@ -122,8 +128,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         // keep the activation halo one K block ahead of the weight slabs
         if (kb + 1 < nkb) issue_A(tile, kb + 1);
         else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)(cb * nkb + kb) * 9 * SM::B_SLOT;
-        for (int tap = 0; tap < 9; ++tap) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)(cb * nkb + kb) * kTaps * SM::B_SLOT;
+        for (int tap = 0; tap < kTaps; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           mbar_expect_tx(&b_full[sb], SM::B_SLOT);
           bulk_load(sB + sb * SM::B_SLOT, wsrc + (size_t)tap * SM::B_SLOT, SM::B_SLOT, &b_full[sb]);
@@ -149,11 +155,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + sa * kTcAStage);
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < kTaps; ++tap) {
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
           const uint32_t b_base = smem_u32(sB + sb * SM::B_SLOT);
-          const int ky = tap / 3, kx = tap - 3 * ky;
+          const int ky = tap / KS, kx = tap - KS * ky;
           if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
@@ -173,8 +179,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
             }
           }
           tc_commit(&b_empty[sb]);
-          if (tap == 8) tc_commit(&a_empty[sa]);
-          if (tap == 8 && kb == nkb - 1) tc_commit(&acc_full[buf]);
+          if (tap == kTaps - 1) tc_commit(&a_empty[sa]);
+          if (tap == kTaps - 1 && kb == nkb - 1) tc_commit(&acc_full[buf]);
           }
           __syncwarp();
           if (++sb == kTcNB) { sb = 0; pb ^= 1; }
@@ -273,12 +279,12 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   }
 }
 
-static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H, int W) {
+static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H, int W, int halo) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[4] = {(cuuint64_t)kTcUnitCh * W, (cuuint64_t)H, (cuuint64_t)c4, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)c4 * H * W * 16};
-  cuuint32_t box[4] = {kTcUnitCh * kTcHalo, kTcHalo, kTcKbGroups, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(kTcUnitCh * halo), (cuuint32_t)halo, kTcKbGroups, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -286,54 +292,60 @@ static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H,
   return r == CUDA_SUCCESS;
 }
 
-template <int NB, bool POOL>
+template <int NB, bool POOL, int KS>
 static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
-  ProfScope prof__(ctx, "tc_conv3x3");
+  using SM = TcConvSmem<NB, KS>;
+  ProfScope prof__(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
+  const int c8_total = p.in_c8_total > 0 ? p.in_c8_total : p.cin / kTcUnitCh;
   CUtensorMap tm_hi, tm_lo;
-  if (!make_act_map(&tm_hi, p.in_hi, p.n, p.cin / kTcUnitCh, p.H, p.W)) return false;
-  if (!make_act_map(&tm_lo, p.in_lo, p.n, p.cin / kTcUnitCh, p.H, p.W)) return false;
+  if (!make_act_map(&tm_hi, p.in_hi, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
+  if (!make_act_map(&tm_lo, p.in_lo, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
   static bool attr_set = false;
-  auto kern = tc_conv3x3_kernel<NB, POOL>;
+  auto kern = tc_conv_kernel<NB, POOL, KS>;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcConvSmem<NB>::BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess)
       return false;
     attr_set = true;
   }
   const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
   const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, 192, TcConvSmem<NB>::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
-  B200M_LAUNCH_CHECK(ctx, "tc_conv3x3");
+  kern<<<grid, 192, SM::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
+  B200M_LAUNCH_CHECK(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
   return true;
 }
 
-bool launch_tc_conv3x3(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
-  if (p.cin % 32 || p.cout_pad % p.nb || (p.nb != 64 && p.nb != 128)) return false;
-  if (p.nb == 64) return p.pool ? launch_tc_t<64, true>(ctx, p, num_sms) : launch_tc_t<64, false>(ctx, p, num_sms);
-  return p.pool ? launch_tc_t<128, true>(ctx, p, num_sms) : launch_tc_t<128, false>(ctx, p, num_sms);
+bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
+  if (p.cin % 32 || p.cout_pad % p.nb || (p.nb != 64 && p.nb != 128) || (p.ks != 1 && p.ks != 3)) return false;
+  if (p.ks == 1) {
+    if (p.pool) return false;
+    return p.nb == 64 ? launch_tc_t<64, false, 1>(ctx, p, num_sms) : launch_tc_t<128, false, 1>(ctx, p, num_sms);
+  }
+  if (p.nb == 64) return p.pool ? launch_tc_t<64, true, 3>(ctx, p, num_sms) : launch_tc_t<64, false, 3>(ctx, p, num_sms);
+  return p.pool ? launch_tc_t<128, true, 3>(ctx, p, num_sms) : launch_tc_t<128, false, 3>(ctx, p, num_sms);
 }
 
 // size of the packed weights in floats (the arena is float-typed; the content is fp16)
-size_t tc_conv_weight_floats(int cin, int cout_pad, int nb) {
-  return (size_t)(cout_pad / nb) * (cin / 32) * 9 * 2 * kTcKbGroups * nb * 4;
+size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks) {
+  return (size_t)(cout_pad / nb) * (cin / 32) * ks * ks * 2 * kTcKbGroups * nb * 4;
 }
 
-// Host-side weight packing: w[cout][cin][3][3] (BatchNorm already folded) ->
+// Host-side weight packing: w[cout][cin][ks][ks] (BatchNorm already folded) ->
 // [cout_blk][kblock(32 ch)][tap][plane hi/lo][unit of 8 ch][n][8 halves], i.e. the exact shared-memory image of a
 // B slab; hi = fp16(w), lo = fp16((w - hi) * 2048).
-void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, float* dst_f) {
+void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, int ks, float* dst_f) {
   __half* dst = reinterpret_cast<__half*>(dst_f);
-  const int ncb = cout_pad / nb, nkb = cin / 32;
+  const int ncb = cout_pad / nb, nkb = cin / 32, taps = ks * ks;
   for (int cb = 0; cb < ncb; ++cb)
     for (int kb = 0; kb < nkb; ++kb)
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < taps; ++tap)
         for (int kc = 0; kc < kTcKbGroups; ++kc)
           for (int n = 0; n < nb; ++n)
             for (int j = 0; j < kTcUnitCh; ++j) {
               const int o = cb * nb + n, ci = kb * 32 + kc * kTcUnitCh + j;
-              const float v = o < cout ? (float)w[((size_t)o * cin + ci) * 9 + tap] : 0.f;
+              const float v = o < cout ? (float)w[((size_t)o * cin + ci) * taps + tap] : 0.f;
               const __half hi = __float2half_rn(v);
               const __half lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
-              const size_t slab = ((size_t)(cb * nkb + kb) * 9 + tap) * 2;
+              const size_t slab = ((size_t)(cb * nkb + kb) * taps + tap) * 2;
               const size_t per_plane = (size_t)kTcKbGroups * nb * kTcUnitCh;
               dst[(slab + 0) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = hi;
               dst[(slab + 1) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = lo;
