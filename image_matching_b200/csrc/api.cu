@@ -1,5 +1,6 @@
 // C ABI of libb200match.so: handle, weight packing and the orchestration of the kernel pipeline.
 // See include/b200m.h for the reference file:line each entry point replaces.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -77,7 +78,11 @@ struct b200m_handle {
   ConvLayer c1b, c2a, c2b, c3a, c3b, c4a, c4b, heads, pb, db;
   // SuperGlue
   std::vector<Linear> kenc;
-  struct Gnn { Linear qkv, merge, mlp1, mlp2; };
+  struct Gnn {
+    Linear qkv, merge, mlp1, mlp2;
+    size_t fused_w_off = 0, fused_b_off = 0;   // tc_gnn.cu weight stream / bias block (D = 128 only)
+    bool fused = false, fused_has_qkv = false;
+  };
   std::vector<Gnn> gnn;
   Linear final_proj;
   float bin_score = 1.f;
@@ -88,6 +93,7 @@ struct b200m_handle {
   bool use_tc = true;            // tcgen05 fp16x3 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
   bool use_tc_attn = true;       // tcgen05 flash attention (B200M_ATTN_IMPL=simt selects the fp32 CUDA-core kernel)
   bool use_tc_gemm = true;       // tcgen05 linear layers (B200M_GEMM_IMPL=simt selects the fp32 CUDA-core GEMM)
+  bool use_fused_gnn = true;     // fused merge/mlp/residual/q|k|v layer kernel (B200M_GNN_IMPL=unfused: four GEMM launches)
   int num_sms = 148;
 };
 
@@ -308,6 +314,22 @@ int pack_superglue(b200m_handle* h, Packer& P) {
     G.mlp2 = P.pack_linear(w, b, D, 2 * D, 2 * D);
     h->gnn.push_back(G);
   }
+  if (D == 128)   // weight streams of the fused layer kernel: layer l carries layer l+1's q|k|v projection
+    for (int l = 0; l < h->cfg.n_gnn_layers; ++l) {
+      b200m_handle::Gnn& G = h->gnn[l];
+      const b200m_handle::Gnn* next = l + 1 < h->cfg.n_gnn_layers ? &h->gnn[l + 1] : nullptr;
+      G.fused_w_off = P.alloc(gnn_fused_weight_floats(next != nullptr));
+      G.fused_b_off = P.alloc(896);
+      gnn_fused_pack_weights(P.host.data() + G.merge.w_off, P.host.data() + G.mlp1.w_off, P.host.data() + G.mlp2.w_off,
+                             next ? P.host.data() + next->qkv.w_off : nullptr, P.host.data() + G.fused_w_off);
+      float* bb = P.host.data() + G.fused_b_off;
+      std::copy_n(P.host.data() + G.merge.b_off, 128, bb);
+      std::copy_n(P.host.data() + G.mlp1.b_off, 256, bb + 128);
+      std::copy_n(P.host.data() + G.mlp2.b_off, 128, bb + 384);
+      if (next) std::copy_n(P.host.data() + next->qkv.b_off, 384, bb + 512);
+      G.fused = true;
+      G.fused_has_qkv = next != nullptr;
+    }
   if (!P.folded(sg + "final_proj", "", D, D, w, b, {D, D})) return fail(B200M_ERR_WEIGHTS, "%s", P.err.c_str());
   h->final_proj = P.pack_linear(w, b, D, D, D);
   return B200M_OK;
@@ -571,6 +593,36 @@ void sg_kenc(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int side, const flo
 void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0, const int* c1, int N, int M,
             int l_begin, int l_end) {
   const int D = h->cfg.descriptor_dim;
+  if (h->use_fused_gnn && h->use_tc_attn && h->use_tc_gemm && D == 128 && w.Np % 8 == 0 && l_begin < l_end &&
+      h->gnn[l_begin].fused) {
+    // attention planes -> fused merge/mlp/residual/next-q|k|v kernel: two launches per layer, the message, the hidden
+    // layer and the concatenation never reach HBM.  MSG doubles as the attention's fp16 hi / lo output planes.
+    __half* att_hi = reinterpret_cast<__half*>(w.MSG);
+    __half* att_lo = att_hi + w.rows * D;
+    run_linear(h, ctx, h->gnn[l_begin].qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false, w.QKV_lo, w.VT, w.VT_lo,
+               2 * D, w.Np);
+    for (int l = l_begin; l < l_end; ++l) {
+      const b200m_handle::Gnn& G = h->gnn[l];
+      const bool cross = h->cfg.gnn_cross[l] != 0;
+      bool ok = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, nullptr, B, w.Np, D, kHeads, c0, c1, N, M,
+                                    cross, att_hi, att_lo);
+      GnnFusedParams p;
+      p.wts = reinterpret_cast<const uint8_t*>(h->d_w + G.fused_w_off);
+      p.bias = h->d_w + G.fused_b_off;
+      p.X = w.X; p.ldx = 2 * D;
+      p.qkv_hi = reinterpret_cast<__half*>(w.QKV); p.qkv_lo = reinterpret_cast<__half*>(w.QKV_lo);
+      p.vt_hi = reinterpret_cast<__half*>(w.VT); p.vt_lo = reinterpret_cast<__half*>(w.VT_lo); p.vt_np = w.Np;
+      p.rows = (int)w.rows;
+      p.nt4 = (l + 1 < l_end && G.fused_has_qkv) ? 3 : 0;
+      p.overflow = nullptr;
+      ok = ok && launch_tc_gnn_layer(ctx, p, att_hi, att_lo, h->num_sms);
+      if (!ok && ctx.err == cudaSuccess) {
+        ctx.err = cudaErrorLaunchFailure;
+        *ctx.err_where = "fused GNN layer (launch declined)";
+      }
+    }
+    return;
+  }
   for (int l = l_begin; l < l_end; ++l) {
     const b200m_handle::Gnn& G = h->gnn[l];
     const bool cross = h->cfg.gnn_cross[l] != 0;
@@ -686,6 +738,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_tc_attn = !(impl && strcmp(impl, "simt") == 0);
   impl = getenv("B200M_GEMM_IMPL");
   h->use_tc_gemm = !(impl && strcmp(impl, "simt") == 0);
+  impl = getenv("B200M_GNN_IMPL");
+  h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
   *out = h;
   return B200M_OK;
 }

@@ -6,6 +6,7 @@
 // 32 consecutive pixels one 512 B coalesced row.
 // SuperGlue token layout: [side][pair][token][ld] fp32 row-major ("token-major"), K contiguous.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace b200m {
@@ -113,9 +114,27 @@ void launch_attention(LaunchCtx& ctx, const float* qkv, float* msg, int B, int N
 // tcgen05 flash attention on tf32 hi/lo planes of the fused q|k|v projection (tc_attn.cu)
 // qkv_*: fp16 planes [2*B*Np][3D] (hi = fp16(x), lo = fp16(x - hi)); vt_*: transposed value planes, fp16,
 // [2*B blocks][D][Np] (keys contiguous) -- all written by the q|k|v projection's epilogue (GemmParams::out_f16)
+// msg_hi / msg_lo set: the message is written as fp16 hi / lo*2048 operand planes [rows][D] instead of fp32 `msg`
 bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                          const void* vt_lo, float* msg, int B, int Np, int D,
-                         int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross);
+                         int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross,
+                         void* msg_hi = nullptr, void* msg_lo = nullptr);
+
+// ------------------------------------------------------------------ fused GNN layer tail (tc_gnn.cu), D = 128
+// merge -> mlp -> residual -> next layer's q|k|v in one kernel; activations never leave the SM between the GEMMs
+struct GnnFusedParams {
+  const uint8_t* wts;        // gnn_fused_pack_weights stream of this layer
+  const float* bias;         // [128 merge | 256 mlp1 | 128 mlp2 | 384 next q|k|v]
+  float* X; int ldx;         // fp32 token state [rows][ldx] (first 128 columns), updated in place
+  __half* qkv_hi; __half* qkv_lo;        // next layer's q|k|v planes [rows][384]
+  __half* vt_hi; __half* vt_lo; int vt_np;   // transposed V planes [rows / vt_np][128][vt_np]
+  int rows;
+  int nt4;                   // 3: also produce the next layer's q|k|v; 0: last layer
+  int* overflow;             // sticky flag: a state left the fp16 range (or null)
+};
+bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* att_hi, const void* att_lo, int num_sms);
+size_t gnn_fused_weight_floats(bool with_qkv);
+void gnn_fused_pack_weights(const float* w_merge, const float* w1, const float* w2, const float* w_qkv, float* dst);
 // fp32 (rows, 3D) q|k|v buffer -> the fp16 plane set above (test hook; the GEMM epilogue does this in the product path)
 void launch_qkv_to_f16_planes(LaunchCtx& ctx, const float* qkv, void* hi, void* lo, void* vt_hi, void* vt_lo,
                               int blocks, int Np, int D);

@@ -127,19 +127,25 @@ constexpr int kOtFusedMaxM = 1024;
 
 int ot_fused_parts(int N) { return cdiv(N + 1, kOtRowsPerCta); }
 
-// (m, s) <- (m, s) (+) y : running logsumexp state, branch-free, one exp
+constexpr float kOtNegBig = -1.0e30f;    // "empty" sentinel: finite, so no inf - inf can appear in the branch-free updates
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ot_ex2(float x) {    // 2^x, one MUFU op (ex2.approx.ftz: rel. error 2^-22)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (m, s) <- (m, s) (+) y : running logsumexp state, branch-free, one exp (one of the two rescale factors is 1)
 __device__ __forceinline__ void lse_push(float& m, float& s, float y) {
   const float dlt = y - m;
-  const float e = __expf(-fabsf(dlt));
+  const float e = ot_ex2(-fabsf(dlt) * kLog2e);
   s = dlt > 0.f ? fmaf(s, e, 1.f) : s + e;
   m = fmaxf(m, y);
 }
-// (m, s) <- (m, s) (+) (m2, s2); an empty state is (-inf, 0)
+// (m, s) <- (m, s) (+) (m2, s2); an empty state is (kOtNegBig, 0)
 __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
   const float M = fmaxf(m, m2);
-  const float a = m == -INFINITY ? 0.f : __expf(m - M);
-  const float b = m2 == -INFINITY ? 0.f : __expf(m2 - M);
-  s = s * a + s2 * b;
+  s = s * ot_ex2((m - M) * kLog2e) + s2 * ot_ex2((m2 - M) * kLog2e);
   m = M;
 }
 
@@ -155,70 +161,98 @@ __global__ void __launch_bounds__(256, 2) ot_iter_kernel(OtParams p, const float
   const int parts = cdiv(d.n + 1, kOtRowsPerCta);
   if ((int)blockIdx.x >= parts) return;                   // uniform per block
   // ---- prologue: v_j = log_nu_j - logsumexp_i(c_ij + u_i) from the previous launch's partials (v = 0 at the start)
-  for (int j = threadIdx.x; j < kOtFusedMaxM + 4; j += 256) {
-    float vj = 0.f;
-    if (!first && j <= d.m) {
-      const float2* col = part_in + (size_t)b * max_parts * ld_part + j;
-      float mm = -INFINITY, ss = 0.f;
-      for (int q = 0; q < parts; ++q) {
-        const float2 t = __ldg(col + (size_t)q * ld_part);
-        lse_merge(mm, ss, t.x, t.y);
+  // (thread = two adjacent columns; all partial rows of a batch are fetched before any is merged, so the L2 round trips
+  // overlap instead of forming a dependent chain)
+  constexpr int kBatch = 18;
+  for (int j0 = 2 * threadIdx.x; j0 < kOtFusedMaxM + 4; j0 += 512) {
+    float va = 0.f, vb = 0.f;
+    if (!first && j0 <= d.m) {
+      const float4* col = reinterpret_cast<const float4*>(part_in + (size_t)b * max_parts * ld_part + j0);
+      const size_t ldq = (size_t)(ld_part >> 1);
+      float m0 = kOtNegBig, s0 = 0.f, m1 = kOtNegBig, s1 = 0.f;
+      for (int q0 = 0; q0 < parts; q0 += kBatch) {
+        float4 t[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+          t[q] = q0 + q < parts ? __ldg(col + (size_t)(q0 + q) * ldq) : make_float4(kOtNegBig, 0.f, kOtNegBig, 0.f);
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+          lse_merge(m0, s0, t[q].x, t[q].y);
+          lse_merge(m1, s1, t[q].z, t[q].w);
+        }
       }
-      vj = (j == d.m ? d.nu_bin : d.norm) - (logf(ss) + mm);
+      va = (j0 == d.m ? d.nu_bin : d.norm) - (logf(s0) + m0);
+      if (j0 + 1 <= d.m) vb = (j0 + 1 == d.m ? d.nu_bin : d.norm) - (logf(s1) + m1);
     }
-    v_s[j] = vj;
+    v_s[j0] = va;
+    v_s[j0 + 1] = vb;
   }
   __syncthreads();
   const int row0 = blockIdx.x * kOtRowsPerCta + warp * kOtRowsPerWarp;
-  const float vbin = v_s[d.m];
+  const float xbin = p.alpha + v_s[d.m];                  // dustbin column term of every row LSE
+  // columns of this lane: 4*lane + 128*k + {0..3}.  Groups k < kfull are valid in every lane, group kfull is the ragged
+  // one (columns >= m masked with the sentinel), groups above it are skipped (warp-uniform conditions).
+  const int kfull = d.m >> 7;
   float cm[32], cs[32];
 #pragma unroll
-  for (int q = 0; q < 32; ++q) { cm[q] = -INFINITY; cs[q] = 0.f; }
-  float bm = -INFINITY, bs = 0.f;                         // dustbin column state (same in every lane)
+  for (int q = 0; q < 32; ++q) { cm[q] = kOtNegBig; cs[q] = 0.f; }
+  float bm = kOtNegBig, bs = 0.f;                         // dustbin column state (same in every lane)
   const float* S = p.S + (size_t)b * p.strideS;
   float* u = p.u + (size_t)b * p.ld_uv;
   const int row_end = min(row0 + kOtRowsPerWarp, d.n + 1);
   for (int i = row0; i < row_end; ++i) {
     const bool bin_row = (i == d.n);
-    float c[32];                         // masked columns (j >= m) hold -inf: they drop out of every sum
+    const float* srow = S + (size_t)i * p.ldS + 4 * lane;
+    float c[32];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int j = 4 * lane + 128 * k;
-      float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
-      if (!bin_row && j < d.m)           // rows are padded to ldS (multiple of 4)
-        t = __ldg(reinterpret_cast<const float4*>(S + (size_t)i * p.ldS + j));
-      c[4 * k] = j < d.m ? t.x : -INFINITY;
-      c[4 * k + 1] = j + 1 < d.m ? t.y : -INFINITY;
-      c[4 * k + 2] = j + 2 < d.m ? t.z : -INFINITY;
-      c[4 * k + 3] = j + 3 < d.m ? t.w : -INFINITY;
+      if (k <= kfull) {
+        const int j = 4 * lane + 128 * k;
+        float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+        if (!bin_row && j < d.m) t = __ldg(reinterpret_cast<const float4*>(srow + 128 * k));   // rows padded to ldS
+        if (k == kfull) {
+          t.x = j < d.m ? t.x : kOtNegBig;
+          t.y = j + 1 < d.m ? t.y : kOtNegBig;
+          t.z = j + 2 < d.m ? t.z : kOtNegBig;
+          t.w = j + 3 < d.m ? t.w : kOtNegBig;
+        }
+        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
+      }
+    }
+    if (i + 1 < row_end && i + 1 < d.n) {   // pull the next row towards L1 while this one is processed
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k <= kfull && 4 * lane + 128 * k < d.m)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(srow + p.ldS + 128 * k));
     }
     // ---- u_i = log_mu_i - logsumexp_j(c_ij + v_j), dustbin column included
-    float mx = p.alpha + vbin;
+    float mx = xbin;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
-      mx = fmaxf(mx, fmaxf(fmaxf(c[4 * k] + vv.x, c[4 * k + 1] + vv.y), fmaxf(c[4 * k + 2] + vv.z, c[4 * k + 3] + vv.w)));
-    }
+    for (int k = 0; k < 8; ++k)
+      if (k <= kfull) {
+        const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
+        mx = fmaxf(mx, fmaxf(fmaxf(c[4 * k] + vv.x, c[4 * k + 1] + vv.y), fmaxf(c[4 * k + 2] + vv.z, c[4 * k + 3] + vv.w)));
+      }
     mx = warp_max(mx);
-    float sum = lane == 0 ? __expf((p.alpha + vbin) - mx) : 0.f;
+    const float nmx = -mx * kLog2e;
+    float sum = lane == 0 ? ot_ex2(fmaf(xbin, kLog2e, nmx)) : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
-      sum += __expf((c[4 * k] + vv.x) - mx) + __expf((c[4 * k + 1] + vv.y) - mx);
-      sum += __expf((c[4 * k + 2] + vv.z) - mx) + __expf((c[4 * k + 3] + vv.w) - mx);
-    }
+    for (int k = 0; k < 8; ++k)
+      if (k <= kfull) {
+        const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
+        sum += ot_ex2(fmaf(c[4 * k] + vv.x, kLog2e, nmx)) + ot_ex2(fmaf(c[4 * k + 1] + vv.y, kLog2e, nmx));
+        sum += ot_ex2(fmaf(c[4 * k + 2] + vv.z, kLog2e, nmx)) + ot_ex2(fmaf(c[4 * k + 3] + vv.w, kLog2e, nmx));
+      }
     sum = warp_sum(sum);
     const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) + mx);
     if (lane == 0) u[i] = ui;
-    // ---- fold this row into the column states: y_ij = c_ij + u_i (masked columns keep the empty state)
+    // ---- fold this row into the column states: y_ij = c_ij + u_i (masked columns accumulate garbage that is never read)
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      float m2 = cm[q], s2 = cs[q];
-      lse_push(m2, s2, c[q] + ui);
-      const bool valid = c[q] > -INFINITY;
-      cm[q] = valid ? m2 : cm[q];
-      cs[q] = valid ? s2 : cs[q];
-    }
+    for (int k = 0; k < 8; ++k)
+      if (k <= kfull) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lse_push(cm[4 * k + e], cs[4 * k + e], c[4 * k + e] + ui);
+      }
     lse_push(bm, bs, p.alpha + ui);
   }
   // ---- tree merge of the 8 warps' column states: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0
@@ -276,10 +310,14 @@ __global__ void __launch_bounds__(256) ot_finish_kernel(OtParams p, const float2
   if (d.n == 0 || d.m == 0 || j > d.m) return;
   const int parts = cdiv(d.n + 1, kOtRowsPerCta);
   const float2* col = partials + (size_t)b * max_parts * ld_part + j;
-  float mm = -INFINITY, ss = 0.f;
-  for (int q = 0; q < parts; ++q) {
-    const float2 t = __ldg(col + (size_t)q * ld_part);
-    lse_merge(mm, ss, t.x, t.y);
+  float mm = kOtNegBig, ss = 0.f;
+  for (int q0 = 0; q0 < parts; q0 += 18) {
+    float2 t[18];
+#pragma unroll
+    for (int q = 0; q < 18; ++q)
+      t[q] = q0 + q < parts ? __ldg(col + (size_t)(q0 + q) * ld_part) : make_float2(kOtNegBig, 0.f);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) lse_merge(mm, ss, t[q].x, t[q].y);
   }
   p.v[(size_t)b * p.ld_uv + j] = (j == d.m ? d.nu_bin : d.norm) - (logf(ss) + mm);
 }

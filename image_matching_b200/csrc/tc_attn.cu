@@ -98,7 +98,9 @@ struct TcAttnSmem {
 };
 
 struct TcAttnParams {
-  float* msg;              // [rows][D] head-major message (pre-merge)
+  float* msg;              // [rows][D] head-major message (pre-merge), fp32 -- or, when msg_hi is set,
+  __half* msg_hi;          // fp16 hi / lo*2048 operand planes [rows][D] for the fused layer kernel (tc_gnn.cu)
+  __half* msg_lo;
   int B, Np, D;
   const int* counts0; const int* counts1;
   int n_full0, n_full1;
@@ -337,13 +339,33 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       const float cb = mb == -INFINITY ? 0.f : fast_exp2((mb - mm) * c);
       const float l = l_run * ca + lb * cb;
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      float4* dst = reinterpret_cast<float4*>(p.msg + ((size_t)(side * p.B + b) * p.Np + row) * p.D + head * HD);
+      const size_t off = ((size_t)(side * p.B + b) * p.Np + row) * p.D + head * HD;
+      if (p.msg_hi) {
+        uint4* dh = reinterpret_cast<uint4*>(p.msg_hi + off);
+        uint4* dl = reinterpret_cast<uint4*>(p.msg_lo + off);
 #pragma unroll
-      for (int g = 0; g < HD / 4; ++g) {
-        float r4[4];
+        for (int g = 0; g < HD / 8; ++g) {
+          __half2 h2[4], l2[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) r4[t] = (o[4 * g + t] * ca + xch[2 + 4 * g + t] * cb) * inv;
-        dst[g] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+          for (int t = 0; t < 4; ++t) {
+            const float a = (o[8 * g + 2 * t] * ca + xch[2 + 8 * g + 2 * t] * cb) * inv;
+            const float bb = (o[8 * g + 2 * t + 1] * ca + xch[2 + 8 * g + 2 * t + 1] * cb) * inv;
+            h2[t] = __floats2half2_rn(a, bb);
+            const float2 back = __half22float2(h2[t]);
+            l2[t] = __floats2half2_rn((a - back.x) * 2048.f, (bb - back.y) * 2048.f);
+          }
+          dh[g] = *reinterpret_cast<uint4*>(h2);
+          dl[g] = *reinterpret_cast<uint4*>(l2);
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(p.msg + off);
+#pragma unroll
+        for (int g = 0; g < HD / 4; ++g) {
+          float r4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) r4[t] = (o[4 * g + t] * ca + xch[2 + 4 * g + t] * cb) * inv;
+          dst[g] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+        }
       }
     }
   }
@@ -373,7 +395,8 @@ static bool make_f16_map(CUtensorMap* m, const void* base, size_t rows, size_t c
 template <int HD, int KT>
 static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                              const void* vt_lo, float* msg, int B, int Np,
-                             int D, int heads, const int* c0, const int* c1, int nf0, int nf1, bool cross) {
+                             int D, int heads, const int* c0, const int* c1, int nf0, int nf1, bool cross,
+                             void* msg_hi, void* msg_lo) {
   ProfScope prof__(ctx, "tc_attention");
   const size_t rows = (size_t)2 * B * Np;
   CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
@@ -389,7 +412,7 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
     attr_set = true;
   }
   TcAttnParams p;
-  p.msg = msg; p.B = B; p.Np = Np; p.D = D; p.counts0 = c0; p.counts1 = c1; p.n_full0 = nf0; p.n_full1 = nf1;
+  p.msg = msg; p.msg_hi = reinterpret_cast<__half*>(msg_hi); p.msg_lo = reinterpret_cast<__half*>(msg_lo); p.B = B; p.Np = Np; p.D = D; p.counts0 = c0; p.counts1 = c1; p.n_full0 = nf0; p.n_full1 = nf1;
   p.cross = cross ? 1 : 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   dim3 grid(cdiv(Np, kTaQ), heads, 2 * B);
@@ -401,12 +424,13 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
 // qkv_*: fp16 planes [2*B*Np][3D] (hi, lo = x - hi, unscaled); vt_*: fp16 planes [2*B][D][Np]
 bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                          const void* vt_lo, float* msg, int B, int Np, int D,
-                         int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross) {
+                         int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross,
+                         void* msg_hi, void* msg_lo) {
   const int hd = D / heads;
   if (Np % 8) return false;   // V^T rows must be 16-byte multiples for TMA
   // hd = 16 (D = 64) rows would be 32 B; the fp32 CUDA-core kernel handles that model
-  if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross);
-  if (hd == 64) return launch_tc_attn_t<64, 32>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross);
+  if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
+  if (hd == 64) return launch_tc_attn_t<64, 32>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
   return false;
 }
 

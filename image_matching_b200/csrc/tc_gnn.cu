@@ -1,0 +1,495 @@
+// One SuperGlue message-passing layer AFTER the attention, fused into a single tcgen05 kernel (D = 128):
+//
+//     msg   = W_merge att + b_merge                      (superglue_test.py:107, MultiHeadedAttention.merge)
+//     hid   = relu(BN(W_1 [x ; msg] + b_1))              (:118-119, AttentionalPropagation.mlp, BatchNorm folded)
+//     x    += W_2 hid + b_2                              (:119, :136 residual)
+//     q|k|v = W_qkv' x + b_qkv'                          (:104-105 of the NEXT layer, heads de-interleaved)
+//
+// The unfused path runs these as four GEMM launches that round-trip msg, hid and x through HBM (~1 GB per layer at 64
+// pairs) and re-split every activation tile per output-column tile.  Here a CTA owns 128 tokens and chains the four
+// GEMMs on chip: activations stay in shared memory as fp16 hi/lo operand planes (fp16x3 split, see tc_gemm.cu /
+// tc_conv.cu), accumulators in TMEM; HBM traffic per layer is the compulsory x read + x write + attention planes in
+// + q|k|v planes out.
+//
+// Shared memory (1 CTA / SM):
+//   XM   4 x 32 KB  activation K blocks (64 columns each, [hi plane | lo plane], 128 rows x 128 B, SWIZZLE_128B K-major):
+//                   GEMM2 reads [x | msg], then hid overwrites all four, then x_new overwrites blocks 2,3;
+//                   blocks 0,1 receive the NEXT tile's x (raw fp32 via TMA, split in place) while GEMM4 still runs.
+//   RING 3 x 32 KB  operand tiles streamed by TMA: the attention planes (A of GEMM1) and every weight tile (B), the
+//                   weights pre-tiled + pre-swizzled on the host in exactly the order they are consumed (1-D bulk copies).
+// The V third of the q|k|v projection is issued with swapped operands (W_v tile as the M operand, x_new as the N operand),
+// so it lands in TMEM transposed and the V^T planes the attention kernel streams are written with 16-byte stores.
+// TMEM: two 256-column accumulator buffers (main | cross-term columns), alternated so an epilogue overlaps the next MMAs
+//   where the data flow allows (GEMM4's three column tiles, GEMM1 of the next tile).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogues / x splitter (thread = (token row, column half)).
+#include <cuda_fp16.h>
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace b200m {
+
+using namespace tc;
+
+constexpr int kGnPlane = 16384;                 // [128 rows][64 fp16]
+constexpr int kGnTile = 2 * kGnPlane;           // hi + lo
+constexpr int kGnRing = 3;
+constexpr int kGnOffRing = 4 * kGnTile;
+constexpr int kGnOffBar = kGnOffRing + kGnRing * kGnTile;
+constexpr int kGnBars = 2 * kGnRing + 6 + 4;
+constexpr size_t kGnSmem = 1024 + kGnOffBar + kGnBars * 8 + 16;
+constexpr float kGnLo = 2048.f;
+
+__device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, float lo_scale) {
+  __half2 h2[4], l2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = v[2 * j], b = v[2 * j + 1];
+    h2[j] = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2[j]);
+    l2[j] = __floats2half2_rn((a - back.x) * lo_scale, (b - back.y) * lo_scale);
+  }
+  hi = *reinterpret_cast<uint4*>(h2);
+  lo = *reinterpret_cast<uint4*>(l2);
+}
+
+__global__ void __launch_bounds__(320, 1)
+tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_constant__ CUtensorMap tm_att_lo,
+                    const __grid_constant__ CUtensorMap tm_x, GnnFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sXM = smem;
+  uint8_t* sRing = smem + kGnOffRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGnOffBar);
+  uint64_t* full = bars;                    // ring tile landed
+  uint64_t* empty = full + kGnRing;         // ring tile consumed by the MMAs
+  uint64_t* x_full = empty + kGnRing;       // raw fp32 x tile landed in XM blocks 0,1
+  uint64_t* x_free = x_full + 1;            // GEMM3 retired: XM blocks 0,1 may be overwritten
+  uint64_t* x_ready = x_free + 1;           // x split into planes
+  uint64_t* msg_ready = x_ready + 1;        // msg planes written (XM blocks 2,3)
+  uint64_t* hid_ready = msg_ready + 1;      // hid planes written (XM blocks 0..3)
+  uint64_t* xnew_ready = hid_ready + 1;     // x_new planes written (XM blocks 2,3)
+  uint64_t* acc_full = xnew_ready + 1;      // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = cdiv(p.rows, 128);
+  const int n_wtiles = 12 + 2 * p.nt4;      // weight tiles per token tile after GEMM1: GEMM2 8, GEMM3 4, GEMM4 2 per column tile
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGnRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(x_full, 1);
+    mbar_init(x_free, 1);
+    mbar_init(x_ready, 8);
+    mbar_init(msg_ready, 8);
+    mbar_init(hid_ready, 8);
+    mbar_init(xnew_ready, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_att_hi); tma_prefetch_desc(&tm_att_lo); tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int s = 0, ph = 0;
+    auto load_x = [&](int tile) {
+      mbar_expect_tx(x_full, 2 * kGnTile);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_2d(sXM + kb * kGnTile, &tm_x, x_full, kb * 64, tile * 128);
+        tma_load_2d(sXM + kb * kGnTile + kGnPlane, &tm_x, x_full, kb * 64 + 32, tile * 128);
+      }
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (it == 0) load_x(tile);
+      const uint8_t* w = p.wts;
+      for (int kb = 0; kb < 2; ++kb) {          // GEMM1: attention planes + W_merge tile per K block
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kGnTile);
+        tma_load_2d(sRing + s * kGnTile, &tm_att_hi, &full[s], kb * 64, tile * 128);
+        tma_load_2d(sRing + s * kGnTile + kGnPlane, &tm_att_lo, &full[s], kb * 64, tile * 128);
+        if (++s == kGnRing) { s = 0; ph ^= 1; }
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kGnTile);
+        bulk_load(sRing + s * kGnTile, w, kGnTile, &full[s]);
+        w += kGnTile;
+        if (++s == kGnRing) { s = 0; ph ^= 1; }
+      }
+      for (int i = 0; i < n_wtiles; ++i) {      // GEMM2 (8), GEMM3 (4), GEMM4 (2 per column tile)
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kGnTile);
+        bulk_load(sRing + s * kGnTile, w, kGnTile, &full[s]);
+        w += kGnTile;
+        if (++s == kGnRing) { s = 0; ph ^= 1; }
+      }
+      const int next = tile + gridDim.x;
+      if (next < ntiles) {                      // x of the next tile: XM blocks 0,1 are free once GEMM3 retired
+        mbar_wait(x_free, it & 1);
+        load_x(next);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one lane issues)
+    const uint32_t idesc = instr_desc(0 /*f16*/, 128, 128);
+    const uint32_t xm = smem_u32(sXM), ring = smem_u32(sRing);
+    int s = 0, ph = 0;
+    uint32_t use[2] = {0, 0};
+    // one K block (64 columns): D_main += Ahi Whi ; D_cross += Ahi Wlo + Alo Whi
+    auto block = [&](uint32_t d, uint32_t a, uint32_t w, bool first) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ah = smem_desc_sw128(a + ks * 32), al = smem_desc_sw128(a + kGnPlane + ks * 32);
+        const uint64_t wh = smem_desc_sw128(w + ks * 32), wl = smem_desc_sw128(w + kGnPlane + ks * 32);
+        const uint32_t acc = !(first && ks == 0);
+        mma_bf16(d, ah, wh, idesc, acc);
+        mma_bf16(d + 128, ah, wl, idesc, acc);
+        mma_bf16(d + 128, al, wh, idesc, 1);
+      }
+    };
+    auto acquire = [&](int b) {
+      mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1);
+      tc_fence_after();
+    };
+    // B tile from the ring, A from XM block `xb` (swapped: the ring tile is the M operand, XM the N operand, i.e. the
+    // product comes out transposed -- used for V, whose consumer wants [channel][token])
+    auto step_xm = [&](int b, int xb, bool first, bool swapped = false) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        if (swapped) block(tmem_base + b * 256, ring + s * kGnTile, xm + xb * kGnTile, first);
+        else block(tmem_base + b * 256, xm + xb * kGnTile, ring + s * kGnTile, first);
+        tc_commit(&empty[s]);
+      }
+      __syncwarp();
+      if (++s == kGnRing) { s = 0; ph ^= 1; }
+    };
+    auto publish = [&](int b) {
+      if (elect_one()) tc_commit(&acc_full[b]);
+      __syncwarp();
+      ++use[b];
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      // ---- GEMM1 (merge) -> buffer 1
+      acquire(1);
+      for (int kb = 0; kb < 2; ++kb) {
+        const int sa = s, pa = ph;
+        if (++s == kGnRing) { s = 0; ph ^= 1; }
+        mbar_wait(&full[sa], pa);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          block(tmem_base + 256, ring + sa * kGnTile, ring + s * kGnTile, kb == 0);
+          tc_commit(&empty[sa]);
+          tc_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == kGnRing) { s = 0; ph ^= 1; }
+      }
+      publish(1);
+      // ---- GEMM2 (mlp layer 1), column tile 0 -> buffer 0: x part first, msg part once the merge epilogue is done
+      mbar_wait(x_ready, it & 1);
+      acquire(0);
+      step_xm(0, 0, true);
+      step_xm(0, 1, false);
+      mbar_wait(msg_ready, it & 1);
+      tc_fence_after();
+      step_xm(0, 2, false);
+      step_xm(0, 3, false);
+      publish(0);
+      // ---- GEMM2 column tile 1 -> buffer 1
+      acquire(1);
+      for (int kb = 0; kb < 4; ++kb) step_xm(1, kb, kb == 0);
+      publish(1);
+      // ---- GEMM3 (mlp layer 2) -> buffer 0
+      mbar_wait(hid_ready, it & 1);
+      acquire(0);
+      for (int kb = 0; kb < 4; ++kb) step_xm(0, kb, kb == 0);
+      if (elect_one()) tc_commit(x_free);
+      __syncwarp();
+      publish(0);
+      // ---- GEMM4 (next layer's q|k|v), column tiles alternate buffers 0,1,0
+      if (p.nt4 > 0) {
+        mbar_wait(xnew_ready, it & 1);
+        tc_fence_after();
+        for (int nt = 0; nt < p.nt4; ++nt) {
+          const int b = nt & 1;
+          acquire(b);
+          step_xm(b, 2, true, nt == 2);
+          step_xm(b, 3, false, nt == 2);
+          publish(b);
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ epilogues (thread = (row, column half))
+    const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;
+    const int row = q4 * 32 + lane;
+    const int sw = row & 7;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    uint32_t use[2] = {0, 0};
+    auto wait_acc = [&](int b) {
+      mbar_wait(&acc_full[b], use[b] & 1);
+      tc_fence_after();
+    };
+    auto release_acc = [&](int b) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+      ++use[b];
+    };
+    auto signal = [&](uint64_t* bar) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // v[32] = main + cross / 2048 for columns [col0, col0 + 32) of buffer b
+    auto load_acc = [&](int b, int col0, float* v) {
+      float vc[32];
+      const uint32_t t = tmem_base + lane_base + b * 256 + col0;
+      tmem_ld32_issue(t, v);
+      tmem_ld32_issue(t + 128, vc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], 1.f / kGnLo, v[j]);
+    };
+    // 32 consecutive columns (starting at column c0 of the 64-column K block) of this row -> hi / lo operand planes
+    auto store_planes = [&](uint8_t* kblock, int c0, const float* v) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        gn_split8(v + 8 * g, hi, lo, kGnLo);
+        const int off = row * 128 + ((((c0 >> 3) + g) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(kblock + off) = hi;
+        *reinterpret_cast<uint4*>(kblock + kGnPlane + off) = lo;
+      }
+    };
+    auto add_bias = [&](float* v, const float* bias) {      // 32 consecutive columns, 16-byte aligned
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + g);
+        v[4 * g] += bb.x; v[4 * g + 1] += bb.y; v[4 * g + 2] += bb.z; v[4 * g + 3] += bb.w;
+      }
+    };
+    const float* b_merge = p.bias;
+    const float* b_mlp1 = p.bias + 128;
+    const float* b_mlp2 = p.bias + 384;
+    const float* b_qkv = p.bias + 512;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int r = tile * 128 + row;
+      const bool rok = r < p.rows;
+      // ---- x: raw fp32 (two 32-column boxes per K block) -> hi / lo planes, in place; this thread: K block `half`
+      mbar_wait(x_full, it & 1);
+      {
+        uint8_t* kb = sXM + half * kGnTile;
+        float e[64];
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(kb + bx * kGnPlane + row * 128 + ((q ^ sw) << 4));
+            e[bx * 32 + q * 4 + 0] = v.x; e[bx * 32 + q * 4 + 1] = v.y;
+            e[bx * 32 + q * 4 + 2] = v.z; e[bx * 32 + q * 4 + 3] = v.w;
+          }
+        __syncwarp();
+        store_planes(kb, 0, e);
+        store_planes(kb, 32, e + 32);
+      }
+      signal(x_ready);
+      // ---- epilogue 1: msg = acc + b_merge -> XM blocks 2,3 (this thread: columns half*64 .. +63)
+      wait_acc(1);
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        float v[32];
+        load_acc(1, half * 64 + ch * 32, v);
+        add_bias(v, b_merge + half * 64 + ch * 32);
+        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v);
+      }
+      release_acc(1);
+      signal(msg_ready);
+      // ---- epilogue 2: hid = relu(acc + b_1); this thread: column tile `half` (buffer `half`), 128 columns.
+      // hid overwrites [x | msg], so every GEMM2 MMA must have retired: wait for both buffers.
+      wait_acc(0);
+      wait_acc(1);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[32];
+        load_acc(half, ch * 32, v);
+        add_bias(v, b_mlp1 + half * 128 + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        store_planes(sXM + (2 * half + (ch >> 1)) * kGnTile, (ch & 1) * 32, v);
+      }
+      release_acc(0);
+      release_acc(1);
+      signal(hid_ready);
+      // ---- epilogue 3: x_new = x + acc + b_2 -> global fp32 state and XM blocks 2,3
+      // (the old x is fetched before the accumulator wait: the L2 round trip hides behind GEMM3)
+      float* xrow = p.X + (size_t)r * p.ldx + half * 64;
+      float4 xold[16];
+#pragma unroll
+      for (int g = 0; g < 16; ++g)
+        xold[g] = rok ? __ldcg(reinterpret_cast<const float4*>(xrow) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wait_acc(0);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        float v[32];
+        const int c0 = half * 64 + ch * 32;
+        load_acc(0, c0, v);
+        add_bias(v, b_mlp2 + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 old = xold[ch * 8 + g];
+          v[4 * g] += old.x; v[4 * g + 1] += old.y; v[4 * g + 2] += old.z; v[4 * g + 3] += old.w;
+          if (rok)
+            *(reinterpret_cast<float4*>(xrow) + ch * 8 + g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v);
+      }
+      release_acc(0);
+      signal(xnew_ready);
+      // ---- epilogue 4: next layer's q | k -> fp16 hi / lo planes [rows][384]; V arrives transposed (TMEM lane =
+      // channel, column = token) and goes to the V^T planes [block][128][Np] as 128-byte runs
+      for (int nt = 0; nt < p.nt4; ++nt) {
+        const int b = nt & 1;
+        wait_acc(b);
+        if (nt < 2) {
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            const int c0 = nt * 128 + half * 64 + ch * 32;         // column of q|k|v
+            load_acc(b, half * 64 + ch * 32, v);
+            add_bias(v, b_qkv + c0);
+            if (rok) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 hi, lo;
+                gn_split8(v + 8 * g, hi, lo, 1.f);              // attention planes carry the unscaled residual
+                const size_t o = (size_t)r * 384 + c0 + 8 * g;
+                *reinterpret_cast<uint4*>(p.qkv_hi + o) = hi;
+                *reinterpret_cast<uint4*>(p.qkv_lo + o) = lo;
+              }
+            }
+          }
+        } else {
+          const int t0 = tile * 128 + half * 64;                 // first token of this thread's 64-token run
+          const bool tok = t0 < p.rows;                          // rows is a multiple of 64 (Np is)
+          const int blk = t0 / p.vt_np, rr0 = t0 - blk * p.vt_np;
+          const float bv = __ldg(b_qkv + 256 + row);             // this thread's channel = TMEM lane = `row`
+          __half* dh = p.vt_hi + ((size_t)blk * 128 + row) * p.vt_np + rr0;
+          __half* dl = p.vt_lo + ((size_t)blk * 128 + row) * p.vt_np + rr0;
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            load_acc(b, half * 64 + ch * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bv;
+            if (tok) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 hi, lo;
+                gn_split8(v + 8 * g, hi, lo, 1.f);
+                *reinterpret_cast<uint4*>(dh + ch * 32 + 8 * g) = hi;
+                *reinterpret_cast<uint4*>(dl + ch * 32 + 8 * g) = lo;
+              }
+            }
+          }
+        }
+        release_acc(b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static bool gn_map_f16(CUtensorMap* m, const void* base, size_t rows, int cols, int ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool gn_map_f32(CUtensorMap* m, const void* base, size_t rows, int cols, int ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// att_hi / att_lo: attention output planes [rows][128] fp16 (lo scaled by 2048).  False if declined.
+bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* att_hi, const void* att_lo, int num_sms) {
+  if (p.rows <= 0 || (p.nt4 != 0 && p.nt4 != 3) || p.ldx % 4) return false;
+  if ((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.wts) | reinterpret_cast<uintptr_t>(p.bias) |
+       reinterpret_cast<uintptr_t>(p.qkv_hi) | reinterpret_cast<uintptr_t>(p.qkv_lo)) & 15)
+    return false;
+  ProfScope prof__(ctx, "tc_gnn_layer");
+  CUtensorMap ma_hi, ma_lo, mx;
+  if (!gn_map_f16(&ma_hi, att_hi, (size_t)p.rows, 128, 128) || !gn_map_f16(&ma_lo, att_lo, (size_t)p.rows, 128, 128) ||
+      !gn_map_f32(&mx, p.X, (size_t)p.rows, 128, p.ldx))
+    return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSmem) != cudaSuccess)
+      return false;
+    attr_set = true;
+  }
+  const int ntiles = cdiv(p.rows, 128);
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, p);
+  B200M_LAUNCH_CHECK(ctx, "tc_gnn_layer");
+  return true;
+}
+
+// ---------------------------------------------------------------- host-side weight stream
+size_t gnn_fused_weight_floats(bool with_qkv) { return (size_t)(14 + (with_qkv ? 6 : 0)) * kGnTile / 4; }
+
+// one 128-row x 64-column tile of a row-major [N][K] fp32 matrix -> hi plane | lo plane, SWIZZLE_128B K-major image
+static void gn_pack_tile(const float* W, int K, int n0, int k0, uint8_t* dst) {
+  __half* hi = reinterpret_cast<__half*>(dst);
+  __half* lo = reinterpret_cast<__half*>(dst + kGnPlane);
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 64; ++k) {
+      const float w = W[(size_t)(n0 + n) * K + k0 + k];
+      const __half h = __float2half_rn(w);
+      const size_t idx = (size_t)n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
+      hi[idx] = h;
+      lo[idx] = __float2half_rn((w - __half2float(h)) * kGnLo);
+    }
+}
+
+// W_merge [128][128], W_1 [256][256], W_2 [128][256], W_qkv [384][128] (or null): fp32 row-major, already permuted /
+// BatchNorm-folded; tiles are emitted in the order the kernel consumes them.
+void gnn_fused_pack_weights(const float* w_merge, const float* w1, const float* w2, const float* w_qkv, float* dst_f) {
+  uint8_t* dst = reinterpret_cast<uint8_t*>(dst_f);
+  for (int kb = 0; kb < 2; ++kb, dst += kGnTile) gn_pack_tile(w_merge, 128, 0, kb * 64, dst);
+  for (int nt = 0; nt < 2; ++nt)
+    for (int kb = 0; kb < 4; ++kb, dst += kGnTile) gn_pack_tile(w1, 256, nt * 128, kb * 64, dst);
+  for (int kb = 0; kb < 4; ++kb, dst += kGnTile) gn_pack_tile(w2, 256, 0, kb * 64, dst);
+  if (w_qkv)
+    for (int nt = 0; nt < 3; ++nt)
+      for (int kb = 0; kb < 2; ++kb, dst += kGnTile) gn_pack_tile(w_qkv, 128, nt * 128, kb * 64, dst);
+}
+
+}  // namespace b200m
