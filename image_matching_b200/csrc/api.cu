@@ -319,14 +319,21 @@ int pack_superglue(b200m_handle* h, Packer& P) {
       b200m_handle::Gnn& G = h->gnn[l];
       const b200m_handle::Gnn* next = l + 1 < h->cfg.n_gnn_layers ? &h->gnn[l + 1] : nullptr;
       G.fused_w_off = P.alloc(gnn_fused_weight_floats(next != nullptr));
-      G.fused_b_off = P.alloc(896);
+      G.fused_b_off = P.alloc(768);
       gnn_fused_pack_weights(P.host.data() + G.merge.w_off, P.host.data() + G.mlp1.w_off, P.host.data() + G.mlp2.w_off,
                              next ? P.host.data() + next->qkv.w_off : nullptr, P.host.data() + G.fused_w_off);
+      // bias block [256 mlp1' | 128 mlp2 | 384 next q|k|v]; the merge bias only ever enters through the mlp's first
+      // layer, so it is folded into that bias: b_1' = b_1 + W_1[:, D:2D] b_merge
       float* bb = P.host.data() + G.fused_b_off;
-      std::copy_n(P.host.data() + G.merge.b_off, 128, bb);
-      std::copy_n(P.host.data() + G.mlp1.b_off, 256, bb + 128);
-      std::copy_n(P.host.data() + G.mlp2.b_off, 128, bb + 384);
-      if (next) std::copy_n(P.host.data() + next->qkv.b_off, 384, bb + 512);
+      const float* W1 = P.host.data() + G.mlp1.w_off;
+      const float* bm = P.host.data() + G.merge.b_off;
+      for (int o = 0; o < 256; ++o) {
+        double acc = P.host[G.mlp1.b_off + o];
+        for (int k = 0; k < 128; ++k) acc += (double)W1[(size_t)o * 256 + 128 + k] * (double)bm[k];
+        bb[o] = (float)acc;
+      }
+      std::copy_n(P.host.data() + G.mlp2.b_off, 128, bb + 256);
+      if (next) std::copy_n(P.host.data() + next->qkv.b_off, 384, bb + 384);
       G.fused = true;
       G.fused_has_qkv = next != nullptr;
     }
@@ -518,7 +525,7 @@ int ot_chunk_pairs(int B, int N, int ldS) {
   return std::max(1, std::min(B, (int)((size_t)(64u << 20) / std::max<size_t>(pair_bytes, 1))));
 }
 size_t ot_part_floats(int B, int N, int M, int ldS) {
-  return ot_fused_scratch_floats(ot_chunk_pairs(B, N, ldS), N, M);
+  return ot_fused_scratch_floats(B, N, M);   // the fused path sweeps every pair in one launch
 }
 
 bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
@@ -666,6 +673,12 @@ void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters
   const int chunk = ot_chunk_pairs(all.B, all.N, all.ldS);
   const bool fused = partials && ot_fused_supported(all);
   launch_ot_init(ctx, all);
+  if (fused) {
+    // one launch per iteration over ALL pairs: the kernel is a DRAM-streaming pass (S is read once per iteration,
+    // rows arrive through per-warp bulk-copy rings), so there is nothing to gain from L2-sized micro-batches
+    launch_ot_sinkhorn_fused(ctx, all, iters, partials, h->num_sms);
+    return;
+  }
   for (int b0 = 0; b0 < all.B; b0 += chunk) {
     OtParams p = all;
     p.B = std::min(chunk, all.B - b0);
@@ -674,10 +687,6 @@ void sg_sinkhorn(b200m_handle* h, LaunchCtx& ctx, const OtParams& all, int iters
     p.v = all.v + (size_t)b0 * all.ld_uv;
     if (p.counts0) p.counts0 += b0;
     if (p.counts1) p.counts1 += b0;
-    if (fused) {
-      launch_ot_sinkhorn_fused(ctx, p, iters, partials);
-      continue;
-    }
     for (int it = 0; it < iters; ++it) {
       launch_ot_row_update(ctx, p);
       launch_ot_col_update(ctx, p);

@@ -124,7 +124,7 @@ bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo,
 // merge -> mlp -> residual -> next layer's q|k|v in one kernel; activations never leave the SM between the GEMMs
 struct GnnFusedParams {
   const uint8_t* wts;        // gnn_fused_pack_weights stream of this layer
-  const float* bias;         // [128 merge | 256 mlp1 | 128 mlp2 | 384 next q|k|v]
+  const float* bias;         // [256 mlp1 with the merge bias folded in | 128 mlp2 | 384 next q|k|v]
   float* X; int ldx;         // fp32 token state [rows][ldx] (first 128 columns), updated in place
   __half* qkv_hi; __half* qkv_lo;        // next layer's q|k|v planes [rows][384]
   __half* vt_hi; __half* vt_lo; int vt_np;   // transposed V planes [rows / vt_np][128][vt_np]
@@ -154,7 +154,7 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p);
 // fused iterations for M <= 1024 (one launch per iteration, S read once per iteration); starts from u = v = 0
 bool ot_fused_supported(const OtParams& p);
 size_t ot_fused_scratch_floats(int pairs, int N, int M);
-void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch);
+void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch, int num_sms);
 void launch_ot_write_Z(LaunchCtx& ctx, const OtParams& p, float* Z);   // dense (B,N+1,M+1), full sizes only
 // argmax over rows / columns of the final Z (computed on the fly from S,u,v)
 void launch_ot_argmax(LaunchCtx& ctx, const OtParams& p, int* idx0, float* max0, int* idx1);

@@ -3,7 +3,9 @@
 // :268-285 (match selection).  HBM/L2-bound streaming kernels: the (N+1)x(M+1) couplings matrix is never
 // materialised -- the bin row/column are the scalar alpha -- and every sweep re-reads S (L2-resident when
 // the caller micro-batches pairs).  LSE uses the same max-shifted two-pass form as torch.logsumexp.
+#include <type_traits>
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace b200m {
 
@@ -110,244 +112,242 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused Sinkhorn iteration for M <= 1024 columns: ONE launch per iteration, S is read once per iteration (the
-// unfused pair of kernels above reads it three times), two exps per element.
-//   A CTA (8 warps) owns 64 consecutive rows of one pair.
-//   prologue : v of the previous iteration is rebuilt from the per-CTA column partials the previous launch wrote
-//              (<= 17 partial rows per pair, flash-softmax style merge), so no separate combine launch is needed.
-//   rows     : a warp owns 8 rows.  A row (<= 1024 floats) lives in 32 registers per lane (8 coalesced float4 loads):
-//              row LSE with v (two-pass in registers, one exp per element) -> u_i; then y = c + u_i is folded into the
-//              warp's running per-column (max, sum) state, also in registers (branch-free online LSE: one exp per
-//              element, exp(-|y - m|), because one of the two rescale factors is always 1).
-//   epilogue : the 8 warps' column states are tree-merged through shared memory and written as ONE partial row.
-// ot_finish_kernel turns the last partials into v for the match selection.
-constexpr int kOtRowsPerWarp = 8;
-constexpr int kOtRowsPerCta = 8 * kOtRowsPerWarp;
+// Fused Sinkhorn iteration for M <= 1024 columns: ONE launch per iteration over all pairs, S is read from HBM once per
+// iteration (the unfused pair of kernels above reads it three times), 7 instructions and 2 exps per matrix element.
+//
+// No running maxima: both logsumexps are shifted by RIGOROUS upper bounds that follow from the previous half-step,
+//     u_i = log_mu_i - LSE_j'(c_ij' + v_j')  =>  c_ij + u_i <= log_mu_i - v_j <= mu_bin - v_j        (column shift)
+//     v_j = log_nu_j - LSE_i'(c_i'j + u_i')  =>  c_ij + v_j <= log_nu_j - u_i <= nu_bin - u_i(prev)  (row shift)
+// (mu_bin / nu_bin are the largest log-marginals), so no term can overflow; the shifts are lowered by kOtHeadroom = 60
+// nats so that only entries 147 nats (e^-147 of a marginal) below the bound flush to zero -- a column / row whose
+// every entry is that small is clamped to the smallest normal sum.  The first iteration (v = 0 did not come from a
+// column update) takes the exact row maximum instead.  With a shift that depends on the column (row) only, partial
+// sums of different rows simply ADD: the cross-warp / cross-CTA merges need no exps at all.
+//
+//   A CTA (8 warps) owns rows_per_cta consecutive rows of one pair (sized so that the whole grid is one resident wave:
+//   6 CTAs x 176 rows per pair at 64 pairs), a warp an eighth of them.  Rows stream in through a per-warp
+//   double-buffered cp.async.bulk ring (requested before the prologue).  A row (<= 1024 floats) is turned into
+//   z_ij = (c_ij + v_j) log2(e) in 32 registers per lane; row sum: 2^(z + r_i) -> u_i; column sums: 2^(z + q_i) with
+//   q_i = (u_i - mu_bin + 60) log2(e), accumulated in 32 registers per lane; the 8 warps' sums are added through shared
+//   memory and written as ONE partial row; the LAST CTA of a pair to finish (atomic ticket) folds the <= 17 partial rows
+//   into the new v.
 constexpr int kOtFusedMaxM = 1024;
-
-int ot_fused_parts(int N) { return cdiv(N + 1, kOtRowsPerCta); }
-
-constexpr float kOtNegBig = -1.0e30f;    // "empty" sentinel: finite, so no inf - inf can appear in the branch-free updates
+constexpr int kOtMaxParts = 20;          // CTAs (= partial rows) per pair, upper bound
+constexpr int kOtCtasPerSm = 2;
+constexpr int kOtRing = 2;                // rows in flight per warp (3 measured no faster)
+constexpr int kOtRowRingBytes = 8 * kOtRing * kOtFusedMaxM * 4;                             // 64 KB
+constexpr int kOtSmemBytes = kOtRowRingBytes + (kOtFusedMaxM + 4) * 4 + 8 * kOtRing * 8;
+constexpr float kOtNegBig = -1.0e30f;    // masked entries: 2^(anything this small) == 0
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kOtHeadroom = 60.f;      // nats
+constexpr float kOtTiny = 1.17549435e-38f;
+
+// CTAs per pair: the whole grid (parts x pairs) should be resident at once -- one wave, no tail, and the per-CTA
+// prologue / merge cost is paid as few times as possible -- but never fewer than 8 rows per warp-sized slice
+int ot_fused_parts(int pairs, int N, int num_sms) {
+  const int slots = num_sms * kOtCtasPerSm;
+  int parts = slots / (pairs > 0 ? pairs : 1);
+  parts = parts < 1 ? 1 : parts;
+  parts = parts > kOtMaxParts ? kOtMaxParts : parts;
+  const int by_rows = cdiv(N + 1, 8);
+  return parts > by_rows ? by_rows : parts;
+}
 
 __device__ __forceinline__ float ot_ex2(float x) {    // 2^x, one MUFU op (ex2.approx.ftz: rel. error 2^-22)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// (m, s) <- (m, s) (+) y : running logsumexp state, branch-free, one exp (one of the two rescale factors is 1)
-__device__ __forceinline__ void lse_push(float& m, float& s, float y) {
-  const float dlt = y - m;
-  const float e = ot_ex2(-fabsf(dlt) * kLog2e);
-  s = dlt > 0.f ? fmaf(s, e, 1.f) : s + e;
-  m = fmaxf(m, y);
-}
-// (m, s) <- (m, s) (+) (m2, s2); an empty state is (kOtNegBig, 0)
-__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
-  const float M = fmaxf(m, m2);
-  s = s * ot_ex2((m - M) * kLog2e) + s2 * ot_ex2((m2 - M) * kLog2e);
-  m = M;
-}
 
-__global__ void __launch_bounds__(256, 2) ot_iter_kernel(OtParams p, const float2* __restrict__ part_in,
-                                                        float2* __restrict__ part_out, int max_parts, int ld_part,
-                                                        int first) {
-  __shared__ __align__(16) float v_s[kOtFusedMaxM + 4];
-  __shared__ __align__(16) float2 xch[4][kOtFusedMaxM + 4];      // warp-state exchange of the tree merge (32 KB)
+__global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, float* __restrict__ partials,
+                                                                    int* __restrict__ tickets, int max_parts,
+                                                                    int ld_part, int rows_per_cta, int first) {
+  // dynamic shared memory: per-warp row ring (8 warps x 2 rows x 4 KB; later reused as the column-sum exchange),
+  // v log2(e) (4 KB + pad), mbarriers
+  extern __shared__ __align__(128) uint8_t ot_smem[];
+  float* rows_s = reinterpret_cast<float*>(ot_smem);                                   // [8][kOtRing][1024]
+  float* v2_s = reinterpret_cast<float*>(ot_smem + kOtRowRingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ot_smem + kOtRowRingBytes + (kOtFusedMaxM + 4) * 4);   // [8][kOtRing]
+  __shared__ int s_ticket;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const PairDims d = pair_dims(p, b);
   if (d.n == 0 || d.m == 0) return;                       // uniform per block
-  const int parts = cdiv(d.n + 1, kOtRowsPerCta);
+  const int parts = cdiv(d.n + 1, rows_per_cta);
   if ((int)blockIdx.x >= parts) return;                   // uniform per block
-  // ---- prologue: v_j = log_nu_j - logsumexp_i(c_ij + u_i) from the previous launch's partials (v = 0 at the start)
-  // (thread = two adjacent columns; all partial rows of a batch are fetched before any is merged, so the L2 round trips
-  // overlap instead of forming a dependent chain)
-  constexpr int kBatch = 18;
-  for (int j0 = 2 * threadIdx.x; j0 < kOtFusedMaxM + 4; j0 += 512) {
-    float va = 0.f, vb = 0.f;
-    if (!first && j0 <= d.m) {
-      const float4* col = reinterpret_cast<const float4*>(part_in + (size_t)b * max_parts * ld_part + j0);
-      const size_t ldq = (size_t)(ld_part >> 1);
-      float m0 = kOtNegBig, s0 = 0.f, m1 = kOtNegBig, s1 = 0.f;
-      for (int q0 = 0; q0 < parts; q0 += kBatch) {
-        float4 t[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q)
-          t[q] = q0 + q < parts ? __ldg(col + (size_t)(q0 + q) * ldq) : make_float4(kOtNegBig, 0.f, kOtNegBig, 0.f);
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-          lse_merge(m0, s0, t[q].x, t[q].y);
-          lse_merge(m1, s1, t[q].z, t[q].w);
-        }
-      }
-      va = (j0 == d.m ? d.nu_bin : d.norm) - (logf(s0) + m0);
-      if (j0 + 1 <= d.m) vb = (j0 + 1 == d.m ? d.nu_bin : d.norm) - (logf(s1) + m1);
-    }
-    v_s[j0] = va;
-    v_s[j0 + 1] = vb;
-  }
-  __syncthreads();
-  const int row0 = blockIdx.x * kOtRowsPerCta + warp * kOtRowsPerWarp;
-  const float xbin = p.alpha + v_s[d.m];                  // dustbin column term of every row LSE
-  // columns of this lane: 4*lane + 128*k + {0..3}.  Groups k < kfull are valid in every lane, group kfull is the ragged
-  // one (columns >= m masked with the sentinel), groups above it are skipped (warp-uniform conditions).
-  const int kfull = d.m >> 7;
-  float cm[32], cs[32];
-#pragma unroll
-  for (int q = 0; q < 32; ++q) { cm[q] = kOtNegBig; cs[q] = 0.f; }
-  float bm = kOtNegBig, bs = 0.f;                         // dustbin column state (same in every lane)
+  // ---- this warp's rows stream in through kOtRing 4 KB buffers (cp.async.bulk + mbarrier): the first ones are requested
+  // before the prologue so their DRAM latency hides behind it
+  const int rows_per_warp = rows_per_cta >> 3;            // rows_per_cta is a multiple of 8
+  const int row0 = blockIdx.x * rows_per_cta + warp * rows_per_warp;
+  const int row_end = min(row0 + rows_per_warp, d.n + 1);
   const float* S = p.S + (size_t)b * p.strideS;
+  float* wrow = rows_s + warp * kOtRing * kOtFusedMaxM;
+  const uint32_t row_bytes = (uint32_t)p.ldS * 4;
+  auto request = [&](int i) {                             // lane 0 only; the dustbin row (i == n) is not stored anywhere
+    if (i < row_end && i < d.n) {
+      uint64_t* bar = &bars[warp * kOtRing + (i - row0) % kOtRing];
+      tc::mbar_expect_tx(bar, row_bytes);
+      tc::bulk_load(wrow + ((i - row0) % kOtRing) * kOtFusedMaxM, S + (size_t)i * p.ldS, row_bytes, bar);
+    }
+  };
+  if (lane == 0) {
+    for (int q = 0; q < kOtRing; ++q) tc::mbar_init(&bars[warp * kOtRing + q], 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    for (int q = 0; q < kOtRing; ++q) request(row0 + q);
+  }
+  __syncwarp();
+  // ---- prologue: v of the previous iteration (zeros before the first one), in log2 units
+  float* vrow = p.v + (size_t)b * p.ld_uv;
+  for (int j = threadIdx.x; j < kOtFusedMaxM + 4; j += 256) v2_s[j] = j <= d.m ? vrow[j] * kLog2e : 0.f;
+  __syncthreads();
+  const float a2 = p.alpha * kLog2e;
+  const float zbin = a2 + v2_s[d.m];                      // dustbin column entry of every row, log2 units
+  const float mu_bin2 = d.mu_bin * kLog2e, head2 = kOtHeadroom * kLog2e;
+  // columns of this lane: 4*lane + 128*k + {0..3}.  Groups k < kfull are valid in every lane, group kfull is the ragged
+  // one (columns >= m masked), groups above it are skipped (warp-uniform conditions).
+  const int kfull = d.m >> 7;
+  float cs[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) cs[q] = 0.f;
+  float bs = 0.f;                                         // dustbin column sum (same in every lane)
   float* u = p.u + (size_t)b * p.ld_uv;
-  const int row_end = min(row0 + kOtRowsPerWarp, d.n + 1);
+  auto run_rows = [&](auto full_tag) {
+  constexpr bool FULL = decltype(full_tag)::value;   // every column group valid in every lane: straight-line code
   for (int i = row0; i < row_end; ++i) {
     const bool bin_row = (i == d.n);
-    const float* srow = S + (size_t)i * p.ldS + 4 * lane;
-    float c[32];
+    const int slot = (i - row0) % kOtRing;
+    const float* srow = wrow + slot * kOtFusedMaxM + 4 * lane;
+    // row shift r_i (log2 units): 60 nats above the negated bound nu_bin - u_i(prev)
+    const float u_prev = u[i];
+    if (!bin_row) tc::mbar_wait(&bars[warp * kOtRing + slot], ((i - row0) / kOtRing) & 1);
+    float z[32];                                          // z_ij = (c_ij + v_j) log2(e)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (k <= kfull) {
+      if (FULL || k <= kfull) {
         const int j = 4 * lane + 128 * k;
         float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
-        if (!bin_row && j < d.m) t = __ldg(reinterpret_cast<const float4*>(srow + 128 * k));   // rows padded to ldS
-        if (k == kfull) {
-          t.x = j < d.m ? t.x : kOtNegBig;
-          t.y = j + 1 < d.m ? t.y : kOtNegBig;
-          t.z = j + 2 < d.m ? t.z : kOtNegBig;
-          t.w = j + 3 < d.m ? t.w : kOtNegBig;
+        if (!bin_row && (FULL || j < d.m)) t = *reinterpret_cast<const float4*>(srow + 128 * k);   // rows padded to ldS
+        const float4 vv = *reinterpret_cast<const float4*>(v2_s + j);
+        z[4 * k] = fmaf(t.x, kLog2e, vv.x); z[4 * k + 1] = fmaf(t.y, kLog2e, vv.y);
+        z[4 * k + 2] = fmaf(t.z, kLog2e, vv.z); z[4 * k + 3] = fmaf(t.w, kLog2e, vv.w);
+        if (!FULL && k == kfull) {
+          z[4 * k] = j < d.m ? z[4 * k] : kOtNegBig;
+          z[4 * k + 1] = j + 1 < d.m ? z[4 * k + 1] : kOtNegBig;
+          z[4 * k + 2] = j + 2 < d.m ? z[4 * k + 2] : kOtNegBig;
+          z[4 * k + 3] = j + 3 < d.m ? z[4 * k + 3] : kOtNegBig;
         }
-        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
       }
     }
-    if (i + 1 < row_end && i + 1 < d.n) {   // pull the next row towards L1 while this one is processed
+    __syncwarp();                           // every lane has its copy of the row: the buffer can take the next one
+    if (lane == 0) request(i + kOtRing);
+    // ---- u_i = log_mu_i - logsumexp_j(c_ij + v_j), dustbin column included
+    float r, rn;                            // the shift in log2 units and in nats
+    if (first) {                            // warp-uniform: exact maximum (v = 0 carries no bound yet)
+      float mx = zbin;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (k <= kfull && 4 * lane + 128 * k < d.m)
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(srow + p.ldS + 128 * k));
+        if (FULL || k <= kfull)
+          mx = fmaxf(mx, fmaxf(fmaxf(z[4 * k], z[4 * k + 1]), fmaxf(z[4 * k + 2], z[4 * k + 3])));
+      r = -warp_max(mx);
+      rn = r * kLn2;
+    } else {
+      rn = kOtHeadroom - (d.nu_bin - u_prev);
+      r = rn * kLog2e;
     }
-    // ---- u_i = log_mu_i - logsumexp_j(c_ij + v_j), dustbin column included
-    float mx = xbin;
+    float s4[4] = {lane == 0 ? ot_ex2(zbin + r) : 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      if (k <= kfull) {
-        const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
-        mx = fmaxf(mx, fmaxf(fmaxf(c[4 * k] + vv.x, c[4 * k + 1] + vv.y), fmaxf(c[4 * k + 2] + vv.z, c[4 * k + 3] + vv.w)));
-      }
-    mx = warp_max(mx);
-    const float nmx = -mx * kLog2e;
-    float sum = lane == 0 ? ot_ex2(fmaf(xbin, kLog2e, nmx)) : 0.f;
+      if (FULL || k <= kfull) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k <= kfull) {
-        const float4 vv = *reinterpret_cast<const float4*>(v_s + 4 * lane + 128 * k);
-        sum += ot_ex2(fmaf(c[4 * k] + vv.x, kLog2e, nmx)) + ot_ex2(fmaf(c[4 * k + 1] + vv.y, kLog2e, nmx));
-        sum += ot_ex2(fmaf(c[4 * k + 2] + vv.z, kLog2e, nmx)) + ot_ex2(fmaf(c[4 * k + 3] + vv.w, kLog2e, nmx));
+        for (int e = 0; e < 4; ++e) s4[e] += ot_ex2(z[4 * k + e] + r);
       }
-    sum = warp_sum(sum);
-    const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) + mx);
+    const float sum = fmaxf(warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])), kOtTiny);
+    const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) - rn);
     if (lane == 0) u[i] = ui;
-    // ---- fold this row into the column states: y_ij = c_ij + u_i (masked columns accumulate garbage that is never read)
+    // ---- column sums: 2^(y_ij - (mu_bin - v_j - 60)) log2 e) = 2^(z_ij + q_i), q_i = (u_i - mu_bin + 60) log2 e
+    const float qi = fmaf(ui, kLog2e, head2 - mu_bin2);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      if (k <= kfull) {
+      if (FULL || k <= kfull) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) lse_push(cm[4 * k + e], cs[4 * k + e], c[4 * k + e] + ui);
+        for (int e = 0; e < 4; ++e) cs[4 * k + e] += ot_ex2(z[4 * k + e] + qi);
       }
-    lse_push(bm, bs, p.alpha + ui);
+    bs += ot_ex2(zbin + qi);
   }
-  // ---- tree merge of the 8 warps' column states: 4..7 -> 0..3, 2..3 -> 0..1, 1 -> 0
-#pragma unroll 1
-  for (int span = 4; span >= 1; span >>= 1) {
-    if (warp >= span && warp < 2 * span) {
-      float2* dst = xch[warp - span];
+  };
+  if (kfull >= 8) run_rows(std::true_type{});
+  else run_rows(std::false_type{});
+  // ---- add the 8 warps' column sums through shared memory (the exchange aliases the row ring: every warp must be
+  // done with its rows first)
+  __syncthreads();
+  float* xch = rows_s + warp * (kOtFusedMaxM + 4);          // [8][1028]
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float4* d4 = reinterpret_cast<float4*>(dst + 4 * lane + 128 * k);
-        d4[0] = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
-        d4[1] = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
-      }
-      if (lane == 0) dst[kOtFusedMaxM] = make_float2(bm, bs);
-    }
-    __syncthreads();
-    if (warp < span) {
-      const float2* src = xch[warp];
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(xch + 4 * lane + 128 * k) = make_float4(cs[4 * k], cs[4 * k + 1], cs[4 * k + 2], cs[4 * k + 3]);
+  if (lane == 0) xch[kOtFusedMaxM] = bs;
+  __syncthreads();
+  float* prow = partials + ((size_t)b * max_parts + blockIdx.x) * ld_part;
+  for (int j = threadIdx.x; j <= d.m; j += 256) {
+    const int jj = j == d.m ? kOtFusedMaxM : j;           // the dustbin column sits in slot 1024 of the exchange
+    float t = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4* s4 = reinterpret_cast<const float4*>(src + 4 * lane + 128 * k);
-        const float4 a = s4[0], bq = s4[1];
-        lse_merge(cm[4 * k], cs[4 * k], a.x, a.y);
-        lse_merge(cm[4 * k + 1], cs[4 * k + 1], a.z, a.w);
-        lse_merge(cm[4 * k + 2], cs[4 * k + 2], bq.x, bq.y);
-        lse_merge(cm[4 * k + 3], cs[4 * k + 3], bq.z, bq.w);
-      }
-      const float2 bb = src[kOtFusedMaxM];
-      lse_merge(bm, bs, bb.x, bb.y);
-    }
-    __syncthreads();
+    for (int w = 0; w < 8; ++w) t += rows_s[w * (kOtFusedMaxM + 4) + jj];
+    prow[j] = t;
   }
-  if (warp == 0) {
-    float2* prow = part_out + ((size_t)b * max_parts + blockIdx.x) * ld_part;
+  __threadfence();                       // publish this CTA's partial row before taking a ticket
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1);
+  __syncthreads();
+  if (s_ticket != parts - 1) return;
+  // ---- the last CTA of the pair folds the partial rows into v_j = log_nu_j - logsumexp_i(c_ij + u_i)
+  //      = log_nu_j - (ln(sum_j) + mu_bin - v_j(old) - 60)
+  __threadfence();
+  for (int j = threadIdx.x; j <= d.m; j += 256) {
+    const float* col = partials + (size_t)b * max_parts * ld_part + j;
+    float t = 0.f;
+    float tq[kOtMaxParts];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = 4 * lane + 128 * k;
-      if (j < d.m) {     // ld_part is a multiple of 4 and > m, so the 4-wide store stays inside the row
-        float4* dst = reinterpret_cast<float4*>(prow + j);
-        dst[0] = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
-        dst[1] = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) prow[d.m] = make_float2(bm, bs);
+    for (int q = 0; q < kOtMaxParts; ++q) tq[q] = q < parts ? __ldcg(col + (size_t)q * ld_part) : 0.f;
+#pragma unroll
+    for (int q = 0; q < kOtMaxParts; ++q) t += tq[q];
+    const float lse = logf(fmaxf(t, kOtTiny)) + ((d.mu_bin - vrow[j]) - kOtHeadroom);
+    vrow[j] = (j == d.m ? d.nu_bin : d.norm) - lse;
   }
-}
-
-// v from the partials of the last iteration
-__global__ void __launch_bounds__(256) ot_finish_kernel(OtParams p, const float2* __restrict__ partials,
-                                                        int max_parts, int ld_part) {
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  const PairDims d = pair_dims(p, b);
-  if (d.n == 0 || d.m == 0 || j > d.m) return;
-  const int parts = cdiv(d.n + 1, kOtRowsPerCta);
-  const float2* col = partials + (size_t)b * max_parts * ld_part + j;
-  float mm = kOtNegBig, ss = 0.f;
-  for (int q0 = 0; q0 < parts; q0 += 18) {
-    float2 t[18];
-#pragma unroll
-    for (int q = 0; q < 18; ++q)
-      t[q] = q0 + q < parts ? __ldg(col + (size_t)(q0 + q) * ld_part) : make_float2(kOtNegBig, 0.f);
-#pragma unroll
-    for (int q = 0; q < 18; ++q) lse_merge(mm, ss, t[q].x, t[q].y);
-  }
-  p.v[(size_t)b * p.ld_uv + j] = (j == d.m ? d.nu_bin : d.norm) - (logf(ss) + mm);
+  if (threadIdx.x == 0) tickets[b] = 0;    // ready for the next iteration (next launch)
 }
 
 bool ot_fused_supported(const OtParams& p) {
   return p.M <= kOtFusedMaxM && p.ldS % 4 == 0 && p.strideS % 4 == 0 && (reinterpret_cast<uintptr_t>(p.S) & 15) == 0;
 }
 
-// floats of scratch for `pairs` pairs: two ping-pong sets of partial rows
+// floats of scratch for `pairs` pairs: per-pair tickets + one set of partial rows
 size_t ot_fused_scratch_floats(int pairs, int N, int M) {
-  return (size_t)2 * pairs * ot_fused_parts(N) * round_up(M + 1, 4) * 2;
+  return (size_t)round_up(pairs, 64) + (size_t)pairs * kOtMaxParts * round_up(M + 1, 4);
 }
 
-// `iters` full Sinkhorn iterations (u update then v update) starting from u = v = 0; leaves u and v in p.u / p.v
-void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch) {
+// `iters` full Sinkhorn iterations (u update then v update) starting from u = v = 0 (launch_ot_init); leaves u and v in
+// p.u / p.v.  One launch per iteration over all pairs.
+void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch, int num_sms) {
   if (iters <= 0) return;
-  const int max_parts = ot_fused_parts(p.N), ld_part = round_up(p.M + 1, 4);
-  float2* part[2];
-  part[0] = reinterpret_cast<float2*>(scratch);
-  part[1] = part[0] + (size_t)p.B * max_parts * ld_part;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ot_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOtSmemBytes);
+    attr_set = true;
+  }
+  const int max_parts = ot_fused_parts(p.B, p.N, num_sms), ld_part = round_up(p.M + 1, 4);
+  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 8);
+  int* tickets = reinterpret_cast<int*>(scratch);
+  float* partials = scratch + round_up(p.B, 64);
+  cudaMemsetAsync(tickets, 0, sizeof(int) * p.B, ctx.stream);
   for (int it = 0; it < iters; ++it) {
     ProfScope prof__(ctx, "ot_iter_fused");
     dim3 grid(max_parts, p.B);
-    ot_iter_kernel<<<grid, 256, 0, ctx.stream>>>(p, part[(it + 1) & 1], part[it & 1], max_parts, ld_part, it == 0);
+    ot_iter_kernel<<<grid, 256, kOtSmemBytes, ctx.stream>>>(p, partials, tickets, max_parts, ld_part, rows_per_cta,
+                                                            it == 0);
     B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
   }
-  ProfScope prof__(ctx, "ot_finish");
-  dim3 grid(cdiv(p.M + 1, 256), p.B);
-  ot_finish_kernel<<<grid, 256, 0, ctx.stream>>>(p, part[(iters - 1) & 1], max_parts, ld_part);
-  B200M_LAUNCH_CHECK(ctx, "ot_finish");
 }
 
 // Z = couplings + u + v - norm, dense (stage API; full sizes)

@@ -36,7 +36,10 @@ constexpr int kGnRing = 3;
 constexpr int kGnOffRing = 4 * kGnTile;
 constexpr int kGnOffBar = kGnOffRing + kGnRing * kGnTile;
 constexpr int kGnBars = 2 * kGnRing + 6 + 4;
-constexpr size_t kGnSmem = 1024 + kGnOffBar + kGnBars * 8 + 16;
+constexpr int kGnOffBias = kGnOffBar + kGnBars * 8 + 16;
+constexpr int kGnBiasFloats = 256 + 128 + 256;  // mlp1 (merge bias folded in) | mlp2 | next q,k  (the V bias is per TMEM lane)
+constexpr size_t kGnSmem = kGnOffBias + kGnBiasFloats * 4;   // 232080 of the 232448 bytes a CTA may have: no alignment slack
+static_assert(kGnSmem <= 232448, "shared memory budget");
 constexpr float kGnLo = 2048.f;
 
 __device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, float lo_scale) {
@@ -55,8 +58,7 @@ __device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, 
 __global__ void __launch_bounds__(320, 1)
 tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_constant__ CUtensorMap tm_att_lo,
                     const __grid_constant__ CUtensorMap tm_x, GnnFusedParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sXM = smem;
   uint8_t* sRing = smem + kGnOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGnOffBar);
@@ -72,7 +74,10 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  float* sBias = reinterpret_cast<float*>(smem + kGnOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (smem_u32(smem) & 1023) __trap();
+  for (int i = threadIdx.x; i < kGnBiasFloats; i += blockDim.x) sBias[i] = p.bias[i];
   const int ntiles = cdiv(p.rows, 128);
   const int n_wtiles = 12 + 2 * p.nt4;      // weight tiles per token tile after GEMM1: GEMM2 8, GEMM3 4, GEMM4 2 per column tile
 
@@ -271,17 +276,16 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         *reinterpret_cast<uint4*>(kblock + kGnPlane + off) = lo;
       }
     };
-    auto add_bias = [&](float* v, const float* bias) {      // 32 consecutive columns, 16-byte aligned
+    auto add_bias = [&](float* v, const float* bias) {      // 32 consecutive columns, 16-byte aligned, shared memory
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + g);
+        const float4 bb = *(reinterpret_cast<const float4*>(bias) + g);
         v[4 * g] += bb.x; v[4 * g + 1] += bb.y; v[4 * g + 2] += bb.z; v[4 * g + 3] += bb.w;
       }
     };
-    const float* b_merge = p.bias;
-    const float* b_mlp1 = p.bias + 128;
-    const float* b_mlp2 = p.bias + 384;
-    const float* b_qkv = p.bias + 512;
+    const float* b_mlp1 = sBias;             // W_1[:, 128:] b_merge + b_1 (the merge bias is folded on the host)
+    const float* b_mlp2 = sBias + 256;
+    const float* b_qk = sBias + 384;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int r = tile * 128 + row;
@@ -304,13 +308,12 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         store_planes(kb, 32, e + 32);
       }
       signal(x_ready);
-      // ---- epilogue 1: msg = acc + b_merge -> XM blocks 2,3 (this thread: columns half*64 .. +63)
+      // ---- epilogue 1: msg = acc (b_merge lives in b_1') -> XM blocks 2,3 (this thread: columns half*64 .. +63)
       wait_acc(1);
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
         load_acc(1, half * 64 + ch * 32, v);
-        add_bias(v, b_merge + half * 64 + ch * 32);
         store_planes(sXM + (2 + half) * kGnTile, ch * 32, v);
       }
       release_acc(1);
@@ -367,7 +370,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
             float v[32];
             const int c0 = nt * 128 + half * 64 + ch * 32;         // column of q|k|v
             load_acc(b, half * 64 + ch * 32, v);
-            add_bias(v, b_qkv + c0);
+            add_bias(v, b_qk + c0);
             if (rok) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -383,7 +386,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
           const int t0 = tile * 128 + half * 64;                 // first token of this thread's 64-token run
           const bool tok = t0 < p.rows;                          // rows is a multiple of 64 (Np is)
           const int blk = t0 / p.vt_np, rr0 = t0 - blk * p.vt_np;
-          const float bv = __ldg(b_qkv + 256 + row);             // this thread's channel = TMEM lane = `row`
+          const float bv = __ldg(p.bias + kGnBiasFloats + row);  // this thread's channel = TMEM lane = `row`
           __half* dh = p.vt_hi + ((size_t)blk * 128 + row) * p.vt_np + rr0;
           __half* dl = p.vt_lo + ((size_t)blk * 128 + row) * p.vt_np + rr0;
 #pragma unroll 1
