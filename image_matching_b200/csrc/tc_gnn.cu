@@ -21,6 +21,10 @@
 // so it lands in TMEM transposed and the V^T planes the attention kernel streams are written with 16-byte stores.
 // TMEM: two 256-column accumulator buffers (main | cross-term columns), alternated so an epilogue overlaps the next MMAs
 //   where the data flow allows (GEMM4's three column tiles, GEMM1 of the next tile).
+// Outputs never leave a thread as row-per-thread stores (32 different cache lines per warp instruction, measured: the
+// LSU, not the tensor pipe, set the pace): x_new (fp32), the q / k planes and the V^T planes are staged in XM blocks
+// 0,1 (free once GEMM3 retired) in the TMA box layout and written with cp.async.bulk.tensor stores; the next tile's x
+// is fetched into the same blocks after the last store has read them.
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogues / x splitter (thread = (token row, column half)).
 #include <cuda_fp16.h>
 #include "kernels.cuh"
@@ -57,7 +61,9 @@ __device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, 
 
 __global__ void __launch_bounds__(320, 1)
 tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_constant__ CUtensorMap tm_att_lo,
-                    const __grid_constant__ CUtensorMap tm_x, GnnFusedParams p) {
+                    const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qkv_hi,
+                    const __grid_constant__ CUtensorMap tm_qkv_lo, const __grid_constant__ CUtensorMap tm_vt_hi,
+                    const __grid_constant__ CUtensorMap tm_vt_lo, GnnFusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sXM = smem;
   uint8_t* sRing = smem + kGnOffRing;
@@ -65,7 +71,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   uint64_t* full = bars;                    // ring tile landed
   uint64_t* empty = full + kGnRing;         // ring tile consumed by the MMAs
   uint64_t* x_full = empty + kGnRing;       // raw fp32 x tile landed in XM blocks 0,1
-  uint64_t* x_free = x_full + 1;            // GEMM3 retired: XM blocks 0,1 may be overwritten
+  uint64_t* x_free = x_full + 1;            // last staged store of the tile has read XM blocks 0,1: the next x may land
   uint64_t* x_ready = x_free + 1;           // x split into planes
   uint64_t* msg_ready = x_ready + 1;        // msg planes written (XM blocks 2,3)
   uint64_t* hid_ready = msg_ready + 1;      // hid planes written (XM blocks 0..3)
@@ -92,6 +98,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
     tma_prefetch_desc(&tm_att_hi); tma_prefetch_desc(&tm_att_lo); tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_qkv_hi); tma_prefetch_desc(&tm_qkv_lo); tma_prefetch_desc(&tm_vt_hi); tma_prefetch_desc(&tm_vt_lo);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -126,6 +133,10 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         w += kGnTile;
         if (++s == kGnRing) { s = 0; ph ^= 1; }
       }
+      if (it > 0) {                             // this tile's x: XM blocks 0,1 are free once the previous tile's last
+        mbar_wait(x_free, (it - 1) & 1);        // staged store has read them (GEMM1 above does not need x)
+        load_x(tile);
+      }
       for (int i = 0; i < n_wtiles; ++i) {      // GEMM2 (8), GEMM3 (4), GEMM4 (2 per column tile)
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], kGnTile);
@@ -133,18 +144,13 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         w += kGnTile;
         if (++s == kGnRing) { s = 0; ph ^= 1; }
       }
-      const int next = tile + gridDim.x;
-      if (next < ntiles) {                      // x of the next tile: XM blocks 0,1 are free once GEMM3 retired
-        mbar_wait(x_free, it & 1);
-        load_x(next);
-      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, one lane issues)
     const uint32_t idesc = instr_desc(0 /*f16*/, 128, 128);
     const uint32_t xm = smem_u32(sXM), ring = smem_u32(sRing);
     int s = 0, ph = 0;
-    uint32_t use[2] = {0, 0};
+    uint32_t use0 = 0, use1 = 0;              // scalars: a runtime-indexed array would live in local memory
     // one K block (64 columns): D_main += Ahi Whi ; D_cross += Ahi Wlo + Alo Whi
     auto block = [&](uint32_t d, uint32_t a, uint32_t w, bool first) {
 #pragma unroll
@@ -158,7 +164,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       }
     };
     auto acquire = [&](int b) {
-      mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1);
+      mbar_wait(&acc_empty[b], ((b ? use1 : use0) & 1) ^ 1);
       tc_fence_after();
     };
     // B tile from the ring, A from XM block `xb` (swapped: the ring tile is the M operand, XM the N operand, i.e. the
@@ -177,7 +183,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     auto publish = [&](int b) {
       if (elect_one()) tc_commit(&acc_full[b]);
       __syncwarp();
-      ++use[b];
+      if (b) ++use1; else ++use0;
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -216,8 +222,6 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       mbar_wait(hid_ready, it & 1);
       acquire(0);
       for (int kb = 0; kb < 4; ++kb) step_xm(0, kb, kb == 0);
-      if (elect_one()) tc_commit(x_free);
-      __syncwarp();
       publish(0);
       // ---- GEMM4 (next layer's q|k|v), column tiles alternate buffers 0,1,0
       if (p.nt4 > 0) {
@@ -239,21 +243,35 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     const int row = q4 * 32 + lane;
     const int sw = row & 7;
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
-    uint32_t use[2] = {0, 0};
+    uint32_t use0 = 0, use1 = 0;
+    const bool storer = threadIdx.x == 64;         // issues (and waits for) every staged TMA store of this CTA
     auto wait_acc = [&](int b) {
-      mbar_wait(&acc_full[b], use[b] & 1);
+      mbar_wait(&acc_full[b], (b ? use1 : use0) & 1);
       tc_fence_after();
     };
     auto release_acc = [&](int b) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
-      ++use[b];
+      if (b) ++use1; else ++use0;
     };
     auto signal = [&](uint64_t* bar) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
+    };
+    auto epi_sync = [&](int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); };   // the 8 epilogue warps
+    // staging protocol for XM blocks 0,1: stage_begin() before the first write of a stage (the previous stage's TMA
+    // stores must have read the buffer), stage_end() after the last write (makes the writes visible to the async proxy
+    // and lets the storer issue)
+    auto stage_begin = [&]() {
+      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      epi_sync(2);
+    };
+    auto stage_end = [&]() {
+      fence_proxy_async();
+      epi_sync(1);
     };
     // v[32] = main + cross / 2048 for columns [col0, col0 + 32) of buffer b
     auto load_acc = [&](int b, int col0, float* v) {
@@ -265,12 +283,12 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], 1.f / kGnLo, v[j]);
     };
-    // 32 consecutive columns (starting at column c0 of the 64-column K block) of this row -> hi / lo operand planes
-    auto store_planes = [&](uint8_t* kblock, int c0, const float* v) {
+    // 32 consecutive columns (starting at column c0 of the 64-column K block) of this row -> hi / lo planes
+    auto store_planes = [&](uint8_t* kblock, int c0, const float* v, float lo_scale) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 hi, lo;
-        gn_split8(v + 8 * g, hi, lo, kGnLo);
+        gn_split8(v + 8 * g, hi, lo, lo_scale);
         const int off = row * 128 + ((((c0 >> 3) + g) ^ sw) << 4);
         *reinterpret_cast<uint4*>(kblock + off) = hi;
         *reinterpret_cast<uint4*>(kblock + kGnPlane + off) = lo;
@@ -304,8 +322,8 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
             e[bx * 32 + q * 4 + 2] = v.z; e[bx * 32 + q * 4 + 3] = v.w;
           }
         __syncwarp();
-        store_planes(kb, 0, e);
-        store_planes(kb, 32, e + 32);
+        store_planes(kb, 0, e, kGnLo);
+        store_planes(kb, 32, e + 32, kGnLo);
       }
       signal(x_ready);
       // ---- epilogue 1: msg = acc (b_merge lives in b_1') -> XM blocks 2,3 (this thread: columns half*64 .. +63)
@@ -314,7 +332,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
         load_acc(1, half * 64 + ch * 32, v);
-        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v);
+        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v, kGnLo);
       }
       release_acc(1);
       signal(msg_ready);
@@ -329,14 +347,15 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         add_bias(v, b_mlp1 + half * 128 + ch * 32);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        store_planes(sXM + (2 * half + (ch >> 1)) * kGnTile, (ch & 1) * 32, v);
+        store_planes(sXM + (2 * half + (ch >> 1)) * kGnTile, (ch & 1) * 32, v, kGnLo);
       }
       release_acc(0);
       release_acc(1);
       signal(hid_ready);
-      // ---- epilogue 3: x_new = x + acc + b_2 -> global fp32 state and XM blocks 2,3
+      // ---- epilogue 3: x_new = x + acc + b_2 -> operand planes in XM blocks 2,3 and, as fp32 in the TMA box layout of
+      // the x load, into XM blocks 0,1 (free: GEMM3 has retired), from where one bulk tensor store writes the tile.
       // (the old x is fetched before the accumulator wait: the L2 round trip hides behind GEMM3)
-      float* xrow = p.X + (size_t)r * p.ldx + half * 64;
+      const float* xrow = p.X + (size_t)r * p.ldx + half * 64;
       float4 xold[16];
 #pragma unroll
       for (int g = 0; g < 16; ++g)
@@ -345,70 +364,82 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
-        const int c0 = half * 64 + ch * 32;
-        load_acc(0, c0, v);
-        add_bias(v, b_mlp2 + c0);
+        load_acc(0, half * 64 + ch * 32, v);
+        add_bias(v, b_mlp2 + half * 64 + ch * 32);
+        uint8_t* box = sXM + half * kGnTile + ch * kGnPlane + row * 128;     // fp32 box: columns half*64 + ch*32 .. +31
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 old = xold[ch * 8 + g];
           v[4 * g] += old.x; v[4 * g + 1] += old.y; v[4 * g + 2] += old.z; v[4 * g + 3] += old.w;
-          if (rok)
-            *(reinterpret_cast<float4*>(xrow) + ch * 8 + g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          *reinterpret_cast<float4*>(box + ((g ^ sw) << 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
-        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v);
+        store_planes(sXM + (2 + half) * kGnTile, ch * 32, v, kGnLo);
       }
       release_acc(0);
       signal(xnew_ready);
+      stage_end();
+      if (storer) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_store_2d(&tm_x, sXM + kb * kGnTile, kb * 64, tile * 128);
+          tma_store_2d(&tm_x, sXM + kb * kGnTile + kGnPlane, kb * 64 + 32, tile * 128);
+        }
+        tma_store_commit();
+      }
+      __syncwarp();
       // ---- epilogue 4: next layer's q | k -> fp16 hi / lo planes [rows][384]; V arrives transposed (TMEM lane =
-      // channel, column = token) and goes to the V^T planes [block][128][Np] as 128-byte runs
+      // channel, column = token) -> V^T planes [block][128][Np].  Each 128-column tile is staged in XM blocks 0,1
+      // (block = 64 columns: hi plane | lo plane, the layout of a SWIZZLE_128B box) and stored by TMA.
       for (int nt = 0; nt < p.nt4; ++nt) {
         const int b = nt & 1;
         wait_acc(b);
-        if (nt < 2) {
+        const float bv = nt == 2 ? __ldg(p.bias + kGnBiasFloats + row) : 0.f;   // V: this thread's channel = `row`
 #pragma unroll 1
-          for (int ch = 0; ch < 2; ++ch) {
-            float v[32];
-            const int c0 = nt * 128 + half * 64 + ch * 32;         // column of q|k|v
-            load_acc(b, half * 64 + ch * 32, v);
-            add_bias(v, b_qk + c0);
-            if (rok) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 hi, lo;
-                gn_split8(v + 8 * g, hi, lo, 1.f);              // attention planes carry the unscaled residual
-                const size_t o = (size_t)r * 384 + c0 + 8 * g;
-                *reinterpret_cast<uint4*>(p.qkv_hi + o) = hi;
-                *reinterpret_cast<uint4*>(p.qkv_lo + o) = lo;
-              }
-            }
-          }
-        } else {
-          const int t0 = tile * 128 + half * 64;                 // first token of this thread's 64-token run
-          const bool tok = t0 < p.rows;                          // rows is a multiple of 64 (Np is)
-          const int blk = t0 / p.vt_np, rr0 = t0 - blk * p.vt_np;
-          const float bv = __ldg(p.bias + kGnBiasFloats + row);  // this thread's channel = TMEM lane = `row`
-          __half* dh = p.vt_hi + ((size_t)blk * 128 + row) * p.vt_np + rr0;
-          __half* dl = p.vt_lo + ((size_t)blk * 128 + row) * p.vt_np + rr0;
-#pragma unroll 1
-          for (int ch = 0; ch < 2; ++ch) {
-            float v[32];
-            load_acc(b, half * 64 + ch * 32, v);
+        for (int ch = 0; ch < 2; ++ch) {
+          float v[32];
+          load_acc(b, half * 64 + ch * 32, v);
+          if (nt < 2) {
+            add_bias(v, b_qk + nt * 128 + half * 64 + ch * 32);
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bv;
-            if (tok) {
+          }
+          if (ch == 0) stage_begin();
+          store_planes(sXM + half * kGnTile, ch * 32, v, 1.f);      // attention planes carry the unscaled residual
+        }
+        release_acc(b);
+        stage_end();
+        if (storer) {
+          if (nt < 2) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 hi, lo;
-                gn_split8(v + 8 * g, hi, lo, 1.f);
-                *reinterpret_cast<uint4*>(dh + ch * 32 + 8 * g) = hi;
-                *reinterpret_cast<uint4*>(dl + ch * 32 + 8 * g) = lo;
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_store_2d(&tm_qkv_hi, sXM + kb * kGnTile, nt * 128 + kb * 64, tile * 128);
+              tma_store_2d(&tm_qkv_lo, sXM + kb * kGnTile + kGnPlane, nt * 128 + kb * 64, tile * 128);
+            }
+          } else {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                       // 64-token runs (64 | Np: a run stays in one block)
+              const int t0 = tile * 128 + hf * 64;
+              if (t0 < p.rows) {
+                const int blk = t0 / p.vt_np, rr0 = t0 - blk * p.vt_np;
+                tma_store_2d(&tm_vt_hi, sXM + hf * kGnTile, rr0, blk * 128);
+                tma_store_2d(&tm_vt_lo, sXM + hf * kGnTile + kGnPlane, rr0, blk * 128);
               }
             }
           }
+          tma_store_commit();
         }
-        release_acc(b);
+        __syncwarp();
       }
+      // ---- the staging blocks may take the next tile's x once the last store has read them
+      if (storer) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(x_free);
+      }
+      __syncwarp();
     }
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // all stores complete before exit
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -448,9 +479,13 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
        reinterpret_cast<uintptr_t>(p.qkv_hi) | reinterpret_cast<uintptr_t>(p.qkv_lo)) & 15)
     return false;
   ProfScope prof__(ctx, "tc_gnn_layer");
-  CUtensorMap ma_hi, ma_lo, mx;
+  if (p.vt_np % 64 || p.rows % 64) return false;
+  CUtensorMap ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo;
+  const size_t vt_rows = (size_t)(p.rows / p.vt_np) * 128;
   if (!gn_map_f16(&ma_hi, att_hi, (size_t)p.rows, 128, 128) || !gn_map_f16(&ma_lo, att_lo, (size_t)p.rows, 128, 128) ||
-      !gn_map_f32(&mx, p.X, (size_t)p.rows, 128, p.ldx))
+      !gn_map_f32(&mx, p.X, (size_t)p.rows, 128, p.ldx) ||
+      !gn_map_f16(&mq_hi, p.qkv_hi, (size_t)p.rows, 384, 384) || !gn_map_f16(&mq_lo, p.qkv_lo, (size_t)p.rows, 384, 384) ||
+      !gn_map_f16(&mv_hi, p.vt_hi, vt_rows, p.vt_np, p.vt_np) || !gn_map_f16(&mv_lo, p.vt_lo, vt_rows, p.vt_np, p.vt_np))
     return false;
   static bool attr_set = false;
   if (!attr_set) {
@@ -460,7 +495,7 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
   }
   const int ntiles = cdiv(p.rows, 128);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, p);
+  tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gnn_layer");
   return true;
 }
