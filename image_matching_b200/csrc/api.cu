@@ -93,6 +93,7 @@ struct b200m_handle {
   bool use_tc = true;            // tcgen05 fp16x3 convolutions (B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)
   bool use_tc_attn = true;       // tcgen05 flash attention (B200M_ATTN_IMPL=simt selects the fp32 CUDA-core kernel)
   bool use_tc_gemm = true;       // tcgen05 linear layers (B200M_GEMM_IMPL=simt selects the fp32 CUDA-core GEMM)
+  bool use_fused_stem = true;    // first conv computed inside the second conv's kernel (B200M_STEM_IMPL=unfused: two kernels)
   bool use_fused_gnn = true;     // fused merge/mlp/residual/q|k|v layer kernel (B200M_GNN_IMPL=unfused: four GEMM launches)
   int num_sms = 148;
 };
@@ -437,8 +438,21 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
   if (h->use_tc) {
     int* ovf = w.overflow ? w.overflow + 1 : nullptr;
     // fp16 hi/lo planes, C8-planar: channel units per image = C / 8
-    launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, w.p0_lo, n, d.H, d.W);
-    run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H, d.W, true, ovf);        // -> 64 x H2 x W2
+    // first conv (1 -> 64) fused into the second one's operand producer: no full-resolution 64-channel map in HBM
+    bool stem = h->use_fused_stem;
+    if (stem) {
+      TcConvParams p;
+      const ConvLayer& L = h->c1b;
+      p.in_hi = nullptr; p.in_lo = nullptr; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
+      p.out_hi = w.p1; p.out_lo = w.p1_lo; p.out_c4_total = 8; p.out_c4_off = 0; p.overflow = ovf;
+      p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = d.H; p.W = d.W; p.relu = 1; p.pool = 1; p.ks = 3;
+      p.img = images; p.c1_w = h->d_w + h->conv1_w; p.c1_b = h->d_w + h->conv1_b;
+      stem = launch_tc_conv(ctx, p, h->num_sms);
+    }
+    if (!stem) {
+      launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, w.p0_lo, n, d.H, d.W);
+      run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H, d.W, true, ovf);      // -> 64 x H2 x W2
+    }
     run_conv_tc(h, ctx, h->c2a, w.p1, w.p1_lo, w.p0, w.p0_lo, 8, n, d.H2, d.W2, false, ovf);
     run_conv_tc(h, ctx, h->c2b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H2, d.W2, true, ovf);      // -> 64 x H3 x W3
     run_conv_tc(h, ctx, h->c3a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.H3, d.W3, false, ovf);    // 128 ch
@@ -747,6 +761,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_tc_attn = !(impl && strcmp(impl, "simt") == 0);
   impl = getenv("B200M_GEMM_IMPL");
   h->use_tc_gemm = !(impl && strcmp(impl, "simt") == 0);
+  impl = getenv("B200M_STEM_IMPL");
+  h->use_fused_stem = !(impl && strcmp(impl, "unfused") == 0);
   impl = getenv("B200M_GNN_IMPL");
   h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
   *out = h;

@@ -116,7 +116,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
                     TcAttnParams p) {
   using SM = TcAttnSmem<HD, KT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + SM::OFF_KV;
   uint8_t* sP = smem + SM::OFF_P;

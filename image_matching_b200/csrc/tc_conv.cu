@@ -24,6 +24,7 @@
 //                                {main, cross} x 64) = 512 TMEM columns, double-buffered; NB=128: single-buffered.
 //   warps 2..5  epilogue       - tcgen05.ld accumulators -> +bias, ReLU, optional 2x2 max-pool (warp shuffles),
 //                                split into fp16 hi/lo planes for the next layer, coalesced 16-byte stores.
+#include <cstring>
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -40,7 +41,7 @@ constexpr int kTcNA = 3;                          // A stages
 
 // KS = 3: 3x3 conv, 18x18 halo tile, nine taps by descriptor shifts.  KS = 1: the 1x1 heads (convPb / convDb),
 // the same pipeline with a 16x16 tile and one tap per K block.
-template <int NB, int KS>
+template <int NB, int KS, bool FUSE1 = false>
 struct TcConvSmem {
   static constexpr int HALO = kTcTile + KS - 1;
   static constexpr int TAPS = KS * KS;
@@ -55,18 +56,30 @@ struct TcConvSmem {
   static constexpr int BAR_OFF = kTcNA * A_STAGE + NBS * B_SLOT;
   static constexpr int N_BARS = 2 * kTcNA + 2 * NBS + 4;
   static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
-  static constexpr size_t BYTES = 128 /*align slack*/ + BAR_OFF + N_BARS * 8 + 16;
+  // fused first layer: 20x20 image patch + the 1->64 stem weights [9][64] + bias [64] (fp32)
+  static constexpr int STEM_OFF = (BAR_OFF + N_BARS * 8 + 16 + 15) & ~15;
+  static constexpr int STEM_BYTES = FUSE1 ? (400 + 9 * 64 + 64) * 4 : 0;
+  static constexpr size_t BYTES = 128 /*align slack*/ + STEM_OFF + STEM_BYTES;
+  static constexpr int STEM_WARPS = 8;
+  static constexpr int THREADS = FUSE1 ? 192 + 32 * STEM_WARPS : 192;
 };
 
-template <int NB, bool POOL, int KS>
-__global__ void __launch_bounds__(192, 1)
+// FUSE1: the layer's input is not read from memory but computed on the fly from the grayscale image: warps 6..13 run
+// the network's first convolution (1 -> 64 channels, 3x3, BatchNorm folded, ReLU; unet_parts.py:10-24 first half) for
+// the 18x18 halo of the tile on the CUDA cores and write it, already split into fp16 hi / lo planes, straight into the
+// A stage the MMA warp consumes (same order of fp32 operations as conv1_direct -> bit-identical activations).  This
+// removes the 157 MB / image-pair activation round trip through HBM of the unfused pair of kernels.
+template <int NB, bool POOL, int KS, bool FUSE1>
+__global__ void __launch_bounds__(FUSE1 ? 448 : 192, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
-  using SM = TcConvSmem<NB, KS>;
+  using SM = TcConvSmem<NB, KS, FUSE1>;
   constexpr int kTcNB = SM::NBS;
   constexpr int kTcHalo = SM::HALO, kTcPlaneB = SM::PLANE_B, kTcAPlane = SM::A_PLANE, kTcAStage = SM::A_STAGE;
   constexpr int kTaps = SM::TAPS, kPad = KS / 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the address space, so every access
+  // below compiles to LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTcNA * kTcAStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -85,7 +98,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int total = p.n * tiles_y * tiles_x * ncb;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], FUSE1 ? SM::STEM_WARPS : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kTcNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
@@ -121,13 +134,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                   p.in_c8_off + kb * kTcKbGroups, img);
       if (++sa == kTcNA) { sa = 0; pa ^= 1; }
     };
-    if ((int)blockIdx.x < total) issue_A(blockIdx.x, 0);
+    if (!FUSE1 && (int)blockIdx.x < total) issue_A(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int cb = tile % ncb;
       for (int kb = 0; kb < nkb; ++kb) {
         // keep the activation halo one K block ahead of the weight slabs
-        if (kb + 1 < nkb) issue_A(tile, kb + 1);
-        else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
+        if (!FUSE1) {
+          if (kb + 1 < nkb) issue_A(tile, kb + 1);
+          else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
+        }
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)(cb * nkb + kb) * kTaps * SM::B_SLOT;
         for (int tap = 0; tap < kTaps; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
@@ -139,11 +154,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    const uint32_t idesc = instr_desc(0 /*f16*/, 128, NB);
+    // Two MMAs per product instead of three: the weight slab keeps, per 16-byte K chunk, the NB hi rows followed by the
+    // NB lo rows, so [W_hi ; W_lo] is ONE N = 2*NB operand and  A_hi x [W_hi ; W_lo]^T  lands as [main | cross] in
+    // adjacent TMEM columns; only A_lo x W_hi^T remains.  Same tensor-pipe time, but 14 (NB = 64) / 20 (NB = 128) KB of
+    // shared-memory operand reads per K step instead of 18 / 24 -- the N = 64 / 128 MMAs were shared-memory-bandwidth
+    // bound (A 4 KB + B 2..4 KB per 34..68 tensor cycles at 128 B/clk).
+    const uint32_t idesc2 = instr_desc(0 /*f16*/, 128, 2 * NB);
+    const uint32_t idesc1 = instr_desc(0 /*f16*/, 128, NB);
     const uint64_t a_hi32 = (smem_desc_nosw(0, kTcPlaneB, kTcHalo * 16) >> 32) << 32;
     const uint32_t a_lo16 = (uint32_t)((kTcPlaneB >> 4) << 16);
-    const uint64_t b_hi32 = (smem_desc_nosw(0, NB * 16, 128) >> 32) << 32;
-    const uint32_t b_lo16 = (uint32_t)(((NB * 16) >> 4) << 16);
+    const uint64_t b_hi32 = (smem_desc_nosw(0, 2 * NB * 16, 128) >> 32) << 32;
+    const uint32_t b_lo16 = (uint32_t)(((2 * NB * 16) >> 4) << 16);
     int sa = 0, pa = 0, sb = 0, pb = 0, lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int buf = SM::ACC_BUFS == 2 ? (lt & 1) : 0;
@@ -163,9 +184,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t b_off = b_base + ks * 2 * NB * 16;
-            const uint64_t bh = b_hi32 | (uint64_t)(b_lo16 | ((b_off >> 4) & 0x3FFF));
-            const uint64_t bl = b_hi32 | (uint64_t)(b_lo16 | (((b_off + SM::B_PLANE) >> 4) & 0x3FFF));
+            const uint32_t b_off = b_base + ks * 2 * (2 * NB * 16);     // K chunks 2ks, 2ks+1: [hi rows | lo rows] each
+            const uint64_t bw = b_hi32 | (uint64_t)(b_lo16 | ((b_off >> 4) & 0x3FFF));
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
               const uint32_t a_off = a_base + ks * 2 * kTcPlaneB + (ky * kTcHalo + kx + sub * 8) * 16;
@@ -173,9 +193,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const uint64_t al = a_hi32 | (uint64_t)(a_lo16 | (((a_off + kTcAPlane) >> 4) & 0x3FFF));
               const uint32_t d = d0 + sub * (2 * NB);      // main accumulator; cross accumulator at d + NB
               const uint32_t acc = (kb | tap | ks) != 0;
-              mma_bf16(d, ah, bh, idesc, acc);          // kind::f16 (format selected by idesc = fp16)
-              mma_bf16(d + NB, ah, bl, idesc, acc);
-              mma_bf16(d + NB, al, bh, idesc, 1);
+              mma_bf16(d, ah, bw, idesc2, acc);         // kind::f16: [A_hi W_hi^T | A_hi W_lo^T]
+              mma_bf16(d + NB, al, bw, idesc1, 1);      // + A_lo W_hi^T (first NB rows of the chunk)
             }
           }
           tc_commit(&b_empty[sb]);
@@ -188,7 +207,76 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         if (++sa == kTcNA) { sa = 0; pa ^= 1; }
       }
     }
-  } else if (warp >= 2) {
+  } else if (FUSE1 && warp >= 6) {
+    // ------------------------------------------------------------------ stem: first convolution -> A stages
+    float* patch = reinterpret_cast<float*>(smem + SM::STEM_OFF);       // 20 x 20 image pixels around the tile
+    float4* w1 = reinterpret_cast<float4*>(patch + 400);                // [9 taps][16 groups of 4 channels]
+    float4* b1 = w1 + 9 * 16;                                            // [16]
+    constexpr int kStemT = 32 * SM::STEM_WARPS;
+    const int t = threadIdx.x - 192;                                     // 0..kStemT-1
+    for (int i = t; i < 9 * 16; i += kStemT) w1[i] = reinterpret_cast<const float4*>(p.c1_w)[i];
+    if (t < 16) b1[t] = reinterpret_cast<const float4*>(p.c1_b)[t];
+    int sa = 0, pa = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int cb, x0, y0, img;
+      decode(tile, cb, x0, y0, img);
+      asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");          // everyone is done with the previous patch
+      const float* im = p.img + (size_t)img * p.H * p.W;
+      for (int i = t; i < 400; i += kStemT) {
+        const int r = i / 20, c = i - r * 20;
+        const int gy = y0 - 2 + r, gx = x0 - 2 + c;
+        patch[i] = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? __ldg(im + (size_t)gy * p.W + gx) : 0.f;
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");
+      for (int kb = 0; kb < nkb; ++kb) {                                 // nkb == 2: channels kb*32 .. +31
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        uint8_t* dst = sA + sa * kTcAStage;
+        for (int i = t; i < kTcKbGroups * kTcHalo * kTcHalo; i += kStemT) {
+          const int g = i / (kTcHalo * kTcHalo), px = i - g * (kTcHalo * kTcHalo);   // 8-channel unit, halo pixel
+          const int py = px / kTcHalo, pxx = px - py * kTcHalo;
+          const int gy = y0 - 1 + py, gx = x0 - 1 + pxx;
+          uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;                // outside the image: the NEXT conv's zero padding
+          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+            float v[9];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = patch[(py + ky) * 20 + pxx + kx];
+            const int g4 = (kb * kTcKbGroups + g) * 2;                   // first 4-channel group of this unit
+            float e[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float4 a = b1[g4 + hh];
+#pragma unroll
+              for (int tp = 0; tp < 9; ++tp) {
+                const float4 wv = w1[tp * 16 + g4 + hh];
+                a.x = fmaf(v[tp], wv.x, a.x); a.y = fmaf(v[tp], wv.y, a.y);
+                a.z = fmaf(v[tp], wv.z, a.z); a.w = fmaf(v[tp], wv.w, a.w);
+              }
+              e[4 * hh] = fmaxf(a.x, 0.f); e[4 * hh + 1] = fmaxf(a.y, 0.f);
+              e[4 * hh + 2] = fmaxf(a.z, 0.f); e[4 * hh + 3] = fmaxf(a.w, 0.f);
+            }
+            __half2 h2[4], l2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __half ha = __float2half_rn(e[2 * j]), hb = __float2half_rn(e[2 * j + 1]);
+              h2[j] = __halves2half2(ha, hb);
+              l2[j] = __halves2half2(__float2half_rn((e[2 * j] - __half2float(ha)) * kLoScale),
+                                     __float2half_rn((e[2 * j + 1] - __half2float(hb)) * kLoScale));
+            }
+            hi = *reinterpret_cast<uint4*>(h2);
+            lo = *reinterpret_cast<uint4*>(l2);
+          }
+          *reinterpret_cast<uint4*>(dst + g * kTcPlaneB + px * 16) = hi;
+          *reinterpret_cast<uint4*>(dst + kTcAPlane + g * kTcPlaneB + px * 16) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == kTcNA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
     // ------------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)
     const int w4 = warp & 3;
     const int m = w4 * 32 + lane;
@@ -292,16 +380,21 @@ static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H,
   return r == CUDA_SUCCESS;
 }
 
-template <int NB, bool POOL, int KS>
+template <int NB, bool POOL, int KS, bool FUSE1 = false>
 static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
-  using SM = TcConvSmem<NB, KS>;
-  ProfScope prof__(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
+  using SM = TcConvSmem<NB, KS, FUSE1>;
+  ProfScope prof__(ctx, KS == 3 ? (FUSE1 ? "tc_conv3x3_stem" : "tc_conv3x3") : "tc_conv1x1");
   const int c8_total = p.in_c8_total > 0 ? p.in_c8_total : p.cin / kTcUnitCh;
   CUtensorMap tm_hi, tm_lo;
-  if (!make_act_map(&tm_hi, p.in_hi, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
-  if (!make_act_map(&tm_lo, p.in_lo, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
+  if (FUSE1) {
+    memset(&tm_hi, 0, sizeof(tm_hi));   // the activation maps are not used: the stem warps produce the A operand
+    memset(&tm_lo, 0, sizeof(tm_lo));
+  } else {
+    if (!make_act_map(&tm_hi, p.in_hi, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
+    if (!make_act_map(&tm_lo, p.in_lo, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
+  }
   static bool attr_set = false;
-  auto kern = tc_conv_kernel<NB, POOL, KS>;
+  auto kern = tc_conv_kernel<NB, POOL, KS, FUSE1>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess)
       return false;
@@ -309,7 +402,7 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   }
   const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
   const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, 192, SM::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
+  kern<<<grid, SM::THREADS, SM::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
   B200M_LAUNCH_CHECK(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
   return true;
 }
@@ -319,6 +412,10 @@ bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   if (p.ks == 1) {
     if (p.pool) return false;
     return p.nb == 64 ? launch_tc_t<64, false, 1>(ctx, p, num_sms) : launch_tc_t<128, false, 1>(ctx, p, num_sms);
+  }
+  if (p.img) {   // fused first layer (image -> 64 channels) in front of a 64 -> 64 pooled layer
+    if (p.nb != 64 || p.cin != 64 || !p.pool || !p.c1_w || !p.c1_b) return false;
+    return launch_tc_t<64, true, 3, true>(ctx, p, num_sms);
   }
   if (p.nb == 64) return p.pool ? launch_tc_t<64, true, 3>(ctx, p, num_sms) : launch_tc_t<64, false, 3>(ctx, p, num_sms);
   return p.pool ? launch_tc_t<128, true, 3>(ctx, p, num_sms) : launch_tc_t<128, false, 3>(ctx, p, num_sms);
@@ -330,8 +427,8 @@ size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks) {
 }
 
 // Host-side weight packing: w[cout][cin][ks][ks] (BatchNorm already folded) ->
-// [cout_blk][kblock(32 ch)][tap][plane hi/lo][unit of 8 ch][n][8 halves], i.e. the exact shared-memory image of a
-// B slab; hi = fp16(w), lo = fp16((w - hi) * 2048).
+// [cout_blk][kblock(32 ch)][tap][unit of 8 ch][plane hi/lo][n][8 halves], i.e. the exact shared-memory image of a
+// B slab (per K chunk the nb hi rows then the nb lo rows: one N = 2*nb operand); hi = fp16(w), lo = fp16((w - hi) * 2048).
 void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, int ks, float* dst_f) {
   __half* dst = reinterpret_cast<__half*>(dst_f);
   const int ncb = cout_pad / nb, nkb = cin / 32, taps = ks * ks;
@@ -345,10 +442,9 @@ void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int 
               const float v = o < cout ? (float)w[((size_t)o * cin + ci) * taps + tap] : 0.f;
               const __half hi = __float2half_rn(v);
               const __half lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
-              const size_t slab = ((size_t)(cb * nkb + kb) * taps + tap) * 2;
-              const size_t per_plane = (size_t)kTcKbGroups * nb * kTcUnitCh;
-              dst[(slab + 0) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = hi;
-              dst[(slab + 1) * per_plane + ((size_t)kc * nb + n) * kTcUnitCh + j] = lo;
+              const size_t slab = ((size_t)(cb * nkb + kb) * taps + tap) * 2 * kTcKbGroups * nb * kTcUnitCh;
+              dst[slab + (((size_t)kc * 2 + 0) * nb + n) * kTcUnitCh + j] = hi;
+              dst[slab + (((size_t)kc * 2 + 1) * nb + n) * kTcUnitCh + j] = lo;
             }
 }
 

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(320, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w_hi,
                const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmBarOff);
   uint64_t* full = bars;                       // TMA bytes landed
   uint64_t* split = full + kGemmStages;        // A split into hi / lo

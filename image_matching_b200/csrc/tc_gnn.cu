@@ -148,18 +148,26 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, one lane issues)
     const uint32_t idesc = instr_desc(0 /*f16*/, 128, 128);
+    const uint32_t idesc256 = instr_desc(0 /*f16*/, 128, 256);
     const uint32_t xm = smem_u32(sXM), ring = smem_u32(sRing);
     int s = 0, ph = 0;
     uint32_t use0 = 0, use1 = 0;              // scalars: a runtime-indexed array would live in local memory
-    // one K block (64 columns): D_main += Ahi Whi ; D_cross += Ahi Wlo + Alo Whi
-    auto block = [&](uint32_t d, uint32_t a, uint32_t w, bool first) {
+    // one K block (64 columns): D_main += Ahi Whi ; D_cross += Ahi Wlo + Alo Whi.  The hi and lo planes of a weight
+    // tile are contiguous (256 rows of 128 B), so [Whi ; Wlo] is one N = 256 operand whose product with Ahi lands as
+    // [main | cross] in adjacent TMEM columns: two MMAs per K step instead of three (fewer shared-memory operand reads).
+    // wide_n = false: `w` is the M-side operand's partner in the swapped (transposed) product and cannot be widened.
+    auto block = [&](uint32_t d, uint32_t a, uint32_t w, bool first, bool wide_n) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint64_t ah = smem_desc_sw128(a + ks * 32), al = smem_desc_sw128(a + kGnPlane + ks * 32);
         const uint64_t wh = smem_desc_sw128(w + ks * 32), wl = smem_desc_sw128(w + kGnPlane + ks * 32);
         const uint32_t acc = !(first && ks == 0);
-        mma_bf16(d, ah, wh, idesc, acc);
-        mma_bf16(d + 128, ah, wl, idesc, acc);
+        if (wide_n) {
+          mma_bf16(d, ah, wh, idesc256, acc);
+        } else {
+          mma_bf16(d, ah, wh, idesc, acc);
+          mma_bf16(d + 128, ah, wl, idesc, acc);
+        }
         mma_bf16(d + 128, al, wh, idesc, 1);
       }
     };
@@ -173,8 +181,9 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       mbar_wait(&full[s], ph);
       tc_fence_after();
       if (elect_one()) {
-        if (swapped) block(tmem_base + b * 256, ring + s * kGnTile, xm + xb * kGnTile, first);
-        else block(tmem_base + b * 256, xm + xb * kGnTile, ring + s * kGnTile, first);
+        // swapped: A = weight tile, B = x_new planes -- also hi plane | lo plane contiguous, so the wide form applies
+        if (swapped) block(tmem_base + b * 256, ring + s * kGnTile, xm + xb * kGnTile, first, true);
+        else block(tmem_base + b * 256, xm + xb * kGnTile, ring + s * kGnTile, first, true);
         tc_commit(&empty[s]);
       }
       __syncwarp();
@@ -196,7 +205,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          block(tmem_base + 256, ring + sa * kGnTile, ring + s * kGnTile, kb == 0);
+          block(tmem_base + 256, ring + sa * kGnTile, ring + s * kGnTile, kb == 0, true);
           tc_commit(&empty[sa]);
           tc_commit(&empty[s]);
         }

@@ -67,3 +67,32 @@ def test_tc_conv_matches_fp32(model, layer, shape):
     print(f"layer {layer} {shape}: rel err simt {e_simt:.2e}  tc(fp16x3) {e_tc:.2e} (mean signed {bias:+.2e})")
     assert e_simt < 2e-6
     assert e_tc < 6e-6          # fp32-class: the fp16 2-term split keeps ~24 mantissa bits per operand (plain TF32: ~5e-4)
+
+
+def test_fused_stem_is_bit_identical_to_two_kernels():
+    """First conv fused into the second conv's operand producer (tc_conv.cu FUSE1) vs conv1_direct + tc_conv3x3:
+    same fp32 operation order, so semi / desc must agree bit for bit (odd sizes exercise the image border)."""
+    import os
+    from image_matching_b200 import Matching, stages, synth
+    from conftest import golden_cfg, real_superpoint_weights
+
+    def model():
+        cfg = golden_cfg()
+        m = Matching({"superpoint": dict(cfg["superpoint"], weights=None),
+                      "superglue": dict(cfg["superglue"], weights="")}).eval()
+        m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in real_superpoint_weights().items()})
+        sg = synth.superglue_weights(0, 128)
+        m.superglue.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sg.items()})
+        return m.to("cuda:0")
+
+    for (H, W) in [(480, 640), (136, 200)]:
+        a, b = synth.make_pair(3, H, W)
+        img = torch.from_numpy(np.stack([a, b])[:, None]).cuda()
+        fused = stages.superpoint_dense(model(), img)
+        os.environ["B200M_STEM_IMPL"] = "unfused"
+        try:
+            two = stages.superpoint_dense(model(), img)
+        finally:
+            os.environ.pop("B200M_STEM_IMPL", None)
+        for x, y in zip(fused, two):
+            assert torch.equal(x, y), float((x - y).abs().max())
