@@ -30,10 +30,12 @@ KENC = [32, 64, 128]
 SINKHORN = 30
 GF_PAIR_TOTAL = 135.43        # algorithmic GFLOP per pair (C1/C2/C4)
 GF_PAIR_QK = 9.664            # attention QK^T only
-# dram__bytes_read+write per tc_conv3x3 launch from profiles/r01_ncu_tc_conv.csv (mean of the 3 captured launches,
-# 16-image micro-batch); the kernel's algorithmic input+output is read/written exactly once
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 798.6e6
-GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers (tc_conv3x3): all but the Cin=1 stencil and the two 1x1 heads
+# dram__bytes_read+write of the dominant conv launch (fused stem + 64->64 layer at 480x640, 16-image micro-batch) from
+# profiles/r01_ncu_tc_conv_stem.txt: 19.9 MB read + 260.2 MB written; algorithmic = 19.7 MB images in + 314.6 MB of
+# pooled fp16 hi/lo planes out (part of the output is still in L2 when the kernel ends)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 280.1e6
+GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers with Cin >= 64 (all but the Cin=1 stem and the two 1x1 heads)
+GF_IMG_CONV1 = 0.354                   # the Cin=1 stem, computed inside the fused first tc_conv launch
 
 
 def make_cfg():
@@ -100,10 +102,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def cpu_oracle():
+    """The CPU arm's implementation: the torch-CPU restatement of the reference path (the reference's own arithmetic
+    library, oneDNN convolutions, all host threads); the numpy oracle stays the parity checker."""
+    import torch
+    from oracle import matching_oracle_torch as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    return O, torch.get_num_threads()
+
+
 def cpu_oracle_pairs_per_s(n_pairs, seeds_from=1000):
-    """The numpy oracle port on the host cores (all BLAS threads); returns (pairs/s, seconds)."""
+    """The oracle port on the host cores (all threads); returns (pairs/s, seconds)."""
     from image_matching_b200 import synth
-    from oracle import matching_oracle as O
+    O, _ = cpu_oracle()
     sp, sg, _ = load_weights()
     cfg = make_cfg()
     a, b = synth.make_pair(seeds_from - 1, H, W)
@@ -120,21 +131,18 @@ def cpu_oracle_pairs_per_s(n_pairs, seeds_from=1000):
 
 
 def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+    import torch
+    return torch.get_num_threads()
 
 
 def run_reference(args):
-    """CPU arm: the reference's algorithm (oracle port; the reference itself is Python/torch and cannot
-    travel to the GPU box) on the host cores.  Each step = 1 pair of the same workload."""
+    """CPU arm: the reference's algorithm (torch-CPU oracle port; the reference itself is a Python script collection
+    that cannot travel to the GPU box) on all host cores.  Each step = 1 pair of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from image_matching_b200 import synth
-    from oracle import matching_oracle as O
+    O, _ = cpu_oracle()
     sp, sg, sp_name = load_weights()
     cfg = make_cfg()
     pairs = [synth.make_pair(2000 + i, H, W) for i in range(args.warmup + args.steps)]
@@ -151,7 +159,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(1, sp_name),
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x 1 pair (640x480, 1024 kpts) through the numpy oracle"},
+                             "sample": f"{args.steps} steps x 1 pair (640x480, 1024 kpts) through the torch-CPU oracle port "
+                                       "(oracle/matching_oracle_torch.py)"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -287,22 +296,24 @@ def run_b200(args):
         e2e = total_pairs * args.steps / (e2e_ms / 1e3)
         dom = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
         roof = None
-        ck = "tc_conv3x3" if "tc_conv3x3" in prof else ("conv3x3_c4" if "conv3x3_c4" in prof else None)
-        if ck:
-            conv_ms = prof[ck]["ms_per_step"]
-            n_launch = prof[ck]["launches_per_step"]
-            flops_step = GF_IMG_CONV3 * 1e9 * 2 * B                    # algorithmic FLOPs (NOT x3 for 3xTF32)
-            ach = flops_step / (conv_ms / 1e3) / 1e12
-            roof = {"kernel": ck + " (SuperPoint 3x3 convs, implicit GEMM, 3xTF32 on tcgen05)", "bound": "tensor",
-                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
+        conv_names = [k for k in ("tc_conv3x3", "tc_conv3x3_stem") if k in prof]
+        if conv_names:
+            conv_ms = sum(prof[k]["ms_per_step"] for k in conv_names)
+            n_launch = sum(prof[k]["launches_per_step"] for k in conv_names)
+            flops_step = (GF_IMG_CONV3 + (GF_IMG_CONV1 if "tc_conv3x3_stem" in prof else 0.0)) * 1e9 * 2 * B
+            ach = flops_step / (conv_ms / 1e3) / 1e12                  # algorithmic FLOPs (NOT x3 for the fp16 split)
+            roof = {"kernel": "tc_conv (SuperPoint 3x3 convolutions: implicit GEMM on tcgen05, fp16 hi/lo operand split; "
+                              "first layer fused into the second one's operand producer)",
+                    "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
                     "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
                     "flops_per_launch": flops_step / max(n_launch, 1), "avg_launch_ms": conv_ms / max(n_launch, 1),
                     "share_of_step": conv_ms / sum(p["ms_per_step"] for p in prof.values()),
                     "dominant_by_time": dom,
-                    "note": "achieved counts algorithmic FLOPs once; the kernel issues 3 tf32 MMAs per product "
-                            "(fp32-class accuracy), i.e. %.0f TFLOP/s of tf32 MMA work against a tf32 pipe peak "
-                            "of half the bf16 figure" % (3 * ach)}
+                    "note": "achieved counts algorithmic FLOPs once; the kernel issues 3 fp16 products per algorithmic "
+                            "product (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32-class accuracy: 0 keypoint flips vs the "
+                            "reference), i.e. %.0f TFLOP/s of fp16 tensor work against the bf16/fp16 dense peak; "
+                            "traffic = dram bytes of the 64->64 full-resolution layer per 16-image launch (ncu)" % (3 * ach)}
         line = {"metric": "image-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -322,8 +333,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             v, dt = cpu_oracle_pairs_per_s(args.cpu_pairs)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": blas_threads(), "kind": "port",
-                                    "sample": f"{args.cpu_pairs} pairs of the same workload through the numpy "
-                                              f"oracle ({dt:.1f} s)"}
+                                    "sample": f"{args.cpu_pairs} pairs of the same workload through the torch-CPU "
+                                              f"oracle port ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

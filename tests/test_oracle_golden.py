@@ -100,3 +100,25 @@ def test_empty_keypoints_branch():
     assert r["matches0"].shape == (0,) and r["matches0"].dtype == np.int32
     assert r["matches1"].shape == (7,) and (r["matches1"] == -1).all()
     assert (r["matching_scores1"] == 0).all()
+
+
+@pytest.mark.parametrize("name,seed,hw,sp_real,kw", [
+    ("small_stages", 1, (120, 160), False, dict(max_kp=256)),
+    ("real_small_stages", 4, (160, 224), True, dict(max_kp=300)),
+])
+def test_torch_cpu_oracle_matches_reference_goldens(name, seed, hw, sp_real, kw):
+    """oracle/matching_oracle_torch.py (the CPU arm bench.py times) against the reference-generated goldens:
+    identical keypoints and matches, descriptors / scores to fp32 rounding."""
+    from oracle import matching_oracle_torch as OT
+    g = load_golden(name)
+    cfg = golden_cfg(**kw)
+    sp = real_superpoint_weights() if sp_real else synth.superpoint_weights(0, 128)
+    sg = synth.superglue_weights(0, 128, cfg["superglue"]["keypoint_encoder"])
+    a, b = synth.make_pair(seed, *hw)
+    r = OT.matching_forward(a, b, sp, sg, cfg)
+    for side in "01":
+        assert np.array_equal(r["keypoints" + side], g[f"keypoints{side}_0"])
+        assert np.abs(r["scores" + side] - g[f"scores{side}_0"]).max() < 1e-6
+        assert np.abs(r["descriptors" + side] - g[f"descriptors{side}_0"]).max() < 1e-5
+    assert np.array_equal(r["matches0"], g["matches0"][0]) and np.array_equal(r["matches1"], g["matches1"][0])
+    assert np.abs(r["matching_scores0"] - g["matching_scores0"][0]).max() < 1e-4
