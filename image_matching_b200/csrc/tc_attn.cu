@@ -90,8 +90,12 @@ struct TcAttnSmem {
   static constexpr int P_PLANE = kTaQ * KT * 2;           // [KT/8 chunks][128 rows][8 halves]
   static constexpr int OFF_KV = 2 * Q_PLANE;
   static constexpr int OFF_P = OFF_KV + NKV * KV_STAGE;
-  static constexpr int OFF_X = OFF_P + 2 * P_PLANE;       // half-merge exchange: 128 rows x (HD + 2) floats
-  static constexpr int OFF_BAR = OFF_X + kTaQ * (HD + 2) * 4;
+  // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring + P planes: it is only touched after the
+  // last P.V MMA has retired (every TMA load consumed, every MMA complete).  As a separate 17 KB region it pushed the CTA to 114.7 KB, i.e. ONE CTA per SM instead of two
+  // (measured: 15.5 % warps active); aliased, the CTA is 97.5 KB and two fit.
+  static constexpr int OFF_X = OFF_KV;
+  static_assert(kTaQ * (HD + 2) * 4 <= NKV * KV_STAGE + 2 * P_PLANE, "exchange buffer must fit in the aliased region");
+  static constexpr int OFF_BAR = OFF_P + 2 * P_PLANE;
   static constexpr int N_BARS = 1 + 3 + 3 + 2 + 2 + 1 + 1 + 2 + 2;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
   static constexpr int TMEM_COLS = (2 * KT + 4 * HD) <= 256 ? 256 : 512;
