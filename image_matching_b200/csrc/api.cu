@@ -75,6 +75,7 @@ struct b200m_handle {
   float* d_w = nullptr;          // device weight arena
   // SuperPoint
   size_t conv1_w = 0, conv1_b = 0;
+  std::vector<float> stem_host;  // [9][64] weights | [64] bias of the first conv (kernel-parameter copy for the fused stem)
   ConvLayer c1b, c2a, c2b, c3a, c3b, c4a, c4b, heads, pb, db;
   // SuperGlue
   std::vector<Linear> kenc;
@@ -223,6 +224,8 @@ int pack_superpoint(b200m_handle* h, Packer& P) {
   for (int t = 0; t < 9; ++t)
     for (int o = 0; o < 64; ++o) P.host[h->conv1_w + t * 64 + o] = (float)w[(size_t)o * 9 + t];
   for (int o = 0; o < 64; ++o) P.host[h->conv1_b + o] = (float)b[o];
+  h->stem_host.assign(P.host.begin() + h->conv1_w, P.host.begin() + h->conv1_w + 9 * 64);
+  h->stem_host.insert(h->stem_host.end(), P.host.begin() + h->conv1_b, P.host.begin() + h->conv1_b + 64);
   auto conv3 = [&](const std::string& conv, const std::string& bn, int cin, int cout, ConvLayer& L) -> bool {
     if (!P.folded(sp + conv, sp + bn, cout, cin * 9, w, b, {cout, cin, 3, 3})) return false;
     L = P.pack_conv(w, b, cout, cin, 3);
@@ -446,7 +449,8 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
       p.in_hi = nullptr; p.in_lo = nullptr; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
       p.out_hi = w.p1; p.out_lo = w.p1_lo; p.out_c4_total = 8; p.out_c4_off = 0; p.overflow = ovf;
       p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = d.H; p.W = d.W; p.relu = 1; p.pool = 1; p.ks = 3;
-      p.img = images; p.c1_w = h->d_w + h->conv1_w; p.c1_b = h->d_w + h->conv1_b;
+      p.img = images;
+      memcpy(p.c1, h->stem_host.data(), sizeof(p.c1));
       stem = launch_tc_conv(ctx, p, h->num_sms);
     }
     if (!stem) {

@@ -53,8 +53,9 @@ struct TcConvParams {
   int ks = 3;                               // 3 (3x3, zero pad 1) or 1 (1x1 heads)
   int in_c8_total = 0, in_c8_off = 0;       // 8-channel units per image in the input buffer (0 = cin/8) / first unit read
   // fused first layer: img != null -> the input activations are computed from the grayscale images (n, H, W) with the
-  // stem weights c1_w [9][64] / c1_b [64] instead of being read from in_hi / in_lo
-  const float* img = nullptr; const float* c1_w = nullptr; const float* c1_b = nullptr;
+  // stem weights c1 = [9 taps][64] | bias [64] (carried in the kernel parameters) instead of being read from in_hi / in_lo
+  const float* img = nullptr;
+  float c1[9 * 64 + 64];
 };
 bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
 size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks);

@@ -37,11 +37,14 @@ constexpr int kTcTile = 16;                       // output tile is 16 x 16 pixe
 constexpr int kTcKbGroups = 4;                    // 16-byte channel groups (8 fp16 channels) per K block -> 32 channels
 constexpr int kTcUnitCh = 8;                      // channels per 16-byte unit
 constexpr float kLoScale = 2048.f;                // lo planes / weights carry (v - hi) * 2^11
-constexpr int kTcNA = 3;                          // A stages
 
 // KS = 3: 3x3 conv, 18x18 halo tile, nine taps by descriptor shifts.  KS = 1: the 1x1 heads (convPb / convDb),
 // the same pipeline with a 16x16 tile and one tap per K block.
-template <int NB, int KS, bool FUSE1 = false>
+// RESIDENT: the layer's whole weight set (cin = 64, NB = 64, 3x3: 18 slabs = 144 KB) is loaded into shared memory once
+// per persistent CTA instead of being re-streamed from L2 for every 16x16 tile.  Measured motivation: a 64 -> 64 layer
+// needs 288 KB of weight slabs + 82 KB of activations per tile, i.e. ~34 B/clk/SM at tensor speed -- 80 % of the
+// chip-wide L2 -> SM bandwidth -- and ran at ~50 % tensor-pipe utilisation.
+template <int NB, int KS, bool FUSE1 = false, bool RESIDENT = false>
 struct TcConvSmem {
   static constexpr int HALO = kTcTile + KS - 1;
   static constexpr int TAPS = KS * KS;
@@ -52,13 +55,16 @@ struct TcConvSmem {
   static constexpr int B_SLOT = 2 * B_PLANE;
   // weight-slab ring: a slab is consumed in 12 MMAs (~400-800 cycles) while an L2 fetch takes ~2-4k cycles, so the
   // ring must hold ~96 KB of slabs in flight (measured: 4 slots left the tensor pipe 60% idle waiting on B)
-  static constexpr int NBS = 98304 / B_SLOT;
-  static constexpr int BAR_OFF = kTcNA * A_STAGE + NBS * B_SLOT;
-  static constexpr int N_BARS = 2 * kTcNA + 2 * NBS + 4;
+  static constexpr int NA = RESIDENT ? 2 : 3;          // A stages
+  static constexpr int NBS = RESIDENT ? 2 * KS * KS : 98304 / B_SLOT;   // resident: every slab of the (cin = 64) layer
+  static constexpr int BAR_OFF = NA * A_STAGE + NBS * B_SLOT;
+  static constexpr int NBB = RESIDENT ? 0 : NBS;       // weight-ring barriers (none when the weights are resident)
+  static constexpr int N_BARS = 2 * NA + 2 * NBB + 4 + 1;
   static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
-  // fused first layer: 20x20 image patch + the 1->64 stem weights [9][64] + bias [64] (fp32)
+  // fused first layer: 20x20 image patch (fp32) + the stem weights [9][64] | bias [64] (with resident conv weights
+  // there is no room: the stem then reads them from the kernel parameters)
   static constexpr int STEM_OFF = (BAR_OFF + N_BARS * 8 + 16 + 15) & ~15;
-  static constexpr int STEM_BYTES = FUSE1 ? (400 + 9 * 64 + 64) * 4 : 0;
+  static constexpr int STEM_BYTES = FUSE1 ? (RESIDENT ? 400 : 400 + 9 * 64 + 64) * 4 : 0;
   static constexpr size_t BYTES = 128 /*align slack*/ + STEM_OFF + STEM_BYTES;
   static constexpr int STEM_WARPS = 8;
   static constexpr int THREADS = FUSE1 ? 192 + 32 * STEM_WARPS : 192;
@@ -69,11 +75,12 @@ struct TcConvSmem {
 // the 18x18 halo of the tile on the CUDA cores and write it, already split into fp16 hi / lo planes, straight into the
 // A stage the MMA warp consumes (same order of fp32 operations as conv1_direct -> bit-identical activations).  This
 // removes the 157 MB / image-pair activation round trip through HBM of the unfused pair of kernels.
-template <int NB, bool POOL, int KS, bool FUSE1>
+template <int NB, bool POOL, int KS, bool FUSE1, bool RESIDENT>
 __global__ void __launch_bounds__(FUSE1 ? 448 : 192, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, TcConvParams p) {
-  using SM = TcConvSmem<NB, KS, FUSE1>;
-  constexpr int kTcNB = SM::NBS;
+tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const __grid_constant__ TcConvParams p) {
+  using SM = TcConvSmem<NB, KS, FUSE1, RESIDENT>;
+  constexpr int kTcNB = SM::NBS, kTcNA = SM::NA;
   constexpr int kTcHalo = SM::HALO, kTcPlaneB = SM::PLANE_B, kTcAPlane = SM::A_PLANE, kTcAStage = SM::A_STAGE;
   constexpr int kTaps = SM::TAPS, kPad = KS / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -86,10 +93,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kTcNA;
   uint64_t* b_full = a_empty + kTcNA;
-  uint64_t* b_empty = b_full + kTcNB;
-  uint64_t* acc_full = b_empty + kTcNB;
+  uint64_t* b_empty = b_full + SM::NBB;
+  uint64_t* acc_full = b_empty + SM::NBB;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;          // RESIDENT: all weight slabs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = cdiv(p.W, kTcTile), tiles_y = cdiv(p.H, kTcTile);
@@ -99,8 +107,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], FUSE1 ? SM::STEM_WARPS : 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < kTcNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < SM::NBB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
@@ -134,6 +143,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                   p.in_c8_off + kb * kTcKbGroups, img);
       if (++sa == kTcNA) { sa = 0; pa ^= 1; }
     };
+    if (RESIDENT) {            // the whole layer (ncb == 1, nkb * taps == NBS slabs), once
+      mbar_expect_tx(w_full, kTcNB * SM::B_SLOT);
+      for (int i = 0; i < kTcNB; ++i)
+        bulk_load(sB + i * SM::B_SLOT, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)i * SM::B_SLOT, SM::B_SLOT, w_full);
+    }
     if (!FUSE1 && (int)blockIdx.x < total) issue_A(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int cb = tile % ncb;
@@ -143,6 +157,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           if (kb + 1 < nkb) issue_A(tile, kb + 1);
           else if (tile + (int)gridDim.x < total) issue_A(tile + gridDim.x, 0);
         }
+        if (RESIDENT) continue;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)(cb * nkb + kb) * kTaps * SM::B_SLOT;
         for (int tap = 0; tap < kTaps; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
@@ -166,6 +181,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const uint64_t b_hi32 = (smem_desc_nosw(0, 2 * NB * 16, 128) >> 32) << 32;
     const uint32_t b_lo16 = (uint32_t)(((2 * NB * 16) >> 4) << 16);
     int sa = 0, pa = 0, sb = 0, pb = 0, lt = 0;
+    if (RESIDENT) mbar_wait(w_full, 0);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int buf = SM::ACC_BUFS == 2 ? (lt & 1) : 0;
       const int aph = SM::ACC_BUFS == 2 ? ((lt >> 1) & 1) : (lt & 1);
@@ -177,9 +193,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + sa * kTcAStage);
         for (int tap = 0; tap < kTaps; ++tap) {
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + sb * SM::B_SLOT);
+          if (!RESIDENT) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+          }
+          const uint32_t b_base = smem_u32(sB + (RESIDENT ? kb * kTaps + tap : sb) * SM::B_SLOT);
           const int ky = tap / KS, kx = tap - KS * ky;
           if (elect_one()) {
 #pragma unroll
@@ -197,7 +215,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               mma_bf16(d + NB, al, bw, idesc1, 1);      // + A_lo W_hi^T (first NB rows of the chunk)
             }
           }
-          tc_commit(&b_empty[sb]);
+          if (!RESIDENT) tc_commit(&b_empty[sb]);
           if (tap == kTaps - 1) tc_commit(&a_empty[sa]);
           if (tap == kTaps - 1 && kb == nkb - 1) tc_commit(&acc_full[buf]);
           }
@@ -210,12 +228,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   } else if (FUSE1 && warp >= 6) {
     // ------------------------------------------------------------------ stem: first convolution -> A stages
     float* patch = reinterpret_cast<float*>(smem + SM::STEM_OFF);       // 20 x 20 image pixels around the tile
-    float4* w1 = reinterpret_cast<float4*>(patch + 400);                // [9 taps][16 groups of 4 channels]
-    float4* b1 = w1 + 9 * 16;                                            // [16]
+    // stem weights [9 taps][16 groups of 4 channels] + bias [16] come from the kernel parameters (constant bank:
+    // every lane of a warp reads the same entry), not from shared memory, which the resident weights fill
     constexpr int kStemT = 32 * SM::STEM_WARPS;
     const int t = threadIdx.x - 192;                                     // 0..kStemT-1
-    for (int i = t; i < 9 * 16; i += kStemT) w1[i] = reinterpret_cast<const float4*>(p.c1_w)[i];
-    if (t < 16) b1[t] = reinterpret_cast<const float4*>(p.c1_b)[t];
+    const float4* w1 = reinterpret_cast<const float4*>(p.c1);
+    if (!RESIDENT) {
+      float4* ws = reinterpret_cast<float4*>(patch + 400);
+      for (int i = t; i < 9 * 16 + 16; i += kStemT) ws[i] = reinterpret_cast<const float4*>(p.c1)[i];
+      w1 = ws;                               // first use is behind the bar.sync below
+    }
+    const float4* b1 = w1 + 9 * 16;
     int sa = 0, pa = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int cb, x0, y0, img;
@@ -380,9 +403,10 @@ static bool make_act_map(CUtensorMap* m, const void* base, int n, int c4, int H,
   return r == CUDA_SUCCESS;
 }
 
-template <int NB, bool POOL, int KS, bool FUSE1 = false>
+template <int NB, bool POOL, int KS, bool FUSE1 = false, bool RESIDENT = false>
 static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
-  using SM = TcConvSmem<NB, KS, FUSE1>;
+  using SM = TcConvSmem<NB, KS, FUSE1, RESIDENT>;
+  static_assert(SM::BYTES <= 232448, "shared memory budget");
   ProfScope prof__(ctx, KS == 3 ? (FUSE1 ? "tc_conv3x3_stem" : "tc_conv3x3") : "tc_conv1x1");
   const int c8_total = p.in_c8_total > 0 ? p.in_c8_total : p.cin / kTcUnitCh;
   CUtensorMap tm_hi, tm_lo;
@@ -394,7 +418,7 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
     if (!make_act_map(&tm_lo, p.in_lo, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
   }
   static bool attr_set = false;
-  auto kern = tc_conv_kernel<NB, POOL, KS, FUSE1>;
+  auto kern = tc_conv_kernel<NB, POOL, KS, FUSE1, RESIDENT>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess)
       return false;
@@ -414,9 +438,13 @@ bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
     return p.nb == 64 ? launch_tc_t<64, false, 1>(ctx, p, num_sms) : launch_tc_t<128, false, 1>(ctx, p, num_sms);
   }
   if (p.img) {   // fused first layer (image -> 64 channels) in front of a 64 -> 64 pooled layer
-    if (p.nb != 64 || p.cin != 64 || !p.pool || !p.c1_w || !p.c1_b) return false;
-    return launch_tc_t<64, true, 3, true>(ctx, p, num_sms);
+    if (p.nb != 64 || p.cin != 64 || p.cout_pad != 64 || !p.pool) return false;
+    // (weights streamed, 3 A stages: the stem warps set the pace here and need the deeper run-ahead; measured 8.2 ms
+    // vs 9.8 ms with resident weights + 2 A stages)
+    return launch_tc_t<64, true, 3, true, false>(ctx, p, num_sms);
   }
+  if (p.nb == 64 && p.cin == 64 && p.cout_pad == 64)     // 64 -> 64 layers: weights resident in shared memory
+    return p.pool ? launch_tc_t<64, true, 3, false, true>(ctx, p, num_sms) : launch_tc_t<64, false, 3, false, true>(ctx, p, num_sms);
   if (p.nb == 64) return p.pool ? launch_tc_t<64, true, 3>(ctx, p, num_sms) : launch_tc_t<64, false, 3>(ctx, p, num_sms);
   return p.pool ? launch_tc_t<128, true, 3>(ctx, p, num_sms) : launch_tc_t<128, false, 3>(ctx, p, num_sms);
 }
