@@ -147,7 +147,9 @@ struct Packer {
     if (!W || !Bv) return false;
     w.assign(W->data.begin(), W->data.end());
     b.assign(Bv->data.begin(), Bv->data.end());
-    if (!bn.empty()) {
+    // a conv without BatchNorm tensors is used as is: the "official" SuperPoint variant
+    // (superglue/models/superpoint.py:95-202) has the same topology with no normalisation layers
+    if (!bn.empty() && h->tensors.count(bn + ".weight")) {
       const HostTensor* g = get(bn + ".weight", {out});
       const HostTensor* be = get(bn + ".bias", {out});
       const HostTensor* mu = get(bn + ".running_mean", {out});

@@ -125,7 +125,7 @@ class _Engine:
             for prefix, mod in (("superpoint.", sp), ("superglue.", sg)):
                 if mod is None:
                     continue
-                for k, v in mod.state_dict().items():
+                for k, v in mod._engine_state().items():
                     if k.endswith("num_batches_tracked"):
                         continue
                     a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
@@ -166,6 +166,10 @@ class _B200Module(nn.Module):
     def load_state_dict(self, *a, **k):
         self._dirty = True
         return super().load_state_dict(*a, **k)
+
+    def _engine_state(self):
+        """name -> tensor as the C library expects them (b200m_set_tensor); subclasses with other key names remap."""
+        return self.state_dict()
 
 
 class SuperPoint(_B200Module):
@@ -237,6 +241,48 @@ class SuperPoint(_B200Module):
         kp, sc, de, cnt = self._run(self._engine, L, x)
         keypoints, scores, descriptors = self._to_lists(kp, sc, de, cnt.cpu().tolist())
         return {"keypoints": keypoints, "scores": scores, "descriptors": descriptors}
+
+
+class SuperPointOfficial(SuperPoint):
+    """The "official" (MagicLeap) SuperPoint of the reference, superglue/models/superpoint.py:95-202: the same
+    encoder / heads topology WITHOUT BatchNorm and with the key names ``conv1a .. conv4b, convPa/Pb/Da/Db`` (so the
+    public ``superpoint_v1.pth`` loads with ``load_state_dict``).  Same kernels: the library uses a convolution as is
+    when no BatchNorm tensors accompany it.  Differences to the reference kept: ``max_keypoints`` validation (:143-145);
+    the dense map is normalised with an eps-clamped norm (:188), identical for any non-zero descriptor."""
+    _NAMES = OrderedDict([("conv1a", "inc.conv.conv.0"), ("conv1b", "inc.conv.conv.3"),
+                          ("conv2a", "down1.mpconv.1.conv.0"), ("conv2b", "down1.mpconv.1.conv.3"),
+                          ("conv3a", "down2.mpconv.1.conv.0"), ("conv3b", "down2.mpconv.1.conv.3"),
+                          ("conv4a", "down3.mpconv.1.conv.0"), ("conv4b", "down3.mpconv.1.conv.3"),
+                          ("convPa", "convPa"), ("convPb", "convPb"), ("convDa", "convDa"), ("convDb", "convDb")])
+
+    def __init__(self, config):
+        _B200Module.__init__(self)
+        self.config = {**self.default_config, **config}
+        c1, c2, c3, c4, c5 = 64, 64, 128, 128, 256
+        shapes = {"conv1a": (c1, 1, 3), "conv1b": (c1, c1, 3), "conv2a": (c2, c1, 3), "conv2b": (c2, c2, 3),
+                  "conv3a": (c3, c2, 3), "conv3b": (c3, c3, 3), "conv4a": (c4, c3, 3), "conv4b": (c4, c4, 3),
+                  "convPa": (c5, c4, 3), "convPb": (65, c5, 1), "convDa": (c5, c4, 3),
+                  "convDb": (self.config["descriptor_dim"], c5, 1)}
+        for name, (cout, cin, k) in shapes.items():
+            _conv_bn_params(self, name, None, cout, cin, k)
+        # the reference loads <its dir>/weights/superpoint_v1.pth unconditionally (:140-141; a git-LFS stub in the
+        # reference tree); here the path comes from config['weights'] (as superpoint_glue_official_test.py:40 passes
+        # it) and a falsy / missing entry leaves the seeded initialisation for load_state_dict()
+        path = self.config.get("weights")
+        if path:
+            self.load_state_dict(torch.load(str(path), map_location="cpu"))
+            print("Loaded SuperPoint model")
+        mk = self.config["max_keypoints"]
+        if mk == 0 or mk < -1:
+            raise ValueError('"max_keypoints" must be positive or "-1"')
+
+    def _engine_state(self):
+        sd = self.state_dict()
+        return OrderedDict((self._NAMES[k.rsplit(".", 1)[0]] + "." + k.rsplit(".", 1)[1], v) for k, v in sd.items())
+
+    def forward(self, data):
+        """reference signature: data = {'image': (B,1,H,W)} (superpoint.py:149)."""
+        return SuperPoint.forward(self, data["image"] if isinstance(data, dict) else data)
 
 
 class SuperGlue(_B200Module):
@@ -319,9 +365,11 @@ class SuperGlue(_B200Module):
 class Matching(nn.Module):
     """Image Matching Frontend (SuperPoint + SuperGlue); reference: superglue/models/matching_test.py:47-82."""
 
+    _superpoint_cls = None   # set below (SuperPoint); MatchingOfficial swaps in SuperPointOfficial
+
     def __init__(self, config={}):
         super().__init__()
-        self.superpoint = SuperPoint(config.get("superpoint", {}))
+        self.superpoint = (self._superpoint_cls or SuperPoint)(config.get("superpoint", {}))
         self.superglue = SuperGlue(config.get("superglue", {}))
         self._engine = _Engine()
         self._engine._sp = self.superpoint
@@ -413,3 +461,8 @@ class Matching(nn.Module):
                 data[k] = torch.stack(data[k])
         pred = {**pred, **self.superglue.forward(data, _engine=self._engine)}
         return pred
+
+
+class MatchingOfficial(Matching):
+    """reference: superglue/models/matching.py:46-82 -- the official SuperPoint (no BatchNorm) + the same SuperGlue."""
+    _superpoint_cls = SuperPointOfficial

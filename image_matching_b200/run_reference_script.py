@@ -20,7 +20,10 @@ def install_shims():
     from . import matching as _m
     for name, attrs in (("superglue.models.matching_test", {"Matching": _m.Matching}),
                         ("superpoint.models.superpoint_test", {"SuperPoint": _m.SuperPoint}),
-                        ("superglue.models.superglue_test", {"SuperGlue": _m.SuperGlue})):
+                        ("superglue.models.superglue_test", {"SuperGlue": _m.SuperGlue}),
+                        # the "official" variant used by superpoint_glue_official_test.py:10
+                        ("superglue.models.matching", {"Matching": _m.MatchingOfficial}),
+                        ("superglue.models.superpoint", {"SuperPoint": _m.SuperPointOfficial})):
         mod = types.ModuleType(name)
         mod.__dict__.update(attrs)
         sys.modules[name] = mod

@@ -154,6 +154,34 @@ def superpoint_weights(seed: int = 0, descriptor_dim: int = 128) -> dict:
     return sd
 
 
+_OFFICIAL_NAMES = {"inc.conv.conv.0": "conv1a", "inc.conv.conv.3": "conv1b",
+                   "down1.mpconv.1.conv.0": "conv2a", "down1.mpconv.1.conv.3": "conv2b",
+                   "down2.mpconv.1.conv.0": "conv3a", "down2.mpconv.1.conv.3": "conv3b",
+                   "down3.mpconv.1.conv.0": "conv4a", "down3.mpconv.1.conv.3": "conv4b",
+                   "convPa": "convPa", "convPb": "convPb", "convDa": "convDa", "convDb": "convDb"}
+_OFFICIAL_BN = {"inc.conv.conv.0": "inc.conv.conv.1", "inc.conv.conv.3": "inc.conv.conv.4",
+                "down1.mpconv.1.conv.0": "down1.mpconv.1.conv.1", "down1.mpconv.1.conv.3": "down1.mpconv.1.conv.4",
+                "down2.mpconv.1.conv.0": "down2.mpconv.1.conv.1", "down2.mpconv.1.conv.3": "down2.mpconv.1.conv.4",
+                "down3.mpconv.1.conv.0": "down3.mpconv.1.conv.1", "down3.mpconv.1.conv.3": "down3.mpconv.1.conv.4",
+                "convPa": "bnPa", "convPb": "bnPb", "convDa": "bnDa", "convDb": "bnDb"}
+
+
+def superpoint_official_weights(seed: int = 0, descriptor_dim: int = 256) -> dict:
+    """Synthetic state_dict of the BatchNorm-free "official" SuperPoint (reference superglue/models/superpoint.py:
+    keys conv1a .. conv4b, convPa/Pb/Da/Db): the synthetic weights above with their BatchNorm folded into the
+    convolutions, so the activations keep sane scales without normalisation layers."""
+    sd = superpoint_weights(seed, descriptor_dim)
+    out = {}
+    for conv, name in _OFFICIAL_NAMES.items():
+        bn = _OFFICIAL_BN[conv]
+        s = sd[bn + ".weight"].astype(np.float64) / np.sqrt(sd[bn + ".running_var"].astype(np.float64) + 1e-5)
+        w = sd[conv + ".weight"].astype(np.float64) * s.reshape(-1, 1, 1, 1)
+        b = (sd[conv + ".bias"].astype(np.float64) - sd[bn + ".running_mean"]) * s + sd[bn + ".bias"]
+        out[name + ".weight"] = w.astype(np.float32)
+        out[name + ".bias"] = b.astype(np.float32)
+    return out
+
+
 def superglue_weights(seed: int = 0, descriptor_dim: int = 128,
                       keypoint_encoder=(32, 64, 128), n_layers: int = 18,
                       sharpen: float = 16.0) -> dict:

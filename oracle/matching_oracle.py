@@ -32,7 +32,10 @@ F32 = np.float32
 # ----------------------------------------------------------------------------- helpers
 def fold_bn(w, b, sd, bn, eps=1e-5):
     """conv+BatchNorm(eval) -> conv.  torch.nn.BatchNorm{1,2}d eval semantics
-    (superpoint/models/unet_parts.py:15-20; superglue/models/superglue_test.py:56-58)."""
+    (superpoint/models/unet_parts.py:15-20; superglue/models/superglue_test.py:56-58).
+    A state_dict without the BatchNorm tensors (the "official" SuperPoint, superglue/models/superpoint.py) is used as is."""
+    if bn + ".weight" not in sd:
+        return w.astype(F32), b.astype(F32)
     g = sd[bn + ".weight"].astype(np.float64)
     beta = sd[bn + ".bias"].astype(np.float64)
     mu = sd[bn + ".running_mean"].astype(np.float64)
@@ -95,6 +98,12 @@ def superpoint_dense(img, sd):
     """Encoder + heads -> (semi (65,h,w), desc (D,h,w) channel-L2-normalised).
     superpoint/models/superpoint_test.py:113-126, unet_parts.py:10-48."""
     x = img.reshape(img.shape[-2], img.shape[-1], 1).astype(F32)       # channel-last internally
+    if "conv1a.weight" in sd:
+        # "official" variant (superglue/models/superpoint.py:116-132, :151-162): same topology, no BatchNorm, other names
+        ren = {"conv1a": "inc.conv.conv.0", "conv1b": "inc.conv.conv.3", "conv2a": "down1.mpconv.1.conv.0",
+               "conv2b": "down1.mpconv.1.conv.3", "conv3a": "down2.mpconv.1.conv.0", "conv3b": "down2.mpconv.1.conv.3",
+               "conv4a": "down3.mpconv.1.conv.0", "conv4b": "down3.mpconv.1.conv.3"}
+        sd = {(ren.get(k.rsplit(".", 1)[0], k.rsplit(".", 1)[0]) + "." + k.rsplit(".", 1)[1]): v for k, v in sd.items()}
 
     def dconv(x, p):
         w, b = fold_bn(sd[p + ".0.weight"], sd[p + ".0.bias"], sd, p + ".1")

@@ -95,6 +95,38 @@ def run_case(name, H, W, seeds, cfg, sp_sd, sg_sd, stages=False):
           "valid matches:", [int((pred["matches0"][i] > -1).sum()) for i in range(len(seeds))])
 
 
+def run_official_case(name, H, W, seeds, cfg, sp_sd, sg_sd):
+    """The "official" variant (superglue/models/matching.py + superpoint.py: SuperPoint without BatchNorm).  Its
+    constructor insists on torch.load-ing weights/superpoint_v1.pth (a git-LFS stub in the reference tree), so
+    torch.load is patched FOR THE CONSTRUCTOR CALL ONLY to hand it the seeded synthetic state_dict; the reference
+    code itself is untouched."""
+    import superglue.models.superpoint as ref_sp
+    from superglue.models.matching import Matching
+    torch.set_grad_enabled(False)
+    real_load = torch.load
+    torch.load = lambda *a, **k: to_torch_sd(sp_sd)
+    try:
+        m = Matching({"superpoint": dict(cfg["superpoint"]), "superglue": dict(cfg["superglue"], weights="")}).eval()
+    finally:
+        torch.load = real_load
+    assert isinstance(m.superpoint, ref_sp.SuperPoint)
+    m.superglue.load_state_dict(to_torch_sd(sg_sd))
+    a, b = synth.make_pair_batch(seeds, H, W)
+    out = {"seeds": np.asarray(seeds), "H": H, "W": W}
+    pred = m({"image0": torch.from_numpy(a), "image1": torch.from_numpy(b)})
+    for k, v in pred.items():
+        if isinstance(v, (list, tuple)):
+            for i, t in enumerate(v):
+                out[f"{k}_{i}"] = t.numpy()
+        else:
+            out[k] = v.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB",
+          "kpts:", [int(pred["keypoints0"][i].shape[0]) for i in range(len(seeds))],
+          "valid matches:", [int((pred["matches0"][i] > -1).sum()) for i in range(len(seeds))])
+
+
 def convert_real_superpoint_weights():
     """The reference's trained SuperPoint checkpoint (D=128, the one BASELINE's C1 is quoted
     on) is a 15 MB CUDA-saved torch pickle with optimizer state; keep only the 84 model
@@ -131,5 +163,17 @@ def main():
              stages=True)
 
 
+def main_official():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    cfg = make_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=300, iters=30)
+    run_official_case("official_small", 160, 224, [5], cfg, synth.superpoint_official_weights(1, 256),
+                      synth.superglue_weights(1, 256, (32, 64, 128, 256)))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "official":
+        main_official()      # only the fixture added for SURVEY.md 8(f3); the others are unchanged
+    else:
+        main()
+        main_official()

@@ -122,3 +122,20 @@ def test_torch_cpu_oracle_matches_reference_goldens(name, seed, hw, sp_real, kw)
         assert np.abs(r["descriptors" + side] - g[f"descriptors{side}_0"]).max() < 1e-5
     assert np.array_equal(r["matches0"], g["matches0"][0]) and np.array_equal(r["matches1"], g["matches1"][0])
     assert np.abs(r["matching_scores0"] - g["matching_scores0"][0]).max() < 1e-4
+
+
+def test_official_variant_oracle_matches_reference_golden():
+    """the BatchNorm-free "official" SuperPoint + SuperGlue (superglue/models/matching.py) -- the
+    oracle against a golden generated from the reference's own official classes (make_golden.py official)."""
+    g = load_golden("official_small")
+    cfg = golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=300, iters=30)
+    sp = synth.superpoint_official_weights(1, 256)
+    sg = synth.superglue_weights(1, 256, (32, 64, 128, 256))
+    a, b = synth.make_pair(5, 160, 224)
+    r = O.matching_forward(a, b, sp, sg, cfg)
+    for side in "01":
+        ref, got = kp_set(g[f"keypoints{side}_0"]), kp_set(r["keypoints" + side])
+        assert len(ref & got) >= 0.98 * len(ref), (len(ref & got), len(ref))
+    ref_pairs = match_pairs(g["keypoints0_0"], g["keypoints1_0"], g["matches0"][0])
+    got_pairs = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
+    assert len(ref_pairs) > 20 and len(ref_pairs & got_pairs) >= 0.9 * len(ref_pairs), (len(ref_pairs & got_pairs), len(ref_pairs))
