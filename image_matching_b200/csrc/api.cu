@@ -384,7 +384,7 @@ SpDims sp_dims(const b200m_handle* h, int H, int W) {
 }
 
 struct SpWs {
-  float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat;
+  float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat, *imgf;
   unsigned long long* keys;
   unsigned char* nms_scratch;
   int *cand_counts, *overflow;      // overflow[0]: candidate list overflow, overflow[1]: fp16 activation overflow
@@ -406,6 +406,7 @@ bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w)
   w.draw = A.take<float>(w.draw_img * mb);
   w.dn = A.take<float>(w.dn_img * mb);
   w.heat = A.take<float>(w.heat_img * mb);
+  w.imgf = A.take<float>((size_t)d.H * d.W * mb);       // fp32 copy of a uint8 micro-batch (b200m_*_u8 entry points)
   w.keys = A.take<unsigned long long>((size_t)d.cand_cap * mb);
   w.nms_scratch = A.take<unsigned char>(nms_scratch_bytes(mb, d.H8, d.W8));
   w.cand_counts = A.take<int>(mb + 2);
@@ -485,7 +486,7 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
   run_conv(h, ctx, h->db, w.p0, 128, 64, w.draw, d.dpad / 4, n, d.hc, d.wc, false, false);
 }
 
-int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_images, int H, int W,
+int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool images_u8, int n_images, int H, int W,
                     float* keypoints, float* scores, float* descriptors, int* counts, int cap,
                     float* semi_out, float* desc_out, float* tok_out, int tok_ld, size_t tok_img_stride,
                     void* ws, size_t ws_bytes) {
@@ -502,7 +503,14 @@ int sp_forward_impl(b200m_handle* h, void* stream, const float* images, int n_im
   cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), ctx.stream);
   for (int i0 = 0; i0 < n_images; i0 += mb) {
     const int n = std::min(mb, n_images - i0);
-    sp_dense(h, ctx, d, w, images + (size_t)i0 * H * W, n);
+    const float* images_mb;
+    if (images_u8) {   // SSHIDataset.py:26-29 normalisation (pixel / 255, rounded to fp32) done on the device
+      launch_u8_to_unit_f32(ctx, static_cast<const uint8_t*>(images_any) + (size_t)i0 * H * W, w.imgf, (size_t)n * H * W);
+      images_mb = w.imgf;
+    } else {
+      images_mb = static_cast<const float*>(images_any) + (size_t)i0 * H * W;
+    }
+    sp_dense(h, ctx, d, w, images_mb, n);
     if (semi_out)
       launch_c4_to_nchw(ctx, w.semi, 32, 0, 65, semi_out + (size_t)i0 * 65 * d.hc * d.wc, n, d.hc, d.wc, false);
     if (desc_out)
@@ -915,14 +923,23 @@ int b200m_superpoint_forward(b200m_handle* h, const float* images, int n_images,
                              void* stream) {
   if (!h || !images || !keypoints || !scores || !counts) return fail(B200M_ERR_INVALID, "null argument");
   if (cap < b200m_keypoint_capacity(h, H, W)) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
-  return sp_forward_impl(h, stream, images, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
+  return sp_forward_impl(h, stream, images, false, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
+                         nullptr, nullptr, 0, 0, ws, ws_bytes);
+}
+
+int b200m_superpoint_forward_u8(b200m_handle* h, const uint8_t* images, int n_images, int H, int W, float* keypoints,
+                                float* scores, float* descriptors, int* counts, int cap, void* ws, size_t ws_bytes,
+                                void* stream) {
+  if (!h || !images || !keypoints || !scores || !counts) return fail(B200M_ERR_INVALID, "null argument");
+  if (cap < b200m_keypoint_capacity(h, H, W)) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
+  return sp_forward_impl(h, stream, images, true, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
                          nullptr, nullptr, 0, 0, ws, ws_bytes);
 }
 
 int b200m_superpoint_dense(b200m_handle* h, const float* images, int n_images, int H, int W, float* semi,
                            float* desc, void* ws, size_t ws_bytes, void* stream) {
   if (!h || !images) return fail(B200M_ERR_INVALID, "null argument");
-  return sp_forward_impl(h, stream, images, n_images, H, W, nullptr, nullptr, nullptr, nullptr, 0, semi, desc,
+  return sp_forward_impl(h, stream, images, false, n_images, H, W, nullptr, nullptr, nullptr, nullptr, 0, semi, desc,
                          nullptr, 0, 0, ws, ws_bytes);
 }
 
@@ -1096,11 +1113,11 @@ size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W
   return align_up(sp_ws_bytes(h, B, H, W), 256) + b200m_superglue_workspace_bytes(h, B, cap, cap) + 256;
 }
 
-int b200m_matching_forward(b200m_handle* h, const float* image0, const float* image1, int B, int H, int W,
-                           float* keypoints0, float* scores0, float* descriptors0, int* counts0, float* keypoints1,
-                           float* scores1, float* descriptors1, int* counts1, int cap, int64_t* matches0,
-                           int64_t* matches1, float* mscores0, float* mscores1, void* ws, size_t ws_bytes,
-                           void* stream) {
+static int matching_forward_impl(b200m_handle* h, const void* image0, const void* image1, bool images_u8, int B, int H,
+                                 int W, float* keypoints0, float* scores0, float* descriptors0, int* counts0,
+                                 float* keypoints1, float* scores1, float* descriptors1, int* counts1, int cap,
+                                 int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
+                                 size_t ws_bytes, void* stream) {
   if (!h || !image0 || !image1) return fail(B200M_ERR_INVALID, "null argument");
   if (!h->packed_sp || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "both SuperPoint and SuperGlue weights must be packed");
   if (B <= 0) return B200M_OK;
@@ -1117,16 +1134,36 @@ int b200m_matching_forward(b200m_handle* h, const float* image0, const float* im
   // so they must be finite
   if (w.Np != cap) cudaMemsetAsync(w.X, 0, w.rows * 2 * D * sizeof(float), (cudaStream_t)stream);
   // SuperPoint writes token-major descriptors straight into X[:, :D] of its side
-  int rc = sp_forward_impl(h, stream, image0, B, H, W, keypoints0, scores0, descriptors0, counts0, cap, nullptr,
+  int rc = sp_forward_impl(h, stream, image0, images_u8, B, H, W, keypoints0, scores0, descriptors0, counts0, cap, nullptr,
                            nullptr, w.X, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
   if (rc) return rc;
-  rc = sp_forward_impl(h, stream, image1, B, H, W, keypoints1, scores1, descriptors1, counts1, cap, nullptr,
+  rc = sp_forward_impl(h, stream, image1, images_u8, B, H, W, keypoints1, scores1, descriptors1, counts1, cap, nullptr,
                        nullptr, w.X + rows * 2 * D, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
   if (rc) return rc;
   LaunchCtx ctx = make_ctx(h, stream);
   sg_core(h, ctx, w, keypoints0, scores0, counts0, keypoints1, scores1, counts1, B, cap, cap, H, W, H, W, matches0,
           matches1, mscores0, mscores1);
   return finish(h, ctx);
+}
+
+int b200m_matching_forward(b200m_handle* h, const float* image0, const float* image1, int B, int H, int W,
+                           float* keypoints0, float* scores0, float* descriptors0, int* counts0, float* keypoints1,
+                           float* scores1, float* descriptors1, int* counts1, int cap, int64_t* matches0,
+                           int64_t* matches1, float* mscores0, float* mscores1, void* ws, size_t ws_bytes,
+                           void* stream) {
+  return matching_forward_impl(h, image0, image1, false, B, H, W, keypoints0, scores0, descriptors0, counts0, keypoints1,
+                               scores1, descriptors1, counts1, cap, matches0, matches1, mscores0, mscores1, ws, ws_bytes,
+                               stream);
+}
+
+int b200m_matching_forward_u8(b200m_handle* h, const uint8_t* image0, const uint8_t* image1, int B, int H, int W,
+                              float* keypoints0, float* scores0, float* descriptors0, int* counts0, float* keypoints1,
+                              float* scores1, float* descriptors1, int* counts1, int cap, int64_t* matches0,
+                              int64_t* matches1, float* mscores0, float* mscores1, void* ws, size_t ws_bytes,
+                              void* stream) {
+  return matching_forward_impl(h, image0, image1, true, B, H, W, keypoints0, scores0, descriptors0, counts0, keypoints1,
+                               scores1, descriptors1, counts1, cap, matches0, matches1, mscores0, mscores1, ws, ws_bytes,
+                               stream);
 }
 
 }  // extern "C"

@@ -31,6 +31,8 @@ struct ConvParams {
 void launch_conv1_direct(LaunchCtx& ctx, const float* img, const float* w9x64, const float* bias,
                          float* out, float* out_lo, int n, int H, int W);
 void launch_conv(LaunchCtx& ctx, const ConvParams& p, int ksize, bool pool);
+// uint8 grayscale -> fp32 in [0,1]: correctly rounded v / 255 (== float(double(v) / 255), the reference's data loader)
+void launch_u8_to_unit_f32(LaunchCtx& ctx, const uint8_t* in, float* out, size_t n);
 void launch_c4_to_nchw(LaunchCtx& ctx, const float* in, int c4_total, int c4_off, int C, float* out,
                        int n, int H, int W, bool l2_normalize, const float* in_lo = nullptr);
 // full-precision fp32 -> tf32-exact hi / lo planes (element-wise; attention test hook)

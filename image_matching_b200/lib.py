@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200m_keypoint_capacity": (_I, [_P, _I, _I]),
     "b200m_superpoint_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "b200m_superpoint_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "b200m_superpoint_forward_u8": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "b200m_superpoint_dense": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "b200m_detector_post": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "b200m_sample_descriptors": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "b200m_matching_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "b200m_matching_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,
                                     _P, _P, _P, _P, _P, _Z, _P]),
+    "b200m_matching_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,
+                                       _P, _P, _P, _P, _P, _Z, _P]),
     "b200m_debug_conv_layer": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
     "b200m_debug_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200m_launch_count": (C.c_longlong, [_P]),

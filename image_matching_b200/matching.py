@@ -32,6 +32,13 @@ def _align_corners_from_torch_version() -> bool:
         return False
 
 
+def _image(x: torch.Tensor) -> torch.Tensor:
+    """(B,1,H,W) image batch as the library takes it: fp32 in [0,1] (the reference's contract), or -- extension,
+    SURVEY.md 8 f2 -- the raw uint8 pixels, normalised by 255 on the device exactly like datasets/SSHIDataset.py:26-29
+    followed by `.float()`, so the 8-bit image can be uploaded instead of a 4x (float64: 8x) larger tensor."""
+    return x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -213,9 +220,9 @@ class SuperPoint(_B200Module):
         cnt = torch.empty((B,), dtype=torch.int32, device=dev)
         nbytes = L.b200m_superpoint_workspace_bytes(engine.handle, B, H, W)
         ws = engine.workspace(nbytes, dev)
-        _lib.check(L.b200m_superpoint_forward(engine.handle, _ptr(x), B, H, W, _ptr(kp), _ptr(sc), _ptr(de),
-                                              _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream()),
-                   "b200m_superpoint_forward")
+        fn = L.b200m_superpoint_forward_u8 if x.dtype == torch.uint8 else L.b200m_superpoint_forward
+        _lib.check(fn(engine.handle, _ptr(x), B, H, W, _ptr(kp), _ptr(sc), _ptr(de),
+                      _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream()), "b200m_superpoint_forward")
         return kp, sc, de, cnt
 
     @staticmethod
@@ -236,7 +243,7 @@ class SuperPoint(_B200Module):
         return keypoints, scores, descriptors
 
     def forward(self, x):
-        x = x.contiguous().float()
+        x = _image(x)
         L = self._engine.ensure(x.device, self, None)
         kp, sc, de, cnt = self._run(self._engine, L, x)
         keypoints, scores, descriptors = self._to_lists(kp, sc, de, cnt.cpu().tolist())
@@ -381,8 +388,10 @@ class Matching(nn.Module):
     def forward_device(self, image0: torch.Tensor, image1: torch.Tensor):
         """Device-resident results without any host synchronisation: dict of padded tensors plus
         per-pair `counts0/1` (number of valid leading keypoints)."""
-        image0 = image0.contiguous().float()
-        image1 = image1.contiguous().float()
+        image0, image1 = _image(image0), _image(image1)
+        if image0.dtype != image1.dtype:
+            image0, image1 = image0.float() / (255.0 if image0.dtype == torch.uint8 else 1.0), \
+                image1.float() / (255.0 if image1.dtype == torch.uint8 else 1.0)
         if image0.shape != image1.shape:
             raise ValueError("forward_device needs equally shaped image batches")
         L = self._ensure(image0.device)
@@ -408,7 +417,8 @@ class Matching(nn.Module):
         nbytes = L.b200m_matching_workspace_bytes(e.handle, B, H, W)
         ws = e.workspace(nbytes, dev)
         c0, c1 = out["counts"][0], out["counts"][1]
-        _lib.check(L.b200m_matching_forward(
+        fn = L.b200m_matching_forward_u8 if image0.dtype == torch.uint8 else L.b200m_matching_forward
+        _lib.check(fn(
             e.handle, _ptr(image0), _ptr(image1), B, H, W,
             _ptr(out["keypoints0"]), _ptr(out["scores0"]), _ptr(out["descriptors0"]), _ptr(c0),
             _ptr(out["keypoints1"]), _ptr(out["scores1"]), _ptr(out["descriptors1"]), _ptr(c1), cap,
@@ -451,7 +461,7 @@ class Matching(nn.Module):
         L = self._ensure(dev)
         for side, need in (("0", need0), ("1", need1)):
             if need:
-                x = data["image" + side].contiguous().float()
+                x = _image(data["image" + side])
                 kp, sc, de, cnt = self.superpoint._run(self._engine, L, x)
                 ks, ss, ds = SuperPoint._to_lists(kp, sc, de, cnt.cpu().tolist())
                 pred.update({"keypoints" + side: ks, "scores" + side: ss, "descriptors" + side: ds})

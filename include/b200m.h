@@ -93,6 +93,10 @@ size_t b200m_superpoint_workspace_bytes(const b200m_handle* h, int n_images, int
 int b200m_superpoint_forward(b200m_handle* h, const float* images, int n_images, int H, int W,
                              float* keypoints, float* scores, float* descriptors, int* counts,
                              int cap, void* ws, size_t ws_bytes, void* stream);
+/* uint8 variant, see b200m_matching_forward_u8 */
+int b200m_superpoint_forward_u8(b200m_handle* h, const uint8_t* images, int n_images, int H, int W,
+                             float* keypoints, float* scores, float* descriptors, int* counts,
+                             int cap, void* ws, size_t ws_bytes, void* stream);
 
 /* stage: images -> semi (n,65,h,w), desc (n,D,h,w) channel-L2-normalised (either may be NULL) */
 int b200m_superpoint_dense(b200m_handle* h, const float* images, int n_images, int H, int W,
@@ -144,6 +148,16 @@ size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W
  * ragged per-pair keypoint counts are handled on the device (counts0/1 tell the caller how many
  * leading entries are valid); the Python shim reproduces the reference's torch.stack error. */
 int b200m_matching_forward(b200m_handle* h, const float* image0, const float* image1, int B, int H, int W,
+                           float* keypoints0, float* scores0, float* descriptors0, int* counts0,
+                           float* keypoints1, float* scores1, float* descriptors1, int* counts1,
+                           int cap, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* Same with 8-bit grayscale images (B,1,H,W) uint8 on the device: the data loader's `img / 255.` normalisation
+ * (datasets/SSHIDataset.py:26-29 followed by the caller's `.float()`, superpoint_glue_test.py:74-75) is done on the
+ * device, correctly rounded, so the results are bit-identical to uploading the fp32 tensor -- with 4x fewer bytes
+ * over PCIe.   */
+int b200m_matching_forward_u8(b200m_handle* h, const uint8_t* image0, const uint8_t* image1, int B, int H, int W,
                            float* keypoints0, float* scores0, float* descriptors0, int* counts0,
                            float* keypoints1, float* scores1, float* descriptors1, int* counts1,
                            int cap, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
