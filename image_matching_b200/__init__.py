@@ -3,7 +3,8 @@
 Drop-in for the reference's ``superglue.models.matching_test.Matching`` (and the two model
 classes it owns).  See DESIGN.md / INTEGRATION.md at the repo root.
 """
-from .matching import Matching, MatchingOfficial, SuperPoint, SuperPointOfficial, SuperGlue  # noqa: F401
+from .matching import (Matching, MatchingOfficial, SuperPoint, SuperPointOfficial, SuperGlue,  # noqa: F401
+                       knn_ratio_match)
 from . import synth, lib  # noqa: F401
 
-__all__ = ["Matching", "MatchingOfficial", "SuperPoint", "SuperPointOfficial", "SuperGlue", "synth", "lib"]
+__all__ = ["Matching", "MatchingOfficial", "SuperPoint", "SuperPointOfficial", "SuperGlue", "knn_ratio_match", "synth", "lib"]

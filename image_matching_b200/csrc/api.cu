@@ -987,6 +987,18 @@ int b200m_sample_descriptors(b200m_handle* h, const float* keypoints, const int*
   return finish(h, ctx);
 }
 
+int b200m_knn_ratio_match(b200m_handle* h, const float* desc0, const float* desc1, const int* counts0,
+                          const int* counts1, int B, int N, int M, float ratio, int64_t* matches, float* dist1,
+                          float* dist2, void* stream) {
+  if (!h || !desc0 || !desc1 || !matches || !dist1 || !dist2) return fail(B200M_ERR_INVALID, "null argument");
+  if (M <= 0 && N > 0) return fail(B200M_ERR_INVALID, "empty train set");
+  LaunchCtx ctx = make_ctx(h, stream);
+  if (!launch_knn_ratio(ctx, desc0, desc1, counts0, counts1, B, h->cfg.descriptor_dim, N, M, ratio,
+                        (long long*)matches, dist1, dist2))
+    return fail(B200M_ERR_INVALID, "descriptor_dim %d not supported by the matcher", h->cfg.descriptor_dim);
+  return finish(h, ctx);
+}
+
 size_t b200m_superglue_workspace_bytes(const b200m_handle* h, int B, int N, int M) {
   if (!h) return 0;
   Arena A(nullptr, 0);

@@ -85,6 +85,11 @@ void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_tota
                                float* out_dcn /* (n,D,cap) or null */,
                                float* out_tok /* token-major rows or null */, int tok_ld, size_t tok_img_stride);
 
+// ------------------------------------------------------------------ descriptor 2-NN + ratio test (sp_knn.cu)
+// desc (B, D, N) / (B, D, M) channel-major; match (B, N) = nearest train index or -1, dist1/dist2 = Euclidean distances
+bool launch_knn_ratio(LaunchCtx& ctx, const float* desc0, const float* desc1, const int* counts0, const int* counts1,
+                      int B, int D, int N, int M, float ratio, long long* match, float* dist1, float* dist2);
+
 // ------------------------------------------------------------------ SuperGlue linear (sg_linear.cu)
 struct GemmParams {
   const float* A; int lda; long long strideA;   // [M,K] row-major

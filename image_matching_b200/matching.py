@@ -250,6 +250,27 @@ class SuperPoint(_B200Module):
         return {"keypoints": keypoints, "scores": scores, "descriptors": descriptors}
 
 
+def knn_ratio_match(superpoint: "SuperPoint", desc0: torch.Tensor, desc1: torch.Tensor, ratio: float = 0.7):
+    """GPU replacement for the FLANN step of superpoint_flann_test.py:69-78: exact 2-nearest-neighbour search between two
+    SuperPoint descriptor sets + Lowe's ratio test.  desc0 (D,N) / desc1 (D,M) (one image pair, as `pred['descriptors'][0]`)
+    or batched (B,D,N) / (B,D,M).  Returns (matches, dist1, dist2): index of the nearest descriptor of desc1 or -1
+    where `dist1 < ratio * dist2` fails, and the Euclidean distances to the two nearest."""
+    single = desc0.dim() == 2
+    d0 = (desc0[None] if single else desc0).contiguous().float()
+    d1 = (desc1[None] if single else desc1).contiguous().float()
+    L = superpoint._engine.ensure(d0.device, superpoint, None)
+    B, D, N = d0.shape
+    M = d1.shape[2]
+    if D != superpoint.config["descriptor_dim"] or d1.shape[0] != B or d1.shape[1] != D:
+        raise ValueError("descriptor shapes do not match the model")
+    match = torch.empty((B, N), dtype=torch.int64, device=d0.device)
+    e1 = torch.empty((B, N), dtype=torch.float32, device=d0.device)
+    e2 = torch.empty((B, N), dtype=torch.float32, device=d0.device)
+    _lib.check(L.b200m_knn_ratio_match(superpoint._engine.handle, _ptr(d0), _ptr(d1), None, None, B, N, M,
+                                       float(ratio), _ptr(match), _ptr(e1), _ptr(e2), _stream()), "b200m_knn_ratio_match")
+    return (match[0], e1[0], e2[0]) if single else (match, e1, e2)
+
+
 class SuperPointOfficial(SuperPoint):
     """The "official" (MagicLeap) SuperPoint of the reference, superglue/models/superpoint.py:95-202: the same
     encoder / heads topology WITHOUT BatchNorm and with the key names ``conv1a .. conv4b, convPa/Pb/Da/Db`` (so the

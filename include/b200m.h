@@ -136,6 +136,13 @@ int b200m_score_matrix(b200m_handle* h, const float* desc0, const float* desc1, 
 /* stage: S (B,N,M) -> Z (B,N+1,M+1) with the handle's bin_score and `iters` Sinkhorn iterations */
 int b200m_sinkhorn(b200m_handle* h, const float* S, int B, int N, int M, int iters, float* Z,
                    void* ws, size_t ws_bytes, void* stream);
+/* Descriptor matching after SuperPoint as superpoint_flann_test.py:69-78 does it (cv2 FLANN knnMatch(k=2) + Lowe's
+ * ratio test `m.distance < ratio * n.distance`), with an EXACT 2-nearest-neighbour search: desc0 (B,D,N), desc1
+ * (B,D,M) in SuperPoint's channel-major layout, optional per-pair counts; matches (B,N) = index of the nearest
+ * train descriptor or -1, dist1 / dist2 (B,N) = Euclidean distance to the nearest / second nearest.   */
+int b200m_knn_ratio_match(b200m_handle* h, const float* desc0, const float* desc1, const int* counts0,
+                          const int* counts1, int B, int N, int M, float ratio, int64_t* matches, float* dist1,
+                          float* dist2, void* stream);
 /* stage: Z (B,N+1,M+1) -> matches / scores */
 int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M,
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
