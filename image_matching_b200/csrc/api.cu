@@ -38,6 +38,7 @@ struct ConvLayer {      // packed conv on C4-planar activations
   size_t w_off = 0, b_off = 0;   // float offsets into the device weight arena
   int nb = 0;                    // tensor-core path: output channels per CTA tile (0 = no tc weights)
   size_t tc_w_off = 0;
+  std::vector<float> bias_host;  // folded bias [cout_pad] (copied into the kernel parameters of small layers)
 };
 struct Linear {         // packed [N][K] row-major weight + bias
   int N = 0, K = 0;
@@ -180,6 +181,7 @@ struct Packer {
               host[L.w_off + ((((size_t)cb * nchunks + cc) * taps + t) * 8 + ci) * 64 + co] = v;
             }
     for (int o = 0; o < cout; ++o) host[L.b_off + o] = (float)b[o];
+    L.bias_host.assign(host.begin() + L.b_off, host.begin() + L.b_off + L.cout_pad);
     return L;
   }
   void pack_tc(ConvLayer& L, const std::vector<double>& w) {   // 3x3 / 1x1 layers with cin % 32 == 0
@@ -434,6 +436,10 @@ void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const floa
   p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.overflow = overflow;
   p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = relu ? 1 : 0;
   p.pool = pool ? 1 : 0; p.ks = L.ks; p.in_c8_total = in_c8_total; p.in_c8_off = in_c8_off;
+  if (L.cout_pad <= 128 && (int)L.bias_host.size() == L.cout_pad) {
+    p.bias_in_params = 1;
+    memcpy(p.bias_c, L.bias_host.data(), sizeof(float) * L.cout_pad);
+  }
   launch_tc_conv(ctx, p, h->num_sms);
 }
 
@@ -454,6 +460,8 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
       p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = d.H; p.W = d.W; p.relu = 1; p.pool = 1; p.ks = 3;
       p.img = images;
       memcpy(p.c1, h->stem_host.data(), sizeof(p.c1));
+      p.bias_in_params = 1;
+      memcpy(p.bias_c, L.bias_host.data(), sizeof(float) * L.cout_pad);
       stem = launch_tc_conv(ctx, p, h->num_sms);
     }
     if (!stem) {

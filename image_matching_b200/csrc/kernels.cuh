@@ -58,6 +58,8 @@ struct TcConvParams {
   // stem weights c1 = [9 taps][64] | bias [64] (carried in the kernel parameters) instead of being read from in_hi / in_lo
   const float* img = nullptr;
   float c1[9 * 64 + 64];
+  int bias_in_params = 0;                   // cout_pad <= 128: the epilogue reads the bias from bias_c (constant bank)
+  float bias_c[128];
 };
 bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
 size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks);

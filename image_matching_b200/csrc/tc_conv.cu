@@ -333,9 +333,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           tmem_ld32(taddr, v);
           tmem_ld32(taddr + NB, vc);
           const int c0 = cb * NB + ch * 32;
+          // bias: from the kernel parameters (constant bank, one uniform read) when the layer has <= 128 output channels,
+          // else 32 L1 loads per chunk
+          float bj[32];
+          if (p.bias_in_params) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bj[j] = p.bias_c[c0 + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bj[j] = __ldg(p.bias + c0 + j);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = fmaf(vc[j], 1.f / kLoScale, v[j]) + __ldg(p.bias + c0 + j);
+            float t = fmaf(vc[j], 1.f / kLoScale, v[j]) + bj[j];
             if (p.relu) t = fmaxf(t, 0.f);
             if (POOL) {
               t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
