@@ -20,9 +20,12 @@
 //   warps 2..9  softmax      : thread = (query row, key half).  tcgen05.ld S_j, running max / sum (ex2.approx with
 //                              the 1/sqrt(d) scale folded into one FFMA), P_j split into fp16 hi/lo and stored to
 //                              shared memory as the next MMA's A operand (no-swizzle K-major, 8 keys per 16-byte
-//                              unit), OT_{j-1} pulled from TMEM and folded into the register accumulator with the
-//                              usual exp(m_old - m_new) correction; the two key halves keep independent statistics
-//                              (2-way split-KV) and are merged once at the end.
+//                              unit).  O stays in TMEM and the tensor core accumulates it across ALL key tiles: P is
+//                              taken relative to a reference maximum that is only moved (and O rescaled in TMEM with
+//                              tcgen05.ld / .st) when the running maximum exceeds it by more than 2^8 -- rare after
+//                              the first tile -- so the common tile needs no O read, no rescale FFMAs and no wait for
+//                              the previous P.V.  The two key halves keep independent statistics (2-way split-KV)
+//                              and are merged once at the end.
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -53,6 +56,25 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
 #pragma unroll
     for (int c = 0; c < N / 32; ++c) tmem_ld32(taddr + c * 32, v + c * 32);
   }
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+        "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+        "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float* v) {
+  static_assert(N % 32 == 0, "32-column granularity");
+#pragma unroll
+  for (int c = 0; c < N / 32; ++c) tmem_st32(taddr + c * 32, v + c * 32);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // ex2.approx.ftz: 1 MUFU op, max relative error 2^-22 (the accurate exp2f expands to ~4 extra instructions)
@@ -98,7 +120,7 @@ struct TcAttnSmem {
   static constexpr int OFF_BAR = OFF_P + 2 * P_PLANE;
   static constexpr int N_BARS = 1 + 3 + 3 + 2 + 2 + 1 + 1 + 2 + 2;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
-  static constexpr int TMEM_COLS = (2 * KT + 4 * HD) <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = (2 * KT + 2 * HD) <= 256 ? 256 : 512;   // S double buffer + one O per key half
 };
 
 struct TcAttnParams {
@@ -133,9 +155,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   uint64_t* s_empty = s_full + 2;
   uint64_t* p_full = s_empty + 2;
   uint64_t* p_empty = p_full + 1;
-  uint64_t* o_full = p_empty + 1;
-  uint64_t* o_empty = o_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* pv_done = p_empty + 1;           // P.V of tile j retired (phase j)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
@@ -153,8 +174,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
+
     }
+    mbar_init(pv_done, 1);
     mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     fence_barrier_init();
@@ -215,7 +237,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       tc_fence_after();
       issue_S(0);
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
         if (j + 1 < T) {
           const int sn = (j + 1) & 1, pn = ((j + 1) >> 1) & 1;
           mbar_wait(&kv_full[(j + 1) % SM::NKV], ((j + 1) / SM::NKV) & 1);
@@ -224,7 +245,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
           issue_S(j + 1);
         }
         mbar_wait(p_full, j & 1);
-        mbar_wait(&o_empty[st], ph ^ 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE + 2 * SM::K_PLANE);
         if (elect_one()) {
@@ -235,14 +255,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             const uint64_t vh = smem_desc_sw<SM::VROW>(v_base + ks * 32);
             const uint64_t vl = smem_desc_sw<SM::VROW>(v_base + SM::V_PLANE + ks * 32);
             // keys [0, KT/2) accumulate into OT[st][0], keys [KT/2, KT) into OT[st][1] (independent softmax halves)
-            const uint32_t dO = tO + st * (2 * HD) + (ks / (KT / 32)) * HD;
-            mma_bf16(dO, ph_, vh, idesc_o, (ks % (KT / 32)) != 0);
+            const uint32_t dO = tO + (ks / (KT / 32)) * HD;
+            mma_bf16(dO, ph_, vh, idesc_o, (j > 0) || (ks % (KT / 32)) != 0);   // accumulates across key tiles
             mma_bf16(dO, ph_, vl, idesc_o, 1);
             mma_bf16(dO, pl_, vh, idesc_o, 1);
           }
           tc_commit(&kv_empty[j % SM::NKV]);
           tc_commit(p_empty);
-          tc_commit(&o_full[st]);
+          tc_commit(pv_done);
         }
         __syncwarp();
       }
@@ -255,26 +275,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     const int m = w4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
     const float c = p.scale_log2e;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, m_o = -INFINITY, m_prev = -INFINITY;
+    constexpr float kLazy = 8.f;      // log2 units: the reference maximum moves only when the true one is > 2^8 above it
+    const uint32_t tO_mine = tO + lane_base + half * HD;
+    float m_run = -INFINITY;          // true running maximum of this row's scores (this key half)
+    float m_ref = 0.f;                // reference the exponentials are taken against (finite; meaningless until set)
+    bool have_ref = false;
+    float l_run = 0.f;                // sum of exp2((s - m_ref) c)
     uint4* Ph = reinterpret_cast<uint4*>(sP) + (half * (KH / 8)) * kTaQ + m;        // [8-key chunk][row][8 halves]
     uint4* Pl = reinterpret_cast<uint4*>(sP + SM::P_PLANE) + (half * (KH / 8)) * kTaQ + m;
-    auto fold_O = [&](int j, float m_tile) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(&o_full[st], ph);
-      tc_fence_after();
-      float ot[HD];
-      tmem_ld_n<HD>(tO + lane_base + st * (2 * HD) + half * HD, ot);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[st]);
-      const float corr = fast_exp2((m_o - m_tile) * c);                   // exp2(-inf) = 0 on the first tile
-#pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr, ot[i]);
-      m_o = m_tile;
-    };
     for (int j = 0; j < T; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       mbar_wait(&s_full[st], ph);
@@ -294,17 +302,33 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
 #pragma unroll
       for (int i = 4; i < KH; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m_run, mx);
-      const float m_safe = m_new == -INFINITY ? 0.f : m_new;              // nothing valid seen yet: stay finite
-      const float neg = -m_safe * c;
+      m_run = fmaxf(m_run, mx);
+      // ---- move the reference?  (first valid score of the row, or the maximum ran away by more than 2^kLazy)
+      const bool move = m_run > -INFINITY && (!have_ref || (m_run - m_ref) * c > kLazy);
+      if (__any_sync(0xffffffffu, move)) {
+        // warp-uniform path (tcgen05.ld / .st are warp-collective); rows that do not move use factor 1
+        const float f = move && have_ref ? fast_exp2((m_ref - m_run) * c) : 1.f;
+        if (j > 0) {                                   // O holds tiles 0 .. j-1: rescale it in place
+          mbar_wait(pv_done, (j - 1) & 1);             // P.V of tile j-1 retired (it cannot be further: it needs our P_j)
+          tc_fence_after();
+          float ot[HD];
+          tmem_ld_n<HD>(tO_mine, ot);
+#pragma unroll
+          for (int i = 0; i < HD; ++i) ot[i] *= f;
+          tmem_st_n<HD>(tO_mine, ot);
+          tc_fence_before();
+        }
+        l_run *= f;
+        if (move) { m_ref = m_run; have_ref = true; }
+      }
+      const float neg = -m_ref * c;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < KH; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], c, neg));
+        s[i] = fast_exp2(fmaf(s[i], c, neg));                             // exp2(-inf) = 0 for masked keys
         sum4[i & 3] += s[i];
       }
-      l_run = l_run * fast_exp2((m_run - m_safe) * c) + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
-      m_run = m_new;
+      l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       // P_j -> shared memory (A operand of the PV MMA), fp16 hi / lo planes
       mbar_wait(p_empty, (j & 1) ^ 1);
 #pragma unroll
@@ -323,10 +347,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (j > 0) fold_O(j - 1, m_prev);
-      m_prev = m_safe;
     }
-    if (T > 0) fold_O(T - 1, m_prev);
+    // ---- O of this key half: one TMEM read after the last P.V
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    if (T > 0) {
+      mbar_wait(pv_done, (T - 1) & 1);
+      tc_fence_after();
+      tmem_ld_n<HD>(tO_mine, o);
+      tc_fence_before();
+    }
+    if (!have_ref) m_run = -INFINITY;                 // no valid key in this half: contributes nothing to the merge
+    else m_run = m_ref;                               // the merge below works with the reference the sums are relative to
     // ---- merge the two key halves
     float* xch = sX + (size_t)m * (HD + 2);
     if (half == 1) {
