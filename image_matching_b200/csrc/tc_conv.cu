@@ -61,10 +61,9 @@ struct TcConvSmem {
   static constexpr int NBB = RESIDENT ? 0 : NBS;       // weight-ring barriers (none when the weights are resident)
   static constexpr int N_BARS = 2 * NA + 2 * NBB + 4 + 1;
   static constexpr int ACC_BUFS = NB == 64 ? 2 : 1;   // TMEM: bufs x 2 halves x {main, cross} x NB <= 512 columns
-  // fused first layer: 20x20 image patch (fp32) + the stem weights [9][64] | bias [64] (with resident conv weights
-  // there is no room: the stem then reads them from the kernel parameters)
+  // fused first layer: 20x20 image patch (fp32); the stem weights go from the kernel parameters into registers
   static constexpr int STEM_OFF = (BAR_OFF + N_BARS * 8 + 16 + 15) & ~15;
-  static constexpr int STEM_BYTES = FUSE1 ? (RESIDENT ? 400 : 400 + 9 * 64 + 64) * 4 : 0;
+  static constexpr int STEM_BYTES = FUSE1 ? 400 * 4 : 0;
   static constexpr size_t BYTES = 128 /*align slack*/ + STEM_OFF + STEM_BYTES;
   static constexpr int STEM_WARPS = 8;
   static constexpr int THREADS = FUSE1 ? 192 + 32 * STEM_WARPS : 192;
@@ -106,7 +105,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int total = p.n * tiles_y * tiles_x * ncb;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], FUSE1 ? SM::STEM_WARPS : 1); mbar_init(&a_empty[i], 1); }
+    // a_full: one TMA transaction, or (fused stem) the four warps that fill the stage
+    for (int i = 0; i < kTcNA; ++i) { mbar_init(&a_full[i], FUSE1 ? SM::STEM_WARPS / 2 : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < SM::NBB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     mbar_init(w_full, 1);
@@ -228,19 +228,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   } else if (FUSE1 && warp >= 6) {
     // ------------------------------------------------------------------ stem: first convolution -> A stages
     float* patch = reinterpret_cast<float*>(smem + SM::STEM_OFF);       // 20 x 20 image pixels around the tile
-    // stem weights [9 taps][16 groups of 4 channels] + bias [16] come from the kernel parameters (constant bank:
-    // every lane of a warp reads the same entry), not from shared memory, which the resident weights fill
+    // A warp owns ONE 8-channel unit (8 warps = the 64 channels = both 32-channel A stages of a tile) and keeps that
+    // unit's 72 weights + 8 biases in registers (read once from the kernel parameters); lane = halo pixel.  Warps 0-3
+    // fill the tile's first A stage, warps 4-7 the second one, concurrently.
     constexpr int kStemT = 32 * SM::STEM_WARPS;
+    static_assert(SM::STEM_WARPS == 8, "one stem warp per 8-channel unit");
     const int t = threadIdx.x - 192;                                     // 0..kStemT-1
-    const float4* w1 = reinterpret_cast<const float4*>(p.c1);
-    if (!RESIDENT) {
-      float4* ws = reinterpret_cast<float4*>(patch + 400);
-      for (int i = t; i < 9 * 16 + 16; i += kStemT) ws[i] = reinterpret_cast<const float4*>(p.c1)[i];
-      w1 = ws;                               // first use is behind the bar.sync below
-    }
-    const float4* b1 = w1 + 9 * 16;
-    int sa = 0, pa = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int unit = t >> 5;                                             // 8-channel unit 0..7
+    const int kbw = unit >> 2, g = unit & 3;                             // A stage of the tile / unit inside the stage
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) wr[tp][ch] = p.c1[tp * 64 + unit * 8 + ch];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) br[ch] = p.c1[9 * 64 + unit * 8 + ch];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       int cb, x0, y0, img;
       decode(tile, cb, x0, y0, img);
       asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");          // everyone is done with the previous patch
@@ -251,53 +255,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         patch[i] = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? __ldg(im + (size_t)gy * p.W + gx) : 0.f;
       }
       asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");
-      for (int kb = 0; kb < nkb; ++kb) {                                 // nkb == 2: channels kb*32 .. +31
-        mbar_wait(&a_empty[sa], pa ^ 1);
-        uint8_t* dst = sA + sa * kTcAStage;
-        for (int i = t; i < kTcKbGroups * kTcHalo * kTcHalo; i += kStemT) {
-          const int g = i / (kTcHalo * kTcHalo), px = i - g * (kTcHalo * kTcHalo);   // 8-channel unit, halo pixel
-          const int py = px / kTcHalo, pxx = px - py * kTcHalo;
-          const int gy = y0 - 1 + py, gx = x0 - 1 + pxx;
-          uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;                // outside the image: the NEXT conv's zero padding
-          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-            float v[9];
+      const int cst = 2 * it + kbw;                                      // running A-stage index (two per tile)
+      const int sa = cst % kTcNA, pa = (cst / kTcNA) & 1;
+      mbar_wait(&a_empty[sa], pa ^ 1);
+      uint8_t* dst = sA + sa * kTcAStage + g * kTcPlaneB;
+#pragma unroll 1
+      for (int px = lane; px < kTcHalo * kTcHalo; px += 32) {
+        const int py = px / kTcHalo, pxx = px - py * kTcHalo;
+        const int gy = y0 - 1 + py, gx = x0 - 1 + pxx;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;                  // outside the image: the NEXT conv's zero padding
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+          float e[8];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+          for (int ch = 0; ch < 8; ++ch) e[ch] = br[ch];
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = patch[(py + ky) * 20 + pxx + kx];
-            const int g4 = (kb * kTcKbGroups + g) * 2;                   // first 4-channel group of this unit
-            float e[8];
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float4 a = b1[g4 + hh];
+            for (int kx = 0; kx < 3; ++kx) {
+              const float v = patch[(py + ky) * 20 + pxx + kx];
 #pragma unroll
-              for (int tp = 0; tp < 9; ++tp) {
-                const float4 wv = w1[tp * 16 + g4 + hh];
-                a.x = fmaf(v[tp], wv.x, a.x); a.y = fmaf(v[tp], wv.y, a.y);
-                a.z = fmaf(v[tp], wv.z, a.z); a.w = fmaf(v[tp], wv.w, a.w);
-              }
-              e[4 * hh] = fmaxf(a.x, 0.f); e[4 * hh + 1] = fmaxf(a.y, 0.f);
-              e[4 * hh + 2] = fmaxf(a.z, 0.f); e[4 * hh + 3] = fmaxf(a.w, 0.f);
+              for (int ch = 0; ch < 8; ++ch) e[ch] = fmaf(v, wr[ky * 3 + kx][ch], e[ch]);
             }
-            __half2 h2[4], l2[4];
+          __half2 h2[4], l2[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __half ha = __float2half_rn(e[2 * j]), hb = __float2half_rn(e[2 * j + 1]);
-              h2[j] = __halves2half2(ha, hb);
-              l2[j] = __halves2half2(__float2half_rn((e[2 * j] - __half2float(ha)) * kLoScale),
-                                     __float2half_rn((e[2 * j + 1] - __half2float(hb)) * kLoScale));
-            }
-            hi = *reinterpret_cast<uint4*>(h2);
-            lo = *reinterpret_cast<uint4*>(l2);
+          for (int j = 0; j < 4; ++j) {
+            const float ea = fmaxf(e[2 * j], 0.f), eb = fmaxf(e[2 * j + 1], 0.f);
+            const __half ha = __float2half_rn(ea), hb = __float2half_rn(eb);
+            h2[j] = __halves2half2(ha, hb);
+            l2[j] = __halves2half2(__float2half_rn((ea - __half2float(ha)) * kLoScale),
+                                   __float2half_rn((eb - __half2float(hb)) * kLoScale));
           }
-          *reinterpret_cast<uint4*>(dst + g * kTcPlaneB + px * 16) = hi;
-          *reinterpret_cast<uint4*>(dst + kTcAPlane + g * kTcPlaneB + px * 16) = lo;
+          hi = *reinterpret_cast<uint4*>(h2);
+          lo = *reinterpret_cast<uint4*>(l2);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[sa]);
-        if (++sa == kTcNA) { sa = 0; pa ^= 1; }
+        *reinterpret_cast<uint4*>(dst + px * 16) = hi;
+        *reinterpret_cast<uint4*>(dst + kTcAPlane + px * 16) = lo;
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[sa]);
     }
   } else if (warp >= 2 && warp < 6) {
     // ------------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)
@@ -449,9 +445,9 @@ bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   }
   if (p.img) {   // fused first layer (image -> 64 channels) in front of a 64 -> 64 pooled layer
     if (p.nb != 64 || p.cin != 64 || p.cout_pad != 64 || !p.pool) return false;
-    // (weights streamed, 3 A stages: the stem warps set the pace here and need the deeper run-ahead; measured 8.2 ms
-    // vs 9.8 ms with resident weights + 2 A stages)
-    return launch_tc_t<64, true, 3, true, false>(ctx, p, num_sms);
+    // (weights resident, 2 A stages = one tile: the two stages are filled concurrently by stem warps 0-3 / 4-7;
+    // measured 7.6 ms vs 8.7 ms with streamed weights + 3 stages)
+    return launch_tc_t<64, true, 3, true, true>(ctx, p, num_sms);
   }
   if (p.nb == 64 && p.cin == 64 && p.cout_pad == 64)     // 64 -> 64 layers: weights resident in shared memory
     return p.pool ? launch_tc_t<64, true, 3, false, true>(ctx, p, num_sms) : launch_tc_t<64, false, 3, false, true>(ctx, p, num_sms);

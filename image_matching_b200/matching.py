@@ -237,10 +237,13 @@ class SuperPoint(_B200Module):
     @staticmethod
     def _to_lists(kp, sc, de, cnt_host):
         SuperPoint._check_counts(cnt_host)
-        keypoints = [kp[i, :n] for i, n in enumerate(cnt_host)]
-        scores = tuple(sc[i, :n] for i, n in enumerate(cnt_host))
-        descriptors = [de[i, :, :n] for i, n in enumerate(cnt_host)]
-        return keypoints, scores, descriptors
+        cap = kp.shape[1]
+        # one unbind per tensor (views) instead of a Python-level slice per image; only short images are narrowed
+        keypoints, scores, descriptors = list(kp.unbind(0)), list(sc.unbind(0)), list(de.unbind(0))
+        for i, n in enumerate(cnt_host):
+            if n != cap:
+                keypoints[i], scores[i], descriptors[i] = keypoints[i][:n], scores[i][:n], descriptors[i][:, :n]
+        return keypoints, tuple(scores), descriptors
 
     def forward(self, x):
         x = _image(x)
