@@ -36,6 +36,7 @@ GF_PAIR_QK = 9.664            # attention QK^T only
 NCU_CONV_DRAM_BYTES_PER_LAUNCH = 280.1e6
 GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers with Cin >= 64 (all but the Cin=1 stem and the two 1x1 heads)
 GF_IMG_CONV1 = 0.354                   # the Cin=1 stem, computed inside the fused first tc_conv launch
+GF_IMG_C1B = 2 * 9 * 64 * 64 * H * W / 1e9   # the 64->64 3x3 conv at full resolution (22.65 GF / image)
 
 
 def make_cfg():
@@ -331,24 +332,31 @@ def run_b200(args):
         e2e = total_pairs * args.steps / (e2e_ms / 1e3)
         dom = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
         roof = None
-        conv_names = [k for k in ("tc_conv3x3", "tc_conv3x3_stem") if k in prof]
-        if conv_names:
-            conv_ms = sum(prof[k]["ms_per_step"] for k in conv_names)
-            n_launch = sum(prof[k]["launches_per_step"] for k in conv_names)
-            flops_step = (GF_IMG_CONV3 + (GF_IMG_CONV1 if "tc_conv3x3_stem" in prof else 0.0)) * 1e9 * 2 * B
+        # roofline of the dominant kernel: the fused first launch of the encoder (stem conv 1->64 computed in the operand
+        # producer + the 64->64 3x3 conv at full resolution + 2x2 max-pool), one launch = one 16-image micro-batch
+        ck = "tc_conv3x3_stem" if "tc_conv3x3_stem" in prof else ("tc_conv3x3" if "tc_conv3x3" in prof else None)
+        if ck:
+            conv_ms = prof[ck]["ms_per_step"]
+            n_launch = prof[ck]["launches_per_step"]
+            gf_img = (GF_IMG_C1B + GF_IMG_CONV1) if ck == "tc_conv3x3_stem" else GF_IMG_CONV3
+            flops_step = gf_img * 1e9 * 2 * B
             ach = flops_step / (conv_ms / 1e3) / 1e12                  # algorithmic FLOPs (NOT x3 for the fp16 split)
-            roof = {"kernel": "tc_conv (SuperPoint 3x3 convolutions: implicit GEMM on tcgen05, fp16 hi/lo operand split; "
-                              "first layer fused into the second one's operand producer)",
+            all_conv_ms = sum(prof[k]["ms_per_step"] for k in ("tc_conv3x3", "tc_conv3x3_stem", "tc_conv1x1") if k in prof)
+            roof = {"kernel": ck + " (tc_conv.cu: fused stem + 64->64 3x3 conv @ 480x640 + max-pool; implicit GEMM on "
+                              "tcgen05, fp16 hi/lo operand split, weights resident in shared memory)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sustained"], "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
                     "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
                     "flops_per_launch": flops_step / max(n_launch, 1), "avg_launch_ms": conv_ms / max(n_launch, 1),
+                    "algorithmic_bytes_per_launch": 16 * (H * W * 4 + 64 * (H // 2) * (W // 2) * 2 * 2),
                     "share_of_step": conv_ms / sum(p["ms_per_step"] for p in prof.values()),
+                    "all_conv_kernels_share_of_step": all_conv_ms / sum(p["ms_per_step"] for p in prof.values()),
+                    "all_conv_kernels_tflops": (GF_IMG_CONV3 + GF_IMG_CONV1 + 0.472) * 2 * B / all_conv_ms,
                     "dominant_by_time": dom,
                     "note": "achieved counts algorithmic FLOPs once; the kernel issues 3 fp16 products per algorithmic "
                             "product (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32-class accuracy: 0 keypoint flips vs the "
                             "reference), i.e. %.0f TFLOP/s of fp16 tensor work against the bf16/fp16 dense peak; "
-                            "traffic = dram bytes of the 64->64 full-resolution layer per 16-image launch (ncu)" % (3 * ach)}
+                            "traffic = dram bytes per launch from ncu (profiles/r01_ncu_tc_conv_stem.txt)" % (3 * ach)}
         line = {"metric": "image-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
