@@ -31,9 +31,9 @@ SINKHORN = 30
 GF_PAIR_TOTAL = 135.43        # algorithmic GFLOP per pair (C1/C2/C4)
 GF_PAIR_QK = 9.664            # attention QK^T only
 # dram__bytes_read+write of the dominant conv launch (fused stem + 64->64 layer at 480x640, 16-image micro-batch) from
-# profiles/r01_ncu_tc_conv_stem.txt: 19.9 MB read + 260.2 MB written; algorithmic = 19.7 MB images in + 314.6 MB of
+# profiles/r01_ncu_tc_conv_stem.txt: 19.8 MB read + 262.2 MB written; algorithmic = 19.7 MB images in + 314.6 MB of
 # pooled fp16 hi/lo planes out (part of the output is still in L2 when the kernel ends)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 280.1e6
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 282.0e6
 GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers with Cin >= 64 (all but the Cin=1 stem and the two 1x1 heads)
 GF_IMG_CONV1 = 0.354                   # the Cin=1 stem, computed inside the fused first tc_conv launch
 GF_IMG_C1B = 2 * 9 * 64 * 64 * H * W / 1e9   # the 64->64 3x3 conv at full resolution (22.65 GF / image)

@@ -590,7 +590,7 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
 
 void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A, int lda, float* C, int ldc,
                 size_t M, bool relu, bool accumulate, float* C_lo = nullptr, float* VT = nullptr,
-                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1) {   // C_lo set => fp16 plane outputs
+                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1, float lo_scale = 1.f) {   // C_lo set => fp16 plane outputs
   GemmParams p;
   p.A = A; p.lda = lda; p.strideA = 0;
   p.Bw = h->d_w + L.w_off; p.ldb = L.K; p.strideB = 0;
@@ -599,7 +599,7 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.M = (int)M; p.N = L.N; p.K = L.K; p.batch = 1;
   p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
   p.C_lo = C_lo; p.out_f16 = C_lo ? 1 : 0;
-  p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np;
+  p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np; p.lo_scale = lo_scale;
   if (h->use_tc_gemm && launch_tc_gemm(ctx, p, h->d_w + L.w_hi_off, h->d_w + L.w_lo_off, h->num_sms)) return;
   launch_gemm(ctx, p);
 }
@@ -693,6 +693,15 @@ void sg_scores(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, int N, int
   p.C = w.S; p.ldc = w.ldS; p.strideC = (long long)N * w.ldS;
   p.bias = nullptr; p.M = N; p.N = M; p.K = D; p.batch = B;
   p.alpha = 1.f / sqrtf((float)D); p.relu = 0; p.accumulate = 0;
+  if (h->use_tc_gemm && w.QKV_lo && D % 64 == 0) {
+    // scores on the tensor cores: side 1's projected descriptors once more as fp16 hi / lo*2048 operand planes (the
+    // q|k|v buffers are free now), then ONE batched fp16x3 GEMM  S_b = mdesc0_b mdesc1_b^T / sqrt(D)  over all pairs
+    const size_t side = (size_t)B * w.Np;
+    run_linear(h, ctx, h->final_proj, w.X + side * 2 * D, 2 * D, w.QKV, D, side, false, false, w.QKV_lo, nullptr, nullptr,
+               0, 1, 2048.f);
+    p.batch_rows_a = w.Np; p.batch_rows_b = w.Np;
+    if (launch_tc_gemm(ctx, p, w.QKV, w.QKV_lo, h->num_sms)) return;
+  }
   launch_gemm(ctx, p);
 }
 

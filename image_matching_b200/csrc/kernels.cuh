@@ -107,6 +107,9 @@ struct GemmParams {
   int out_f16 = 0;
   float* C_lo = nullptr;
   float* VT = nullptr; float* VT_lo = nullptr; int vt_col0 = 0; int vt_np = 1;
+  float lo_scale = 1.f;        // out_f16: C_lo = fp16((v - C) * lo_scale)  (2048 for planes consumed as the weight operand)
+  // tensor-core GEMM, batch > 1: rows of A / W of problem b start at b * batch_rows_a / b * batch_rows_b of the same arrays
+  int batch_rows_a = 0, batch_rows_b = 0;
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
 // tcgen05 fp16x3 version for weight GEMMs (w_hi / w_lo: [N][K] fp16 planes, lo scaled by 2048); false if declined

@@ -50,8 +50,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // batched mode (score matrix): `batch` independent problems whose A / W rows are stacked with a fixed row pitch in
+  // the SAME 2-D arrays (tensor-map row coordinate = bt * pitch + tile row) and whose C blocks are strideC apart
   const int m_tiles = cdiv(p.M, 128), n_tiles = cdiv(p.N, kGemmNT);
-  const int total = m_tiles * n_tiles;
+  const int per_batch = m_tiles * n_tiles;
+  const int total = per_batch * p.batch;
   const int nkb = cdiv(p.K, kGemmKB);
 
   if (threadIdx.x == 0) {
@@ -69,15 +72,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     int s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * kGemmNT;
+      const int bt = tile / per_batch, tt = tile - bt * per_batch;
+      const int m0 = (tt / n_tiles) * 128, n0 = (tt % n_tiles) * kGemmNT;
+      const int ra = bt * p.batch_rows_a + m0, rb = bt * p.batch_rows_b + n0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], 2 * kGemmATile + 2 * kGemmBTile);
         uint8_t* st = smem + s * kGemmStage;
-        tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, m0);
-        tma_load_2d(st + kGemmATile, &tm_a, &full[s], kb * kGemmKB + 32, m0);
-        tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * kGemmKB, n0);
-        tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * kGemmKB, n0);
+        tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, ra);
+        tma_load_2d(st + kGemmATile, &tm_a, &full[s], kb * kGemmKB + 32, ra);
+        tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * kGemmKB, rb);
+        tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * kGemmKB, rb);
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
       }
     }
@@ -154,13 +159,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int mrow = w4 * 32 + lane;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-      const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * kGemmNT;
+      const int bt = tile / per_batch, tt = tile - bt * per_batch;
+      const int m0 = (tt / n_tiles) * 128, n0 = (tt % n_tiles) * kGemmNT;
       const int buf = lt & 1, aph = (lt >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       const int r = m0 + mrow;
       const bool rok = r < p.M;
-      float* crow = p.C + (size_t)r * p.ldc;
+      float* crow = p.C + (size_t)bt * p.strideC + (size_t)r * p.ldc;
       const int blk = p.VT ? r / p.vt_np : 0, rr = p.VT ? r - blk * p.vt_np : 0;
 #pragma unroll 1
       for (int ch = 0; ch < kGemmNT / 32; ++ch) {
@@ -190,8 +196,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               // fp16 hi / lo planes (+ transposed V planes): consumed by the attention kernel
               const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
               const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-              const __half2 l01 = __floats2half2_rn(o.x - b01.x, o.y - b01.y);
-              const __half2 l23 = __floats2half2_rn(o.z - b23.x, o.w - b23.y);
+              const float ls = p.lo_scale;     // 1: attention planes (unscaled residual); 2048: weight-side operand planes
+              const __half2 l01 = __floats2half2_rn((o.x - b01.x) * ls, (o.y - b01.y) * ls);
+              const __half2 l23 = __floats2half2_rn((o.z - b23.x) * ls, (o.w - b23.y) * ls);
               __half* ch = reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c;
               __half* cl = reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c;
               *reinterpret_cast<__half2*>(ch) = h01; *reinterpret_cast<__half2*>(ch + 2) = h23;
@@ -254,12 +261,17 @@ static bool make_sw128_map2(CUtensorMap* m, const float* base, size_t rows, int 
 // W_hi / W_lo: [N][K] row-major fp16 planes (hi, lo*2048; split at pack time).  Requirements: batch == 1, K % 8 == 0,
 // lda % 4 == 0, N % 4 == 0 and 16-byte aligned bases; anything else is declined (caller uses the CUDA-core GEMM).
 bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms) {
-  if (p.batch != 1 || p.K % 8 || p.lda % 4 || p.ldc % 4 || p.N % 4 || p.K < 32 || p.M <= 0) return false;
+  if (p.batch < 1 || p.K % 8 || p.lda % 4 || p.ldc % 4 || (p.N % 4 && p.batch == 1) || p.K < 32 || p.M <= 0) return false;
+  if (p.batch > 1 && (p.out_f16 || p.accumulate || p.strideC % 4)) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(w_hi)) & 15) return false;
   ProfScope prof__(ctx, "tc_gemm");
   CUtensorMap ma, mh, ml;
-  if (!make_sw128_map2(&ma, p.A, (size_t)p.M, p.K, p.lda, 128) ||
-      !make_sw128_map_f16(&mh, w_hi, (size_t)p.N, p.K, p.K, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, (size_t)p.N, p.K, p.K, kGemmNT))
+  // batched: the maps span all stacked problems (rows beyond a problem's own M / N are computed but never stored)
+  const size_t a_rows = p.batch > 1 ? (size_t)(p.batch - 1) * p.batch_rows_a + p.M : (size_t)p.M;
+  const size_t w_rows = p.batch > 1 ? (size_t)(p.batch - 1) * p.batch_rows_b + p.N : (size_t)p.N;
+  const int ldw = p.batch > 1 ? p.ldb : p.K;
+  if (!make_sw128_map2(&ma, p.A, a_rows, p.K, p.lda, 128) ||
+      !make_sw128_map_f16(&mh, w_hi, w_rows, p.K, ldw, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, w_rows, p.K, ldw, kGemmNT))
     return false;
   static bool attr_set = false;
   if (!attr_set) {
@@ -267,7 +279,7 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
       return false;
     attr_set = true;
   }
-  const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT);
+  const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT) * p.batch;
   const int grid = total < num_sms ? total : num_sms;
   tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
