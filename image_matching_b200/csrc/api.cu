@@ -43,7 +43,7 @@ struct ConvLayer {      // packed conv on C4-planar activations
 struct Linear {         // packed [N][K] row-major weight + bias
   int N = 0, K = 0;
   size_t w_off = 0, b_off = 0;
-  size_t w_hi_off = 0, w_lo_off = 0;   // tf32-exact hi / lo planes of the same matrix (tensor-core path)
+  size_t w_hi_off = 0, w_lo_off = 0;   // fp16 hi / lo*2048 planes of the same matrix (tensor-core path)
 };
 
 constexpr int kHeads = 4;

@@ -3,7 +3,7 @@
 // Reference: superglue/models/superglue_test.py:49-60 (MLP), :98-107 (proj / merge), :110-119 (propagation MLP),
 // :214-216 (final_proj).
 //
-//   C[M,N] (+)= A[M,K] * W[N,K]^T + bias   (optional ReLU, residual accumulate, tf32 hi/lo output planes, V^T copy)
+//   C[M,N] (+)= A[M,K] * W[N,K]^T + bias   (optional ReLU, residual accumulate, fp16 hi/lo output planes, V^T copy; batched mode for the score matrix)
 //
 // Persistent CTA per SM, 320 threads:
 //   warp 0      TMA producer  : per 64-column K block the raw fp32 A tile (two 128 rows x 128 B boxes) and the
@@ -116,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
   } else if (warp >= 2 && warp < 6) {
-    // ------------------------------------------------------------------ splitter: raw fp32 A -> tf32 hi / lo
+    // ------------------------------------------------------------------ splitter: raw fp32 A -> fp16 hi / lo planes
     const int t = threadIdx.x - 64;    // 0..127
     int s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {

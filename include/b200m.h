@@ -171,7 +171,7 @@ int b200m_matching_forward_u8(b200m_handle* h, const uint8_t* image0, const uint
                            void* ws, size_t ws_bytes, void* stream);
 
 /* Test hook: run ONE packed 3x3 encoder/head layer (0=inc.conv[3], 1..2=down1, 3..4=down2, 5..6=down3, 7=convPa|convDa)
- * on `in` (n,cin,H,W) -> `out` (n,cout,H',W') with the tcgen05 3xTF32 kernel (use_tc=1) or the fp32 CUDA-core
+ * on `in` (n,cin,H,W) -> `out` (n,cout,H',W') with the tcgen05 fp16 hi/lo-split kernel (use_tc=1) or the fp32 CUDA-core
  * kernel (use_tc=0), so the two implementations can be compared layer by layer. */
 int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* in, float* out, int n, int H,
                            int W, void* stream);
