@@ -298,6 +298,25 @@ def run_b200(args):
         step_e2e()
     barrier()
     e2e_u8_ms = 1e3 * (time.perf_counter() - t0)
+    # informational: the caller's next step on the device -- batched estimateAffinePartial2D(RANSAC)
+    # straight from the device-resident matches, then the matrices / inlier masks read back
+    from image_matching_b200 import estimate_affine_partial_2d
+
+    def step_registered():
+        out = m.forward_device(d0, d1)
+        mats, inl, info = estimate_affine_partial_2d(m, out["keypoints0"], out["keypoints1"], out["matches0"],
+                                                     out["counts"][0], 7.0)
+        return mats.cpu(), inl.cpu(), info.cpu()
+
+    step_registered()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(args.steps):
+        reg = step_registered()
+    r1.record()
+    barrier()
+    reg_ms = r0.elapsed_time(r1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -367,6 +386,12 @@ def run_b200(args):
                         "note": "Matching.forward on fp32 host images; the upload of step i+1 overlaps step i on a side stream"},
                 "e2e_uint8_images": {"value": total_pairs * args.steps / (e2e_u8_ms / 1e3), "unit": "pairs/s",
                                      "h2d_bytes_per_step": int(2 * B * H * W), "ms_per_step": e2e_u8_ms / args.steps},
+                "with_registration": {"value": B * args.steps / (reg_ms / 1e3), "unit": "pairs/s (this rank)",
+                                      "ms_per_step": reg_ms / args.steps,
+                                      "inliers_per_pair": float(reg[2][:, 1].float().mean()),
+                                      "ransac_iterations_per_pair": float(reg[2][:, 2].float().mean()),
+                                      "note": "forward_device + b200m_estimate_affine_partial (cv2-identical RANSAC, "
+                                              "7 px) + D2H of matrices and inlier masks"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.result(),
                 "roofline": roof,
@@ -394,7 +419,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step (C2 = 64)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic pairs generated per rank")
-    ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs timed through the CPU oracle (cpu_baseline)")
+    ap.add_argument("--cpu-pairs", type=int, default=16, help="pairs timed through the CPU oracle (cpu_baseline)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

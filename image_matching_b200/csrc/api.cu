@@ -1016,6 +1016,32 @@ int b200m_knn_ratio_match(b200m_handle* h, const float* desc0, const float* desc
   return finish(h, ctx);
 }
 
+int b200m_estimate_affine_partial(b200m_handle* h, const float* kpts0, const float* kpts1, const int64_t* matches0,
+                                  const int* counts0, int B, int N, int M, double ransac_reproj_threshold,
+                                  int max_iters, double confidence, int refine_iters, double* matrices,
+                                  uint8_t* inlier0, int* info, void* stream) {
+  if (!h || !kpts0 || !kpts1 || !matches0 || !matrices || !inlier0 || !info)
+    return fail(B200M_ERR_INVALID, "null argument");
+  if (B < 0 || N < 0 || M < 0) return fail(B200M_ERR_INVALID, "negative size");
+  LaunchCtx ctx = make_ctx(h, stream);
+  if (!launch_ransac_affine_partial(ctx, kpts0, kpts1, (const long long*)matches0, counts0, B, N, M,
+                                    ransac_reproj_threshold, max_iters, confidence, refine_iters > 0, matrices,
+                                    inlier0, info))
+    return fail(B200M_ERR_INVALID, "N = %d keypoints per image exceed the estimator's shared-memory capacity", N);
+  return finish(h, ctx);
+}
+
+int b200m_warp_affine(b200m_handle* h, const void* src, int dtype, int B, int src_h, int src_w,
+                      const double* matrices, void* dst, int dst_h, int dst_w, void* stream) {
+  if (!h || !src || !matrices || !dst) return fail(B200M_ERR_INVALID, "null argument");
+  if (src_h <= 0 || src_w <= 0 || src_h > 32767 || src_w > 32767)
+    return fail(B200M_ERR_INVALID, "source size %dx%d outside [1, 32767] (cv2's short coordinate maps)", src_h, src_w);
+  LaunchCtx ctx = make_ctx(h, stream);
+  if (!launch_warp_affine(ctx, src, dtype, B, src_h, src_w, matrices, dst, dst_h, dst_w))
+    return fail(B200M_ERR_INVALID, "dtype %d not supported (0 = uint8, 1 = float32, 2 = float64)", dtype);
+  return finish(h, ctx);
+}
+
 size_t b200m_superglue_workspace_bytes(const b200m_handle* h, int B, int N, int M) {
   if (!h) return 0;
   Arena A(nullptr, 0);

@@ -92,6 +92,16 @@ void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_tota
 bool launch_knn_ratio(LaunchCtx& ctx, const float* desc0, const float* desc1, const int* counts0, const int* counts1,
                       int B, int D, int N, int M, float ratio, long long* match, float* dist1, float* dist2);
 
+// ------------------------------------------------------------------ registration after the path (sp_register.cu)
+// cv2.estimateAffinePartial2D(RANSAC) over the valid matches of each pair + cv2.warpAffine (superpoint_glue_test.py:83-101)
+size_t ransac_smem_bytes(int N);
+bool launch_ransac_affine_partial(LaunchCtx& ctx, const float* kpts0, const float* kpts1, const long long* matches0,
+                                  const int* counts0, int B, int N, int M, double thr, int max_iters, double confidence,
+                                  int refine, double* matrices, unsigned char* inlier0, int* info);
+// dtype: 0 = uint8, 1 = float32, 2 = float64
+bool launch_warp_affine(LaunchCtx& ctx, const void* src, int dtype, int B, int sH, int sW, const double* matrices,
+                        void* dst, int dH, int dW);
+
 // ------------------------------------------------------------------ SuperGlue linear (sg_linear.cu)
 struct GemmParams {
   const float* A; int lda; long long strideA;   // [M,K] row-major

@@ -54,6 +54,9 @@ SIGNATURES = {
     "b200m_score_matrix": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "b200m_sinkhorn": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "b200m_knn_ratio_match": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P, _P, _P, _P]),
+    "b200m_estimate_affine_partial": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_double, _I, C.c_double, _I, _P, _P, _P,
+                                           _P]),
+    "b200m_warp_affine": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "b200m_match_select": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "b200m_matching_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "b200m_matching_forward": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,

@@ -17,6 +17,10 @@
  *   superglue_test.py:256-260  (final_proj + scores)       -> b200m_score_matrix
  *   superglue_test.py:141-170  (log_optimal_transport)     -> b200m_sinkhorn
  *   superglue_test.py:268-285  (match selection)           -> b200m_match_select
+ * Callers' next steps (SURVEY.md 8 f):
+ *   superpoint_glue_test.py:83-92 (cv2.estimateAffinePartial2D, RANSAC) -> b200m_estimate_affine_partial
+ *   superpoint_glue_test.py:101   (cv2.warpAffine)                      -> b200m_warp_affine
+ *   superpoint_flann_test.py:69-78 (FLANN knnMatch + ratio test)        -> b200m_knn_ratio_match
  *
  * Conventions
  *   - plain C: pointers + sizes only, no torch types.  All tensor pointers are DEVICE pointers
@@ -143,6 +147,26 @@ int b200m_sinkhorn(b200m_handle* h, const float* S, int B, int N, int M, int ite
 int b200m_knn_ratio_match(b200m_handle* h, const float* desc0, const float* desc1, const int* counts0,
                           const int* counts1, int B, int N, int M, float ratio, int64_t* matches, float* dist1,
                           float* dist2, void* stream);
+/* Registration step of the caller, superpoint_glue_test.py:83-92:
+ *   valid = matches > -1; mkpts0 = kpts0[valid]; mkpts1 = kpts1[matches[valid]]
+ *   Matrix, mask = cv2.estimateAffinePartial2D(mkpts0, mkpts1, method=cv2.RANSAC, ransacReprojThreshold=thr)
+ * for B pairs at once, straight from the device-resident outputs of b200m_matching_forward (no D2H round trip).
+ * kpts0 (B,N,2) / kpts1 (B,M,2) xy fp32, matches0 (B,N) int64, counts0 (B) valid keypoints per pair or NULL.
+ * Restates OpenCV 4.13's RANSAC (fixed RNG seed, adaptive iteration bound; cv2's defaults are max_iters 2000,
+ * confidence 0.99, refine_iters 10): `inlier0` (B,N) uint8 is cv2's mask scattered back to keypoint indices of
+ * image0 (bit-identical set), `matrices` (B,2,3) float64 is cv2's matrix to ~1e-12 (the Levenberg-Marquardt
+ * refinement is replaced by its closed-form fixed point; refine_iters == 0 skips it like cv2 does).
+ * info (B,4) int32: correspondences, inliers, RANSAC iterations run, 1 if a model was found (cv2: Matrix is not None). */
+int b200m_estimate_affine_partial(b200m_handle* h, const float* kpts0, const float* kpts1, const int64_t* matches0,
+                                  const int* counts0, int B, int N, int M, double ransac_reproj_threshold,
+                                  int max_iters, double confidence, int refine_iters, double* matrices,
+                                  uint8_t* inlier0, int* info, void* stream);
+/* cv2.warpAffine(src, Matrix, (dst_w, dst_h)) with the defaults the caller uses (superpoint_glue_test.py:101:
+ * INTER_LINEAR, BORDER_CONSTANT 0, forward matrix inverted internally) for B single-channel images, each with its
+ * own matrix (B,2,3) float64 on the device.  dtype: 0 = uint8, 1 = float32, 2 = float64 (the caller's case).
+ * Bit-identical to cv2 4.13 (10-bit fixed-point coordinates, 1/32-pixel interpolation grid). */
+int b200m_warp_affine(b200m_handle* h, const void* src, int dtype, int B, int src_h, int src_w,
+                      const double* matrices, void* dst, int dst_h, int dst_w, void* stream);
 /* stage: Z (B,N+1,M+1) -> matches / scores */
 int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M,
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
