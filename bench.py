@@ -33,7 +33,7 @@ GF_PAIR_QK = 9.664            # attention QK^T only
 # dram__bytes_read+write of the dominant conv launch (fused stem + 64->64 layer at 480x640, 16-image micro-batch) from
 # profiles/r01_ncu_tc_conv_stem.txt: 19.8 MB read + 262.2 MB written; algorithmic = 19.7 MB images in + 314.6 MB of
 # pooled fp16 hi/lo planes out (part of the output is still in L2 when the kernel ends)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 282.0e6
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 282.0e6   # per 16-image launch (17.6 MB / image; scaled by the images one launch covers)
 GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers with Cin >= 64 (all but the Cin=1 stem and the two 1x1 heads)
 GF_IMG_CONV1 = 0.354                   # the Cin=1 stem, computed inside the fused first tc_conv launch
 GF_IMG_C1B = 2 * 9 * 64 * 64 * H * W / 1e9   # the 64->64 3x3 conv at full resolution (22.65 GF / image)
@@ -317,6 +317,17 @@ def run_b200(args):
     r1.record()
     barrier()
     reg_ms = r0.elapsed_time(r1)
+    # informational: single-pair latency (the reference script's own batch_size=1 loop, superpoint_glue_test.py:66,72)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        m.forward_device(d0[:1], d1[:1])
+    barrier()
+    l0.record()
+    for _ in range(20):
+        m.forward_device(d0[:1], d1[:1])
+    l1.record()
+    barrier()
+    lat_ms = l0.elapsed_time(l1) / 20
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -364,10 +375,12 @@ def run_b200(args):
             roof = {"kernel": ck + " (tc_conv.cu: fused stem + 64->64 3x3 conv @ 480x640 + max-pool; implicit GEMM on "
                               "tcgen05, fp16 hi/lo operand split, weights resident in shared memory)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
+                    "frac": ach / pk["tf_sustained"],
+                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH * (2 * B / max(n_launch, 1)) / 16,
                     "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
                     "flops_per_launch": flops_step / max(n_launch, 1), "avg_launch_ms": conv_ms / max(n_launch, 1),
-                    "algorithmic_bytes_per_launch": 16 * (H * W * 4 + 64 * (H // 2) * (W // 2) * 2 * 2),
+                    "algorithmic_bytes_per_launch": int(2 * B / max(n_launch, 1) * (H * W * 4 + 64 * (H // 2) * (W // 2) * 2 * 2)),
+                    "images_per_launch": 2 * B / max(n_launch, 1),
                     "share_of_step": conv_ms / sum(p["ms_per_step"] for p in prof.values()),
                     "all_conv_kernels_share_of_step": all_conv_ms / sum(p["ms_per_step"] for p in prof.values()),
                     "all_conv_kernels_tflops": (GF_IMG_CONV3 + GF_IMG_CONV1 + 0.472) * 2 * B / all_conv_ms,
@@ -392,6 +405,7 @@ def run_b200(args):
                                       "ransac_iterations_per_pair": float(reg[2][:, 2].float().mean()),
                                       "note": "forward_device + b200m_estimate_affine_partial (cv2-identical RANSAC, "
                                               "7 px) + D2H of matrices and inlier masks"},
+                "latency_batch1_ms": lat_ms,
                 "gpu_launches": int(launches),
                 "clocks": sampler.result(),
                 "roofline": roof,

@@ -98,6 +98,7 @@ struct b200m_handle {
   bool use_fused_stem = true;    // first conv computed inside the second conv's kernel (B200M_STEM_IMPL=unfused: two kernels)
   bool use_fused_gnn = true;     // fused merge/mlp/residual/q|k|v layer kernel (B200M_GNN_IMPL=unfused: four GEMM launches)
   int num_sms = 148;
+  int sp_micro_batch = kSpMicroBatch;   // images per SuperPoint micro-batch (B200M_SP_MICROBATCH overrides)
 };
 
 namespace {
@@ -503,7 +504,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool 
   if (H < 8 || W < 8) return fail(B200M_ERR_INVALID, "image smaller than 8x8");
   const int D = h->cfg.descriptor_dim;
   SpDims d = sp_dims(h, H, W);
-  const int mb = std::min(n_images, kSpMicroBatch);
+  const int mb = std::min(n_images, h->sp_micro_batch);
   Arena A(ws, ws_bytes);
   SpWs w;
   if (!sp_carve(h, d, mb, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperPoint workspace too small: need %zu bytes", A.off);
@@ -544,7 +545,7 @@ size_t sp_ws_bytes(const b200m_handle* h, int n_images, int H, int W) {
   SpDims d = sp_dims(h, H, W);
   Arena A(nullptr, 0);
   SpWs w;
-  sp_carve(h, d, std::max(1, std::min(n_images, kSpMicroBatch)), A, w);
+  sp_carve(h, d, std::max(1, std::min(n_images, h->sp_micro_batch)), A, w);
   return A.off + 256;
 }
 
@@ -796,6 +797,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_fused_stem = !(impl && strcmp(impl, "unfused") == 0);
   impl = getenv("B200M_GNN_IMPL");
   h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
+  impl = getenv("B200M_SP_MICROBATCH");
+  if (impl && atoi(impl) > 0) h->sp_micro_batch = std::min(atoi(impl), 256);
   *out = h;
   return B200M_OK;
 }

@@ -1,6 +1,8 @@
 // SuperPoint detector post-processing and descriptor sampling (HBM / shared-memory bound, fp32,
 // compare-only NMS => bit-exact given the same heat-map).
 // Reference: superpoint/models/superpoint_test.py:7-52 and :128-155.
+#include <stdlib.h>
+#include <string.h>
 #include "kernels.cuh"
 
 namespace b200m {
@@ -153,12 +155,167 @@ static void launch_nms_r(LaunchCtx& ctx, const float* heat, float* ss, unsigned 
 #undef B200M_NMS_PASS
 }
 
+// ---- nms_radius == 4 (the reference default): all five pools in ONE kernel ---------------------------------------
+// A 32x32 output tile with the 20-pixel dependency halo (72x72 scores) stays in shared memory through the five chained
+// 9x9 max-pools; pool k is evaluated only where its result can still reach the tile (the valid region shrinks by 4
+// pixels = one float4 chunk per pool), so the halo costs 2.5x redundant work instead of 5x.  Each pool is separable and
+// evaluated with register sliding windows: a row-pass thread loads three float4 chunks and emits four outputs
+// (9 three-input max instructions instead of 32 two-input ones), a column-pass thread walks 12 rows for four outputs.
+// The intermediate maps (mask, suppression flags) never leave shared memory: one read of the heat-map, one launch
+// (the five-pass version moved ~0.5 GB through the L2 per 16 images and spent 140 us on them; this one ~45 us).
+constexpr int kNfT = 32, kNfHalo = 20, kNfW = kNfT + 2 * kNfHalo;   // 72 = 18 chunks of 4
+constexpr int kNfC = kNfW / 4;
+
+struct NmsFusedSmem {
+  float s[kNfW][kNfW];            // scores, -inf outside the image
+  float t[kNfW][kNfW];            // row-pass result of the current pool
+  unsigned char m[kNfW][kNfW];    // max mask
+  unsigned char sp[kNfW][kNfW];   // suppression flags of the current round
+};
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// SRC: 0 = scores, 1 = mask as 0/1, 2 = suppressed scores (supp ? 0 : s); out-of-image pixels are -inf in all three
+template <int SRC>
+__device__ __forceinline__ float4 nms_src_chunk(const NmsFusedSmem& S, int y, int c) {
+  const float4 sv = *reinterpret_cast<const float4*>(&S.s[y][4 * c]);
+  if (SRC == 0) return sv;
+  const float NEG = -INFINITY;
+  if (SRC == 1) {
+    const uchar4 mv = *reinterpret_cast<const uchar4*>(&S.m[y][4 * c]);
+    return make_float4(sv.x == NEG ? NEG : (float)mv.x, sv.y == NEG ? NEG : (float)mv.y,
+                       sv.z == NEG ? NEG : (float)mv.z, sv.w == NEG ? NEG : (float)mv.w);
+  }
+  const uchar4 pv = *reinterpret_cast<const uchar4*>(&S.sp[y][4 * c]);
+  return make_float4(pv.x && sv.x != NEG ? 0.f : sv.x, pv.y && sv.y != NEG ? 0.f : sv.y,
+                     pv.z && sv.z != NEG ? 0.f : sv.z, pv.w && sv.w != NEG ? 0.f : sv.w);
+}
+
+// pool number K (0..4) of the chain: input valid on [4K, 72-4K)^2, output on [4K+4, 72-4K-4)^2
+template <int K, int SRC>
+__device__ __forceinline__ void nms_row_pass(NmsFusedSmem& S) {
+  constexpr int rows = kNfW - 8 * K, c0 = K + 1, nc = kNfC - 2 * (K + 1);
+  for (int i = threadIdx.x; i < rows * nc; i += 256) {
+    const int y = 4 * K + i / nc, c = c0 + i % nc;
+    const float4 a = nms_src_chunk<SRC>(S, y, c - 1), b = nms_src_chunk<SRC>(S, y, c), d = nms_src_chunk<SRC>(S, y, c + 1);
+    // inputs a.x..a.w b.x..b.w d.x..d.w = positions -4..7 relative to the chunk; output j covers positions j-4..j+4
+    const float core = fmaxf(max3(a.w, b.x, b.y), max3(b.z, b.w, d.x));     // positions -1..4, common to all four
+    float4 o;
+    o.x = fmaxf(max3(a.x, a.y, a.z), core);                                  // -4..4
+    o.y = fmaxf(max3(a.y, a.z, d.y), core);                                  // -3..5
+    o.z = fmaxf(max3(a.z, d.y, d.z), core);                                  // -2..6
+    o.w = fmaxf(max3(d.y, d.z, d.w), core);                                  // -1..7
+    *reinterpret_cast<float4*>(&S.t[y][4 * c]) = o;
+  }
+}
+
+// column pass + the element-wise step that follows pool K.  EP: 0 -> m = (s == P(s));  1 -> supp = P(m) > 0;
+// 2 -> m |= (ss == P(ss)) & ~supp.  `fin` receives (y, x, keep) for the last pool.
+template <int K, int EP, typename Fin>
+__device__ __forceinline__ void nms_col_pass(NmsFusedSmem& S, Fin fin) {
+  constexpr int lo = 4 * (K + 1), w = kNfW - 8 * (K + 1), g0 = K + 1, ng = kNfC - 2 * (K + 1);
+  const float NEG = -INFINITY;
+  for (int i = threadIdx.x; i < w * ng; i += 256) {
+    const int x = lo + i % w, g = g0 + i / w;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = S.t[4 * g - 4 + k][x];
+    const float core = fmaxf(max3(v[3], v[4], v[5]), max3(v[6], v[7], v[8]));
+    float o[4];
+    o[0] = fmaxf(max3(v[0], v[1], v[2]), core);
+    o[1] = fmaxf(max3(v[1], v[2], v[9]), core);
+    o[2] = fmaxf(max3(v[2], v[9], v[10]), core);
+    o[3] = fmaxf(max3(v[9], v[10], v[11]), core);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int y = 4 * g + j;
+      const float sc = S.s[y][x];
+      const bool inside = sc != NEG;
+      if (EP == 0) {
+        S.m[y][x] = inside && sc == o[j];
+      } else if (EP == 1) {
+        S.sp[y][x] = o[j] > 0.f;
+      } else {
+        const bool sup = S.sp[y][x] != 0;
+        const float ss = sup ? 0.f : sc;
+        const bool mk = S.m[y][x] != 0 || (inside && !sup && ss == o[j]);
+        if (K < 4) S.m[y][x] = mk;
+        else fin(y, x, mk, sc);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nms_fused_r4_kernel(const float* __restrict__ heat, float* __restrict__ nms_dense,
+                                                           int H8, int W8, float thr, int border,
+                                                           unsigned long long* __restrict__ cand_keys,
+                                                           int* __restrict__ cand_counts, int cand_cap,
+                                                           int* __restrict__ overflow_flag) {
+  extern __shared__ __align__(16) unsigned char nms_smem_raw[];
+  NmsFusedSmem& S = *reinterpret_cast<NmsFusedSmem*>(nms_smem_raw);
+  const int n = blockIdx.z;
+  const size_t img = (size_t)n * H8 * W8;
+  const int x0 = blockIdx.x * kNfT - kNfHalo, y0 = blockIdx.y * kNfT - kNfHalo;   // multiples of 4; W8 is one too
+  const float NEG = -INFINITY;
+  for (int i = threadIdx.x; i < kNfW * kNfC; i += 256) {
+    const int y = i / kNfC, c = i - y * kNfC;
+    const int gy = y0 + y, gx = x0 + 4 * c;
+    float4 v = make_float4(NEG, NEG, NEG, NEG);
+    if (gy >= 0 && gy < H8 && gx >= 0 && gx < W8)
+      v = *reinterpret_cast<const float4*>(heat + img + (size_t)gy * W8 + gx);
+    *reinterpret_cast<float4*>(&S.s[y][4 * c]) = v;
+  }
+  auto none = [](int, int, bool, float) {};
+  __syncthreads();
+  nms_row_pass<0, 0>(S); __syncthreads(); nms_col_pass<0, 0>(S, none); __syncthreads();   // m = s == P(s)
+  nms_row_pass<1, 1>(S); __syncthreads(); nms_col_pass<1, 1>(S, none); __syncthreads();   // supp = P(m) > 0
+  nms_row_pass<2, 2>(S); __syncthreads(); nms_col_pass<2, 2>(S, none); __syncthreads();   // m |= ...
+  nms_row_pass<3, 1>(S); __syncthreads(); nms_col_pass<3, 1>(S, none); __syncthreads();
+  nms_row_pass<4, 2>(S); __syncthreads();
+  nms_col_pass<4, 2>(S, [&](int y, int x, bool mk, float s) {
+    const int gy = y0 + y, gx = x0 + x;
+    if (gy >= H8 || gx >= W8) return;
+    const float sc = mk ? s : 0.f;
+    const size_t o = img + (size_t)gy * W8 + gx;
+    if (nms_dense) nms_dense[o] = sc;
+    if (cand_keys && sc > thr && gy >= border && gy < H8 - border && gx >= border && gx < W8 - border) {
+      const int slot = atomicAdd(&cand_counts[n], 1);
+      if (slot < cand_cap) {
+        const unsigned int lin = (unsigned int)(gy * W8 + gx);
+        cand_keys[(size_t)n * cand_cap + slot] =
+            ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+      } else {
+        *overflow_flag = 1;
+      }
+    }
+  });
+}
+
+static void launch_nms_fused_r4(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8, float thr,
+                                int border, unsigned long long* cand_keys, int* cand_counts, int cand_cap,
+                                int* overflow_flag) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(nms_fused_r4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsFusedSmem));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(W8, kNfT), cdiv(H8, kNfT), n);
+  nms_fused_r4_kernel<<<grid, 256, sizeof(NmsFusedSmem), ctx.stream>>>(heat, nms_dense, H8, W8, thr, border, cand_keys,
+                                                                      cand_counts, cand_cap, overflow_flag);
+  B200M_LAUNCH_CHECK(ctx, "nms_fused");
+}
+
 size_t nms_scratch_bytes(int n, int H8, int W8) { return (size_t)n * H8 * W8 * 6 + 1024; }
 
 void launch_nms_candidates(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8,
                            int radius, float thr, int border, unsigned long long* cand_keys,
                            int* cand_counts, int cand_cap, int* overflow_flag, void* scratch) {
   ProfScope prof__(ctx, "nms_candidates");
+  static const bool multipass = [] { const char* e = getenv("B200M_NMS_IMPL"); return e && strcmp(e, "multipass") == 0; }();
+  if (radius == 4 && W8 % 4 == 0 && !multipass) {
+    launch_nms_fused_r4(ctx, heat, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap, overflow_flag);
+    return;
+  }
   const size_t px = (size_t)n * H8 * W8;
   float* ss = reinterpret_cast<float*>(scratch);
   unsigned char* m = reinterpret_cast<unsigned char*>(ss + px);
