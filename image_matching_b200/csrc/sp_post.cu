@@ -163,21 +163,23 @@ static void launch_nms_r(LaunchCtx& ctx, const float* heat, float* ss, unsigned 
 // (9 three-input max instructions instead of 32 two-input ones), a column-pass thread walks 12 rows for four outputs.
 // The intermediate maps (mask, suppression flags) never leave shared memory: one read of the heat-map, one launch
 // (the five-pass version moved ~0.5 GB through the L2 per 16 images and spent 140 us on them; this one ~45 us).
-constexpr int kNfT = 32, kNfHalo = 20, kNfW = kNfT + 2 * kNfHalo;   // 72 = 18 chunks of 4
-constexpr int kNfC = kNfW / 4;
+constexpr int kNfHalo = 20;
 
+template <int T>
 struct NmsFusedSmem {
-  float s[kNfW][kNfW];            // scores, -inf outside the image
-  float t[kNfW][kNfW];            // row-pass result of the current pool
-  unsigned char m[kNfW][kNfW];    // max mask
-  unsigned char sp[kNfW][kNfW];   // suppression flags of the current round
+  static constexpr int W = T + 2 * kNfHalo;   // 72 (T = 32) or 104 (T = 64): a whole number of float4 chunks
+  static constexpr int C = W / 4;
+  float s[W][W];            // scores, -inf outside the image
+  float t[W][W];            // row-pass result of the current pool
+  unsigned char m[W][W];    // max mask
+  unsigned char sp[W][W];   // suppression flags of the current round
 };
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // SRC: 0 = scores, 1 = mask as 0/1, 2 = suppressed scores (supp ? 0 : s); out-of-image pixels are -inf in all three
-template <int SRC>
-__device__ __forceinline__ float4 nms_src_chunk(const NmsFusedSmem& S, int y, int c) {
+template <int SRC, typename SM>
+__device__ __forceinline__ float4 nms_src_chunk(const SM& S, int y, int c) {
   const float4 sv = *reinterpret_cast<const float4*>(&S.s[y][4 * c]);
   if (SRC == 0) return sv;
   const float NEG = -INFINITY;
@@ -191,11 +193,12 @@ __device__ __forceinline__ float4 nms_src_chunk(const NmsFusedSmem& S, int y, in
                      pv.z && sv.z != NEG ? 0.f : sv.z, pv.w && sv.w != NEG ? 0.f : sv.w);
 }
 
-// pool number K (0..4) of the chain: input valid on [4K, 72-4K)^2, output on [4K+4, 72-4K-4)^2
-template <int K, int SRC>
-__device__ __forceinline__ void nms_row_pass(NmsFusedSmem& S) {
-  constexpr int rows = kNfW - 8 * K, c0 = K + 1, nc = kNfC - 2 * (K + 1);
-  for (int i = threadIdx.x; i < rows * nc; i += 256) {
+// pool number K (0..4) of the chain: input valid on [4K, W-4K)^2, output on [4K+4, W-4K-4)^2
+template <int K, int SRC, int NT, typename SM>
+__device__ __forceinline__ void nms_row_pass(SM& S) {
+  constexpr int rows = SM::W - 8 * K, c0 = K + 1, nc = SM::C - 2 * (K + 1);
+#pragma unroll 2
+  for (int i = threadIdx.x; i < rows * nc; i += NT) {
     const int y = 4 * K + i / nc, c = c0 + i % nc;
     const float4 a = nms_src_chunk<SRC>(S, y, c - 1), b = nms_src_chunk<SRC>(S, y, c), d = nms_src_chunk<SRC>(S, y, c + 1);
     // inputs a.x..a.w b.x..b.w d.x..d.w = positions -4..7 relative to the chunk; output j covers positions j-4..j+4
@@ -210,12 +213,13 @@ __device__ __forceinline__ void nms_row_pass(NmsFusedSmem& S) {
 }
 
 // column pass + the element-wise step that follows pool K.  EP: 0 -> m = (s == P(s));  1 -> supp = P(m) > 0;
-// 2 -> m |= (ss == P(ss)) & ~supp.  `fin` receives (y, x, keep) for the last pool.
-template <int K, int EP, typename Fin>
-__device__ __forceinline__ void nms_col_pass(NmsFusedSmem& S, Fin fin) {
-  constexpr int lo = 4 * (K + 1), w = kNfW - 8 * (K + 1), g0 = K + 1, ng = kNfC - 2 * (K + 1);
+// 2 -> m |= (ss == P(ss)) & ~supp.  `fin` receives (y, x, keep, score) for the last pool.
+template <int K, int EP, int NT, typename SM, typename Fin>
+__device__ __forceinline__ void nms_col_pass(SM& S, Fin fin) {
+  constexpr int lo = 4 * (K + 1), w = SM::W - 8 * (K + 1), g0 = K + 1, ng = SM::C - 2 * (K + 1);
   const float NEG = -INFINITY;
-  for (int i = threadIdx.x; i < w * ng; i += 256) {
+#pragma unroll 2
+  for (int i = threadIdx.x; i < w * ng; i += NT) {
     const int x = lo + i % w, g = g0 + i / w;
     float v[12];
 #pragma unroll
@@ -246,33 +250,47 @@ __device__ __forceinline__ void nms_col_pass(NmsFusedSmem& S, Fin fin) {
   }
 }
 
-__global__ void __launch_bounds__(256) nms_fused_r4_kernel(const float* __restrict__ heat, float* __restrict__ nms_dense,
-                                                           int H8, int W8, float thr, int border,
-                                                           unsigned long long* __restrict__ cand_keys,
-                                                           int* __restrict__ cand_counts, int cand_cap,
-                                                           int* __restrict__ overflow_flag) {
+template <int T, int NT>
+__global__ void __launch_bounds__(NT) nms_fused_r4_kernel(const float* __restrict__ heat, float* __restrict__ nms_dense,
+                                                          int H8, int W8, float thr, int border,
+                                                          unsigned long long* __restrict__ cand_keys,
+                                                          int* __restrict__ cand_counts, int cand_cap,
+                                                          int* __restrict__ overflow_flag) {
+  using SM = NmsFusedSmem<T>;
   extern __shared__ __align__(16) unsigned char nms_smem_raw[];
-  NmsFusedSmem& S = *reinterpret_cast<NmsFusedSmem*>(nms_smem_raw);
+  SM& S = *reinterpret_cast<SM*>(nms_smem_raw);
   const int n = blockIdx.z;
   const size_t img = (size_t)n * H8 * W8;
-  const int x0 = blockIdx.x * kNfT - kNfHalo, y0 = blockIdx.y * kNfT - kNfHalo;   // multiples of 4; W8 is one too
+  const int x0 = blockIdx.x * T - kNfHalo, y0 = blockIdx.y * T - kNfHalo;   // multiples of 4; W8 is one too
   const float NEG = -INFINITY;
-  for (int i = threadIdx.x; i < kNfW * kNfC; i += 256) {
-    const int y = i / kNfC, c = i - y * kNfC;
-    const int gy = y0 + y, gx = x0 + 4 * c;
-    float4 v = make_float4(NEG, NEG, NEG, NEG);
-    if (gy >= 0 && gy < H8 && gx >= 0 && gx < W8)
-      v = *reinterpret_cast<const float4*>(heat + img + (size_t)gy * W8 + gx);
-    *reinterpret_cast<float4*>(&S.s[y][4 * c]) = v;
+  {
+    // the whole halo tile in one go: all of a thread's loads are issued before the first shared-memory store
+    constexpr int kItems = SM::W * SM::C, kPer = (kItems + NT - 1) / NT;
+    float4 v[kPer];
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+      const int i = threadIdx.x + r * NT;
+      const int y = i / SM::C, c = i - y * SM::C;
+      const int gy = y0 + y, gx = x0 + 4 * c;
+      v[r] = make_float4(NEG, NEG, NEG, NEG);
+      if (i < kItems && gy >= 0 && gy < H8 && gx >= 0 && gx < W8)
+        v[r] = __ldg(reinterpret_cast<const float4*>(heat + img + (size_t)gy * W8 + gx));
+    }
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+      const int i = threadIdx.x + r * NT;
+      const int y = i / SM::C, c = i - y * SM::C;
+      if (i < kItems) *reinterpret_cast<float4*>(&S.s[y][4 * c]) = v[r];
+    }
   }
   auto none = [](int, int, bool, float) {};
   __syncthreads();
-  nms_row_pass<0, 0>(S); __syncthreads(); nms_col_pass<0, 0>(S, none); __syncthreads();   // m = s == P(s)
-  nms_row_pass<1, 1>(S); __syncthreads(); nms_col_pass<1, 1>(S, none); __syncthreads();   // supp = P(m) > 0
-  nms_row_pass<2, 2>(S); __syncthreads(); nms_col_pass<2, 2>(S, none); __syncthreads();   // m |= ...
-  nms_row_pass<3, 1>(S); __syncthreads(); nms_col_pass<3, 1>(S, none); __syncthreads();
-  nms_row_pass<4, 2>(S); __syncthreads();
-  nms_col_pass<4, 2>(S, [&](int y, int x, bool mk, float s) {
+  nms_row_pass<0, 0, NT>(S); __syncthreads(); nms_col_pass<0, 0, NT>(S, none); __syncthreads();   // m = s == P(s)
+  nms_row_pass<1, 1, NT>(S); __syncthreads(); nms_col_pass<1, 1, NT>(S, none); __syncthreads();   // supp = P(m) > 0
+  nms_row_pass<2, 2, NT>(S); __syncthreads(); nms_col_pass<2, 2, NT>(S, none); __syncthreads();   // m |= ...
+  nms_row_pass<3, 1, NT>(S); __syncthreads(); nms_col_pass<3, 1, NT>(S, none); __syncthreads();
+  nms_row_pass<4, 2, NT>(S); __syncthreads();
+  nms_col_pass<4, 2, NT>(S, [&](int y, int x, bool mk, float s) {
     const int gy = y0 + y, gx = x0 + x;
     if (gy >= H8 || gx >= W8) return;
     const float sc = mk ? s : 0.f;
@@ -291,18 +309,35 @@ __global__ void __launch_bounds__(256) nms_fused_r4_kernel(const float* __restri
   });
 }
 
+template <int T, int NT>
+static void launch_nms_fused_r4_t(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8, float thr,
+                                  int border, unsigned long long* cand_keys, int* cand_counts, int cand_cap,
+                                  int* overflow_flag) {
+  static bool attr_set = false;
+  auto kern = nms_fused_r4_kernel<T, NT>;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsFusedSmem<T>));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(W8, T), cdiv(H8, T), n);
+  kern<<<grid, NT, sizeof(NmsFusedSmem<T>), ctx.stream>>>(heat, nms_dense, H8, W8, thr, border, cand_keys, cand_counts,
+                                                         cand_cap, overflow_flag);
+  B200M_LAUNCH_CHECK(ctx, "nms_fused");
+}
+
+// 64x64 tiles (2.6x halo redundancy, 108 KB, two 512-thread CTAs per SM) for real images; 32x32 tiles (5x, 52 KB) when the
+// image is so small that 64x64 tiles would leave most of the chip idle
 static void launch_nms_fused_r4(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8, float thr,
                                 int border, unsigned long long* cand_keys, int* cand_counts, int cand_cap,
                                 int* overflow_flag) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(nms_fused_r4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsFusedSmem));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(W8, kNfT), cdiv(H8, kNfT), n);
-  nms_fused_r4_kernel<<<grid, 256, sizeof(NmsFusedSmem), ctx.stream>>>(heat, nms_dense, H8, W8, thr, border, cand_keys,
-                                                                      cand_counts, cand_cap, overflow_flag);
-  B200M_LAUNCH_CHECK(ctx, "nms_fused");
+  static const int forced = [] { const char* e = getenv("B200M_NMS_TILE"); return e ? atoi(e) : 0; }();
+  const bool big = forced ? forced == 64 : (size_t)cdiv(W8, 64) * cdiv(H8, 64) * n >= 296;
+  if (big)
+    launch_nms_fused_r4_t<64, 512>(ctx, heat, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap,
+                                   overflow_flag);
+  else
+    launch_nms_fused_r4_t<32, 256>(ctx, heat, nms_dense, n, H8, W8, thr, border, cand_keys, cand_counts, cand_cap,
+                                   overflow_flag);
 }
 
 size_t nms_scratch_bytes(int n, int H8, int W8) { return (size_t)n * H8 * W8 * 6 + 1024; }
