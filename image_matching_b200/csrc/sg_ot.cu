@@ -113,7 +113,7 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused Sinkhorn iteration for M <= 1024 columns: ONE launch per iteration over all pairs, S is read from HBM once per
-// iteration (the unfused pair of kernels above reads it three times), 7 instructions and 2 exps per matrix element.
+// iteration (the unfused pair of kernels above reads it three times), 5 instructions and 1 exp per matrix element.
 //
 // No running maxima: both logsumexps are shifted by RIGOROUS upper bounds that follow from the previous half-step,
 //     u_i = log_mu_i - LSE_j'(c_ij' + v_j')  =>  c_ij + u_i <= log_mu_i - v_j <= mu_bin - v_j        (column shift)
@@ -256,25 +256,32 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
       rn = kOtHeadroom - (d.nu_bin - u_prev);
       r = rn * kLog2e;
     }
-    float s4[4] = {lane == 0 ? ot_ex2(zbin + r) : 0.f, 0.f, 0.f, 0.f};
+    const float ebin = ot_ex2(zbin + r);
+    float s4[4] = {lane == 0 ? ebin : 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (FULL || k <= kfull) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) s4[e] += ot_ex2(z[4 * k + e] + r);
+        for (int e = 0; e < 4; ++e) {
+          z[4 * k + e] = ot_ex2(z[4 * k + e] + r);        // e_ij = 2^(z_ij + r_i): kept for the column sums below
+          s4[e] += z[4 * k + e];
+        }
       }
     const float sum = fmaxf(warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])), kOtTiny);
     const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) - rn);
     if (lane == 0) u[i] = ui;
-    // ---- column sums: 2^(y_ij - (mu_bin - v_j - 60)) log2 e) = 2^(z_ij + q_i), q_i = (u_i - mu_bin + 60) log2 e
+    // ---- column sums: 2^(y_ij - (mu_bin - v_j - 60)) log2 e) = 2^(z_ij + q_i), q_i = (u_i - mu_bin + 60) log2 e.
+    // The exponent differs from the row term's only by the per-row constant q_i - r_i, so the second exp of every
+    // element is one multiply-add with f_i = 2^(q_i - r_i) (clamped: no inf * 0): ONE MUFU op per matrix element.
     const float qi = fmaf(ui, kLog2e, head2 - mu_bin2);
+    const float fi = ot_ex2(fminf(qi - r, 126.f));
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (FULL || k <= kfull) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) cs[4 * k + e] += ot_ex2(z[4 * k + e] + qi);
+        for (int e = 0; e < 4; ++e) cs[4 * k + e] = fmaf(z[4 * k + e], fi, cs[4 * k + e]);
       }
-    bs += ot_ex2(zbin + qi);
+    bs = fmaf(ebin, fi, bs);
   }
   };
   if (kfull >= 8) run_rows(std::true_type{});
