@@ -50,6 +50,8 @@ def estimate_affine_partial_2d(owner, kpts0: torch.Tensor, kpts1: torch.Tensor, 
     mats = torch.empty((B, 2, 3), dtype=torch.float64, device=dev)
     inl = torch.empty((B, N), dtype=torch.uint8, device=dev)
     info = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    if B == 0 or N == 0 or M == 0:      # nothing to estimate from (cv2: Matrix None, empty / all-zero mask)
+        return mats.zero_(), inl.zero_(), info.zero_()
     if counts0 is not None:
         counts0 = counts0.contiguous().to(torch.int32)
     _lib.check(L.b200m_estimate_affine_partial(h, _ptr(k0), _ptr(k1), _ptr(m0), _ptr(counts0), B, N, M,

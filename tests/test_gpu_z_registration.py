@@ -82,6 +82,16 @@ def test_ransac_edge_counts(owner):
     assert info[0, 2] == 1 and info[0, 1] == 500
 
 
+def test_ransac_empty_inputs(owner):
+    from image_matching_b200 import estimate_affine_partial_2d
+    k0 = torch.zeros((2, 0, 2), device="cuda")
+    k1 = torch.rand((2, 5, 2), device="cuda")
+    mats, inl, info = estimate_affine_partial_2d(owner, k0, k1, torch.zeros((2, 0), dtype=torch.int32, device="cuda"))
+    assert mats.shape == (2, 2, 3) and inl.shape == (2, 0) and int(info.abs().sum()) == 0
+    with pytest.raises(RuntimeError):
+        estimate_affine_partial_2d(owner, k0.cpu(), k1.cpu(), torch.zeros((2, 0), dtype=torch.int64))
+
+
 def test_ransac_padded_counts_and_large_n(owner):
     rs = np.random.default_rng(13)
     probs = [_problem(rs, 4096, 4096, 3000, 1.0, 0.5) for _ in range(3)]
