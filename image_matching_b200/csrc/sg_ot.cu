@@ -3,6 +3,7 @@
 // :268-285 (match selection).  HBM/L2-bound streaming kernels: the (N+1)x(M+1) couplings matrix is never
 // materialised -- the bin row/column are the scalar alpha -- and every sweep re-reads S (L2-resident when
 // the caller micro-batches pairs).  LSE uses the same max-shifted two-pass form as torch.logsumexp.
+#include <algorithm>
 #include <type_traits>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -132,7 +133,9 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
 //   memory and written as ONE partial row; the LAST CTA of a pair to finish (atomic ticket) folds the <= 17 partial rows
 //   into the new v.
 constexpr int kOtFusedMaxM = 1024;
-constexpr int kOtMaxParts = 20;          // CTAs (= partial rows) per pair, upper bound
+constexpr int kOtWideMaxM = 4096;        // ot_iter_wide_kernel (rows kept in shared memory)
+constexpr int kOtMaxParts = 20;          // CTAs (= partial rows) per pair, upper bound (register-resident kernel)
+constexpr int kOtWideMaxParts = 48;      // same for the wide kernels (few pairs of many rows: one CTA per SM)
 constexpr int kOtCtasPerSm = 2;
 constexpr int kOtRing = 2;                // rows in flight per warp (3 measured no faster)
 constexpr int kOtRowRingBytes = 8 * kOtRing * kOtFusedMaxM * 4;                             // 64 KB
@@ -325,13 +328,201 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
   if (threadIdx.x == 0) tickets[b] = 0;    // ready for the next iteration (next launch)
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same fused iteration for 1024 < M <= 4096 columns (BASELINE configs 3 and 5: 2048 / 4096 keypoints).  A row no
+// longer fits a lane's registers next to the column sums, so the row terms e_ij = 2^(z_ij + r_i) are written back IN
+// PLACE into the row's shared-memory buffer (a lane only ever touches its own columns) and re-read for the column
+// sums; the registers hold only the 4G column sums.  G = 128-column groups per row (16 or 32), NW warps per CTA
+// (8 or 6: the ring of NW x 2 rows must fit shared memory), one CTA per SM.
+template <int G, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, float* __restrict__ partials,
+                                                                  int* __restrict__ tickets, int max_parts,
+                                                                  int ld_part, int rows_per_cta, int first) {
+  constexpr int MAXM = 128 * G, NT = NW * 32;
+  extern __shared__ __align__(128) uint8_t ot_smem[];
+  float* rows_s = reinterpret_cast<float*>(ot_smem);                                   // [NW][kOtRing][MAXM]
+  float* v2_s = rows_s + NW * kOtRing * MAXM;                                          // [MAXM + 4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v2_s + MAXM + 4);                       // [NW][kOtRing]
+  __shared__ int s_ticket;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PairDims d = pair_dims(p, b);
+  if (d.n == 0 || d.m == 0) return;                       // uniform per block
+  const int parts = cdiv(d.n + 1, rows_per_cta);
+  if ((int)blockIdx.x >= parts) return;                   // uniform per block
+  const int rows_per_warp = rows_per_cta / NW;            // rows_per_cta is a multiple of NW
+  const int row0 = blockIdx.x * rows_per_cta + warp * rows_per_warp;
+  const int row_end = min(row0 + rows_per_warp, d.n + 1);
+  const float* S = p.S + (size_t)b * p.strideS;
+  float* wrow = rows_s + warp * kOtRing * MAXM;
+  const uint32_t row_bytes = (uint32_t)p.ldS * 4;
+  auto request = [&](int i) {                             // lane 0 only; the dustbin row (i == n) is not stored anywhere
+    if (i < row_end && i < d.n) {
+      uint64_t* bar = &bars[warp * kOtRing + (i - row0) % kOtRing];
+      tc::mbar_expect_tx(bar, row_bytes);
+      tc::bulk_load(wrow + ((i - row0) % kOtRing) * MAXM, S + (size_t)i * p.ldS, row_bytes, bar);
+    }
+  };
+  if (lane == 0) {
+    for (int q = 0; q < kOtRing; ++q) tc::mbar_init(&bars[warp * kOtRing + q], 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    for (int q = 0; q < kOtRing; ++q) request(row0 + q);
+  }
+  __syncwarp();
+  float* vrow = p.v + (size_t)b * p.ld_uv;
+  for (int j0 = threadIdx.x; j0 < MAXM + 4; j0 += 8 * NT) {      // eight loads in flight per thread, then the stores
+    float t8[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q * NT;
+      t8[q] = j <= d.m ? vrow[j] * kLog2e : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q * NT;
+      if (j < MAXM + 4) v2_s[j] = t8[q];
+    }
+  }
+  __syncthreads();
+  const float a2 = p.alpha * kLog2e;
+  const float zbin = a2 + v2_s[d.m];
+  const float mu_bin2 = d.mu_bin * kLog2e, head2 = kOtHeadroom * kLog2e;
+  const int kfull = d.m >> 7;                             // groups k < kfull are full, group kfull is ragged (if any)
+  const bool ragged = (d.m & 127) != 0;
+  const int kend = kfull + (ragged ? 1 : 0);              // groups to visit (warp-uniform), <= G
+  float cs[4 * G];
+#pragma unroll
+  for (int q = 0; q < 4 * G; ++q) cs[q] = 0.f;
+  float bs = 0.f;
+  float* u = p.u + (size_t)b * p.ld_uv;
+  auto run_rows = [&](auto ragged_tag) {
+  constexpr bool RAGGED = decltype(ragged_tag)::value;    // m a multiple of 128 (2048, 4096): no masking code at all
+  for (int i = row0; i < row_end; ++i) {
+    const bool bin_row = (i == d.n);
+    const int slot = (i - row0) % kOtRing;
+    float* srow = wrow + slot * MAXM + 4 * lane;          // this lane's columns: 4*lane + 128*k + {0..3}
+    const float u_prev = u[i];
+    if (!bin_row) tc::mbar_wait(&bars[warp * kOtRing + slot], ((i - row0) / kOtRing) & 1);
+    // z_ij = (c_ij + v_j) log2(e) for group k (masked columns: -1e30 -> 2^z == 0)
+    auto zgroup = [&](int k, float* z) {
+      const int j = 4 * lane + 128 * k;
+      float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+      if (!bin_row && (!RAGGED || j < d.m)) t = *reinterpret_cast<const float4*>(srow + 128 * k);   // rows are padded to ldS
+      const float4 vv = *reinterpret_cast<const float4*>(v2_s + j);
+      z[0] = fmaf(t.x, kLog2e, vv.x); z[1] = fmaf(t.y, kLog2e, vv.y);
+      z[2] = fmaf(t.z, kLog2e, vv.z); z[3] = fmaf(t.w, kLog2e, vv.w);
+      if (RAGGED && k == kfull) {                         // the ragged group (warp-uniform branch)
+        z[0] = j < d.m ? z[0] : kOtNegBig; z[1] = j + 1 < d.m ? z[1] : kOtNegBig;
+        z[2] = j + 2 < d.m ? z[2] : kOtNegBig; z[3] = j + 3 < d.m ? z[3] : kOtNegBig;
+      }
+    };
+    float r, rn;
+    if (first) {                                          // warp-uniform: exact maximum (v = 0 carries no bound yet)
+      float mx = zbin;
+#pragma unroll 8
+      for (int k = 0; k < G; ++k)
+        if (k < kend) {
+          float z[4];
+          zgroup(k, z);
+          mx = fmaxf(mx, fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])));
+        }
+      r = -warp_max(mx);
+      rn = r * kLn2;
+    } else {
+      rn = kOtHeadroom - (d.nu_bin - u_prev);
+      r = rn * kLog2e;
+    }
+    const float ebin = ot_ex2(zbin + r);
+    float s4[4] = {lane == 0 ? ebin : 0.f, 0.f, 0.f, 0.f};
+    // (unrolled: with one or two warps per scheduler the independent groups are the only latency hiding there is)
+#pragma unroll 8
+    for (int k = 0; k < G; ++k)
+      if (k < kend) {
+        float z[4];
+        zgroup(k, z);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { z[e] = ot_ex2(z[e] + r); s4[e] += z[e]; }
+        *reinterpret_cast<float4*>(srow + 128 * k) = make_float4(z[0], z[1], z[2], z[3]);   // e_ij, in place
+      }
+    const float sum = fmaxf(warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])), kOtTiny);
+    const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) - rn);
+    if (lane == 0) u[i] = ui;
+    const float qi = fmaf(ui, kLog2e, head2 - mu_bin2);
+    const float fi = ot_ex2(fminf(qi - r, 126.f));
+#pragma unroll
+    for (int k = 0; k < G; ++k)
+      if (k < kend) {
+        const float4 e4 = *reinterpret_cast<const float4*>(srow + 128 * k);
+        cs[4 * k] = fmaf(e4.x, fi, cs[4 * k]); cs[4 * k + 1] = fmaf(e4.y, fi, cs[4 * k + 1]);
+        cs[4 * k + 2] = fmaf(e4.z, fi, cs[4 * k + 2]); cs[4 * k + 3] = fmaf(e4.w, fi, cs[4 * k + 3]);
+      }
+    bs = fmaf(ebin, fi, bs);
+    tc::fence_proxy_async();              // generic-proxy writes of this buffer are ordered before the next bulk copy
+    __syncwarp();
+    if (lane == 0) request(i + kOtRing);
+  }
+  };
+  if (ragged) run_rows(std::true_type{});
+  else run_rows(std::false_type{});
+  // ---- add the warps' column sums through shared memory (the exchange aliases the row ring)
+  __syncthreads();
+  float* xch = rows_s + warp * (MAXM + 4);
+#pragma unroll
+  for (int k = 0; k < G; ++k)
+    *reinterpret_cast<float4*>(xch + 4 * lane + 128 * k) = make_float4(cs[4 * k], cs[4 * k + 1], cs[4 * k + 2], cs[4 * k + 3]);
+  if (lane == 0) xch[MAXM] = bs;
+  __syncthreads();
+  float* prow = partials + ((size_t)b * max_parts + blockIdx.x) * ld_part;
+  for (int j = threadIdx.x; j <= d.m; j += NT) {
+    const int jj = j == d.m ? MAXM : j;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += rows_s[w * (MAXM + 4) + jj];
+    prow[j] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1);
+  __syncthreads();
+  if (s_ticket != parts - 1) return;
+  __threadfence();
+  // (up to 48 partial rows of up to 4097 columns: float4 columns, eight loads in flight per thread, summed in part order)
+  const float4* pbase = reinterpret_cast<const float4*>(partials + (size_t)b * max_parts * ld_part);
+  const int ld4 = ld_part >> 2;
+  for (int j4 = threadIdx.x; 4 * j4 <= d.m; j4 += NT) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q0 = 0; q0 < parts; q0 += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        x[qq] = q0 + qq < parts ? __ldcg(pbase + (size_t)(q0 + qq) * ld4 + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) { t.x += x[qq].x; t.y += x[qq].y; t.z += x[qq].z; t.w += x[qq].w; }
+    }
+    const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * j4 + e;
+      if (j <= d.m) {
+        const float lse = logf(fmaxf(tt[e], kOtTiny)) + ((d.mu_bin - vrow[j]) - kOtHeadroom);
+        vrow[j] = (j == d.m ? d.nu_bin : d.norm) - lse;
+      }
+    }
+  }
+  if (threadIdx.x == 0) tickets[b] = 0;
+}
+
+template <int G, int NW>
+constexpr int ot_wide_smem_bytes() { return (NW * kOtRing * 128 * G + 128 * G + 4) * 4 + NW * kOtRing * 8; }
+
 bool ot_fused_supported(const OtParams& p) {
-  return p.M <= kOtFusedMaxM && p.ldS % 4 == 0 && p.strideS % 4 == 0 && (reinterpret_cast<uintptr_t>(p.S) & 15) == 0;
+  return p.M <= kOtWideMaxM && p.ldS % 4 == 0 && p.strideS % 4 == 0 && (reinterpret_cast<uintptr_t>(p.S) & 15) == 0;
 }
 
 // floats of scratch for `pairs` pairs: per-pair tickets + one set of partial rows
 size_t ot_fused_scratch_floats(int pairs, int N, int M) {
-  return (size_t)round_up(pairs, 64) + (size_t)pairs * kOtMaxParts * round_up(M + 1, 4);
+  return (size_t)round_up(pairs, 64) + (size_t)pairs * (M > kOtFusedMaxM ? kOtWideMaxParts : kOtMaxParts) * round_up(M + 1, 4);
 }
 
 // `iters` full Sinkhorn iterations (u update then v update) starting from u = v = 0 (launch_ot_init); leaves u and v in
@@ -341,18 +532,33 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(ot_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOtSmemBytes);
+    cudaFuncSetAttribute(ot_iter_wide_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         ot_wide_smem_bytes<16, 8>());
+    cudaFuncSetAttribute(ot_iter_wide_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         ot_wide_smem_bytes<32, 6>());
     attr_set = true;
   }
-  const int max_parts = ot_fused_parts(p.B, p.N, num_sms), ld_part = round_up(p.M + 1, 4);
-  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 8);
+  const int wide = p.M <= kOtFusedMaxM ? 0 : (p.M <= 2048 ? 1 : 2);
+  int max_parts = std::max(1, std::min(kOtWideMaxParts, num_sms / std::max(p.B, 1)));   // one CTA per SM, one wave
+  max_parts = std::min(max_parts, cdiv(p.N + 1, 24));
+  if (!wide) max_parts = ot_fused_parts(p.B, p.N, num_sms);
+  const int ld_part = round_up(p.M + 1, 4);
+  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 24);                      // a multiple of 8 and of 6 warps
   int* tickets = reinterpret_cast<int*>(scratch);
   float* partials = scratch + round_up(p.B, 64);
   cudaMemsetAsync(tickets, 0, sizeof(int) * p.B, ctx.stream);
   for (int it = 0; it < iters; ++it) {
     ProfScope prof__(ctx, "ot_iter_fused");
     dim3 grid(max_parts, p.B);
-    ot_iter_kernel<<<grid, 256, kOtSmemBytes, ctx.stream>>>(p, partials, tickets, max_parts, ld_part, rows_per_cta,
-                                                            it == 0);
+    if (wide == 0)
+      ot_iter_kernel<<<grid, 256, kOtSmemBytes, ctx.stream>>>(p, partials, tickets, max_parts, ld_part, rows_per_cta,
+                                                              it == 0);
+    else if (wide == 1)
+      ot_iter_wide_kernel<16, 8><<<grid, 256, ot_wide_smem_bytes<16, 8>(), ctx.stream>>>(
+          p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
+    else
+      ot_iter_wide_kernel<32, 6><<<grid, 192, ot_wide_smem_bytes<32, 6>(), ctx.stream>>>(
+          p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
     B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
   }
 }

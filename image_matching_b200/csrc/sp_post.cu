@@ -385,7 +385,7 @@ __device__ void block_bitonic_desc(unsigned long long* keys, int npow2) {
   }
 }
 
-constexpr int kSelectSmemKeys = 8192;
+constexpr int kSelectSmemKeys = 16384;   // 128 KB: the ~10 k candidates of a 1280x960 image sort in shared memory
 
 __global__ void __launch_bounds__(1024) select_keypoints_kernel(unsigned long long* __restrict__ cand_keys,
                                                                 const int* __restrict__ cand_counts,
@@ -402,17 +402,60 @@ __global__ void __launch_bounds__(1024) select_keypoints_kernel(unsigned long lo
   while (npow2 < cnt) npow2 <<= 1;
   const bool in_smem = npow2 <= kSelectSmemKeys;
   unsigned long long* keys = in_smem ? skeys : gk;   // cand_cap is a power of two >= npow2
-  // Build sort keys.  Row-major mode sorts by ~linear-index descending == index ascending.
-  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-    unsigned long long k = 0ull;
-    if (i < cnt) {
-      k = gk[i];
-      if (!topk) k = ((k & 0xFFFFFFFFull) << 32) | (k >> 32);
+  int nsort = npow2;
+  if (topk && !in_smem && max_kp <= kSelectSmemKeys) {
+    // More candidates than shared memory holds (a 1280x960 image easily has 30 k): instead of a bitonic sort of all of
+    // them in global memory, find the max_kp-th largest key with an MSB radix select (8 passes over the L2-resident
+    // list, 256-bin shared-memory histograms; the keys are unique, so exactly max_kp keys are >= it), compact those
+    // into shared memory and sort only them.
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_remaining, s_fill;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = max_kp; s_fill = 0; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const unsigned long long k = gk[i];
+        const bool match = shift == 56 || (k >> (shift + 8)) == (prefix >> (shift + 8));
+        if (match) atomicAdd(&hist[(int)((k >> shift) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int acc = 0, d = 255;
+        for (; d > 0; --d) {
+          if (acc + hist[d] >= s_remaining) break;
+          acc += hist[d];
+        }
+        s_remaining -= acc;                       // rank of the wanted key inside bin d
+        s_prefix = prefix | ((unsigned long long)d << shift);
+      }
+      __syncthreads();
     }
-    keys[i] = k;   // padding keys are 0 -> sort to the end
+    const unsigned long long kth = s_prefix;
+    nsort = 1;
+    while (nsort < max_kp) nsort <<= 1;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x) skeys[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned long long k = gk[i];
+      if (k >= kth) skeys[atomicAdd(&s_fill, 1)] = k;
+    }
+    keys = skeys;
+  } else {
+    // Build sort keys.  Row-major mode sorts by ~linear-index descending == index ascending.
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+      unsigned long long k = 0ull;
+      if (i < cnt) {
+        k = gk[i];
+        if (!topk) k = ((k & 0xFFFFFFFFull) << 32) | (k >> 32);
+      }
+      keys[i] = k;   // padding keys are 0 -> sort to the end
+    }
   }
   __syncthreads();
-  block_bitonic_desc(keys, npow2);
+  block_bitonic_desc(keys, nsort);
   const int keep = topk ? max_kp : min(cnt, cap);
   float* kp = keypoints + (size_t)n * cap * 2;
   float* sc = scores + (size_t)n * cap;

@@ -108,6 +108,30 @@ def test_stage_detector_post(stage):
         print(f"detector side{side}: {n} keypoints, {flips} order flips vs reference")
 
 
+@pytest.mark.parametrize("max_kp", [1024, 3000, -1])
+def test_detector_post_many_candidates(max_kp):
+    """A 1280x960-sized map with ~25 k NMS survivors (more than the shared-memory sort holds): the radix-select top-k
+    path, the 64x64-tile fused NMS and the row-major (max_keypoints = -1) path, bit-exact against the oracle evaluated
+    on the SAME heat-map (NMS, threshold, border and top-k are compare-only)."""
+    from image_matching_b200 import stages, synth
+    from oracle import matching_oracle as O
+    cfg = golden_cfg(max_kp=max_kp)
+    m = _matching(cfg, synth.superpoint_weights(0, 128), synth.superglue_weights(0, 128))
+    rng = np.random.default_rng(17)
+    semi = rng.standard_normal((2, 65, 120, 160)).astype(np.float32)
+    heat, nms, kp, sc, cnt = stages.detector_post(m, _t(semi))
+    for i in range(2):
+        h = heat[i].cpu().numpy()
+        assert np.abs(h - O.heatmap(semi[i])).max() < 1e-6
+        ref_nms = O.simple_nms(h, 4)
+        assert np.array_equal(nms[i].cpu().numpy(), ref_nms)
+        ref_kp, ref_sc = O.extract_keypoints(ref_nms, 0.005, 4, max_kp)
+        n = int(cnt[i])
+        assert n == len(ref_sc) and (max_kp < 0 or n == max_kp) and (ref_nms > 0.005).sum() > 16384
+        assert np.array_equal(kp[i, :n].cpu().numpy(), ref_kp)
+        assert np.array_equal(sc[i, :n].cpu().numpy(), ref_sc)
+
+
 def test_stage_sample_descriptors(stage):
     from image_matching_b200 import stages
     g = stage["g"]
@@ -308,6 +332,25 @@ def test_sinkhorn_properties_full_size():
     perm = torch.randperm(N, device=DEV)
     Zp = stages.sinkhorn(m, _t(S)[:, perm], iters=30)
     assert (Zp[:, :N] - Z[:, perm].float()[:, :N]).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("N,M,iters", [(1100, 1500, 12), (2048, 2048, 10), (1500, 4096, 8), (4096, 3000, 8),
+                                        (700, 1024, 12), (64, 1025, 6)])
+def test_sinkhorn_wide_vs_oracle(N, M, iters):
+    """Sinkhorn for more than 1024 columns (BASELINE configs 3 / 5: the row terms live in shared memory) against the
+    numpy oracle, Z within 1e-3; (700, 1024) is the register-resident kernel for comparison."""
+    from image_matching_b200 import stages
+    from oracle import matching_oracle as O
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    rng = np.random.default_rng(N + M)
+    S = (rng.standard_normal((2, N, M)) * 4).astype(np.float32)
+    S[1, rng.integers(0, N, N // 2), rng.integers(0, M, N // 2)] += 25.0       # sharp matches next to a flat background
+    Z = stages.sinkhorn(m, _t(S), iters=iters).cpu().numpy()
+    alpha = float(c["sg"]["bin_score"])
+    for b in range(2):
+        ref = O.log_optimal_transport(S[b], alpha, iters)
+        assert np.abs(Z[b] - ref).max() < 1e-3, (b, np.abs(Z[b] - ref).max())
 
 
 def test_full_size_batch_runs_and_is_consistent():
