@@ -332,35 +332,44 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
 // The same fused iteration for 1024 < M <= 4096 columns (BASELINE configs 3 and 5: 2048 / 4096 keypoints).  A row no
 // longer fits a lane's registers next to the column sums, so the row terms e_ij = 2^(z_ij + r_i) are written back IN
 // PLACE into the row's shared-memory buffer (a lane only ever touches its own columns) and re-read for the column
-// sums; the registers hold only the 4G column sums.  G = 128-column groups per row (16 or 32), NW warps per CTA
-// (8 or 6: the ring of NW x 2 rows must fit shared memory), one CTA per SM.
+// sums; the registers hold only the column sums.  TWO warps share a row (each owns one half of the columns: its own
+// bulk-copy ring, its own 4G column sums) and exchange their partial row sums through shared memory and a 64-thread
+// named barrier, so that 12 (M <= 4096) or 16 (M <= 2048) warps fit next to the ring instead of 6 / 8: with one or
+// two warps per scheduler the kernel was bound by instruction latency, not by HBM.
+// G = 128-column groups per WARP (a row has 2G), NW warps per CTA, one CTA per SM.
 template <int G, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, float* __restrict__ partials,
                                                                   int* __restrict__ tickets, int max_parts,
                                                                   int ld_part, int rows_per_cta, int first) {
-  constexpr int MAXM = 128 * G, NT = NW * 32;
+  constexpr int HALF = 128 * G, MAXM = 2 * HALF, NT = NW * 32, NTEAM = NW / 2;
   extern __shared__ __align__(128) uint8_t ot_smem[];
-  float* rows_s = reinterpret_cast<float*>(ot_smem);                                   // [NW][kOtRing][MAXM]
-  float* v2_s = rows_s + NW * kOtRing * MAXM;                                          // [MAXM + 4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v2_s + MAXM + 4);                       // [NW][kOtRing]
+  float* rows_s = reinterpret_cast<float*>(ot_smem);                                   // [NW][kOtRing][HALF]
+  float* v2_s = rows_s + NW * kOtRing * HALF;                                          // [MAXM + 4]
+  float* psum = v2_s + MAXM + 4;                                                       // [2][NW] partial row sums
+  float* pmax = psum + 2 * NW;                                                         // [NW]   partial row maxima
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pmax + NW);                             // [NW][kOtRing]
   __shared__ int s_ticket;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp >> 1, side = warp & 1;
   const PairDims d = pair_dims(p, b);
   if (d.n == 0 || d.m == 0) return;                       // uniform per block
   const int parts = cdiv(d.n + 1, rows_per_cta);
   if ((int)blockIdx.x >= parts) return;                   // uniform per block
-  const int rows_per_warp = rows_per_cta / NW;            // rows_per_cta is a multiple of NW
-  const int row0 = blockIdx.x * rows_per_cta + warp * rows_per_warp;
-  const int row_end = min(row0 + rows_per_warp, d.n + 1);
-  const float* S = p.S + (size_t)b * p.strideS;
-  float* wrow = rows_s + warp * kOtRing * MAXM;
-  const uint32_t row_bytes = (uint32_t)p.ldS * 4;
+  const int rows_per_team = rows_per_cta / NTEAM;         // rows_per_cta is a multiple of NTEAM
+  const int row0 = blockIdx.x * rows_per_cta + team * rows_per_team;
+  const int row_end = min(row0 + rows_per_team, d.n + 1);
+  const int coff = side * HALF;                           // first column of this warp
+  const int my_m = max(0, min(HALF, d.m - coff));         // valid columns of this warp
+  const int my_ld = max(0, min(HALF, p.ldS - coff));      // floats of a (padded) row this warp loads
+  const float* S = p.S + (size_t)b * p.strideS + coff;
+  float* wrow = rows_s + warp * kOtRing * HALF;
+  const uint32_t row_bytes = (uint32_t)my_ld * 4;
   auto request = [&](int i) {                             // lane 0 only; the dustbin row (i == n) is not stored anywhere
-    if (i < row_end && i < d.n) {
+    if (i < row_end && i < d.n && my_ld > 0) {
       uint64_t* bar = &bars[warp * kOtRing + (i - row0) % kOtRing];
       tc::mbar_expect_tx(bar, row_bytes);
-      tc::bulk_load(wrow + ((i - row0) % kOtRing) * MAXM, S + (size_t)i * p.ldS, row_bytes, bar);
+      tc::bulk_load(wrow + ((i - row0) % kOtRing) * HALF, S + (size_t)i * p.ldS, row_bytes, bar);
     }
   };
   if (lane == 0) {
@@ -388,37 +397,39 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
   const float a2 = p.alpha * kLog2e;
   const float zbin = a2 + v2_s[d.m];
   const float mu_bin2 = d.mu_bin * kLog2e, head2 = kOtHeadroom * kLog2e;
-  const int kfull = d.m >> 7;                             // groups k < kfull are full, group kfull is ragged (if any)
-  const bool ragged = (d.m & 127) != 0;
-  const int kend = kfull + (ragged ? 1 : 0);              // groups to visit (warp-uniform), <= G
+  const int kfull = my_m >> 7;                            // this warp's groups k < kfull are full, group kfull is ragged (if any)
+  const bool ragged = (d.m & 127) != 0;                   // block-uniform: both warps of a team take the same variant
+  const int kend = kfull + ((my_m & 127) ? 1 : 0);        // groups to visit (warp-uniform), <= G
+  const float* v2w = v2_s + coff;
   float cs[4 * G];
 #pragma unroll
   for (int q = 0; q < 4 * G; ++q) cs[q] = 0.f;
   float bs = 0.f;
   float* u = p.u + (size_t)b * p.ld_uv;
+  auto team_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory"); };
   auto run_rows = [&](auto ragged_tag) {
   constexpr bool RAGGED = decltype(ragged_tag)::value;    // m a multiple of 128 (2048, 4096): no masking code at all
   for (int i = row0; i < row_end; ++i) {
     const bool bin_row = (i == d.n);
     const int slot = (i - row0) % kOtRing;
-    float* srow = wrow + slot * MAXM + 4 * lane;          // this lane's columns: 4*lane + 128*k + {0..3}
+    float* srow = wrow + slot * HALF + 4 * lane;          // this lane's columns: coff + 4*lane + 128*k + {0..3}
     const float u_prev = u[i];
-    if (!bin_row) tc::mbar_wait(&bars[warp * kOtRing + slot], ((i - row0) / kOtRing) & 1);
+    if (!bin_row && my_ld > 0) tc::mbar_wait(&bars[warp * kOtRing + slot], ((i - row0) / kOtRing) & 1);
     // z_ij = (c_ij + v_j) log2(e) for group k (masked columns: -1e30 -> 2^z == 0)
     auto zgroup = [&](int k, float* z) {
-      const int j = 4 * lane + 128 * k;
+      const int j = 4 * lane + 128 * k;                   // column inside this warp's half
       float4 t = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
-      if (!bin_row && (!RAGGED || j < d.m)) t = *reinterpret_cast<const float4*>(srow + 128 * k);   // rows are padded to ldS
-      const float4 vv = *reinterpret_cast<const float4*>(v2_s + j);
+      if (!bin_row && (!RAGGED || j < my_m)) t = *reinterpret_cast<const float4*>(srow + 128 * k);   // rows are padded to ldS
+      const float4 vv = *reinterpret_cast<const float4*>(v2w + j);
       z[0] = fmaf(t.x, kLog2e, vv.x); z[1] = fmaf(t.y, kLog2e, vv.y);
       z[2] = fmaf(t.z, kLog2e, vv.z); z[3] = fmaf(t.w, kLog2e, vv.w);
       if (RAGGED && k == kfull) {                         // the ragged group (warp-uniform branch)
-        z[0] = j < d.m ? z[0] : kOtNegBig; z[1] = j + 1 < d.m ? z[1] : kOtNegBig;
-        z[2] = j + 2 < d.m ? z[2] : kOtNegBig; z[3] = j + 3 < d.m ? z[3] : kOtNegBig;
+        z[0] = j < my_m ? z[0] : kOtNegBig; z[1] = j + 1 < my_m ? z[1] : kOtNegBig;
+        z[2] = j + 2 < my_m ? z[2] : kOtNegBig; z[3] = j + 3 < my_m ? z[3] : kOtNegBig;
       }
     };
     float r, rn;
-    if (first) {                                          // warp-uniform: exact maximum (v = 0 carries no bound yet)
+    if (first) {                                          // block-uniform: exact maximum (v = 0 carries no bound yet)
       float mx = zbin;
 #pragma unroll 8
       for (int k = 0; k < G; ++k)
@@ -427,15 +438,18 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
           zgroup(k, z);
           mx = fmaxf(mx, fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])));
         }
-      r = -warp_max(mx);
+      mx = warp_max(mx);
+      if (lane == 0) pmax[warp] = mx;
+      team_sync();
+      r = -fmaxf(pmax[2 * team], pmax[2 * team + 1]);
       rn = r * kLn2;
     } else {
       rn = kOtHeadroom - (d.nu_bin - u_prev);
       r = rn * kLog2e;
     }
     const float ebin = ot_ex2(zbin + r);
-    float s4[4] = {lane == 0 ? ebin : 0.f, 0.f, 0.f, 0.f};
-    // (unrolled: with one or two warps per scheduler the independent groups are the only latency hiding there is)
+    float s4[4] = {(lane == 0 && side == 0) ? ebin : 0.f, 0.f, 0.f, 0.f};
+    // (unrolled: the independent groups are most of the latency hiding there is)
 #pragma unroll 8
     for (int k = 0; k < G; ++k)
       if (k < kend) {
@@ -445,9 +459,13 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
         for (int e = 0; e < 4; ++e) { z[e] = ot_ex2(z[e] + r); s4[e] += z[e]; }
         *reinterpret_cast<float4*>(srow + 128 * k) = make_float4(z[0], z[1], z[2], z[3]);   // e_ij, in place
       }
-    const float sum = fmaxf(warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])), kOtTiny);
+    const float part = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3]));
+    float* ps = psum + ((i - row0) & 1) * NW;             // double-buffered: the partner is at most one barrier behind
+    if (lane == 0) ps[warp] = part;
+    team_sync();
+    const float sum = fmaxf(ps[2 * team] + ps[2 * team + 1], kOtTiny);     // same order in both warps: same u_i
     const float ui = (bin_row ? d.mu_bin : d.norm) - (logf(sum) - rn);
-    if (lane == 0) u[i] = ui;
+    if (lane == 0 && side == 0) u[i] = ui;
     const float qi = fmaf(ui, kLog2e, head2 - mu_bin2);
     const float fi = ot_ex2(fminf(qi - r, 126.f));
 #pragma unroll
@@ -465,20 +483,20 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
   };
   if (ragged) run_rows(std::true_type{});
   else run_rows(std::false_type{});
-  // ---- add the warps' column sums through shared memory (the exchange aliases the row ring)
+  // ---- add the teams' column sums through shared memory (the exchange aliases the row ring)
   __syncthreads();
-  float* xch = rows_s + warp * (MAXM + 4);
+  float* xch = rows_s + team * (MAXM + 4) + coff;           // [NTEAM][MAXM + 4]
 #pragma unroll
   for (int k = 0; k < G; ++k)
     *reinterpret_cast<float4*>(xch + 4 * lane + 128 * k) = make_float4(cs[4 * k], cs[4 * k + 1], cs[4 * k + 2], cs[4 * k + 3]);
-  if (lane == 0) xch[MAXM] = bs;
+  if (lane == 0 && side == 0) rows_s[team * (MAXM + 4) + MAXM] = bs;
   __syncthreads();
   float* prow = partials + ((size_t)b * max_parts + blockIdx.x) * ld_part;
   for (int j = threadIdx.x; j <= d.m; j += NT) {
     const int jj = j == d.m ? MAXM : j;
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) t += rows_s[w * (MAXM + 4) + jj];
+    for (int w = 0; w < NTEAM; ++w) t += rows_s[w * (MAXM + 4) + jj];
     prow[j] = t;
   }
   __threadfence();
@@ -514,7 +532,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
 }
 
 template <int G, int NW>
-constexpr int ot_wide_smem_bytes() { return (NW * kOtRing * 128 * G + 128 * G + 4) * 4 + NW * kOtRing * 8; }
+constexpr int ot_wide_smem_bytes() { return (NW * kOtRing * 128 * G + 2 * 128 * G + 4 + 3 * NW) * 4 + NW * kOtRing * 8 + 16; }
 
 bool ot_fused_supported(const OtParams& p) {
   return p.M <= kOtWideMaxM && p.ldS % 4 == 0 && p.strideS % 4 == 0 && (reinterpret_cast<uintptr_t>(p.S) & 15) == 0;
@@ -532,10 +550,10 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(ot_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOtSmemBytes);
-    cudaFuncSetAttribute(ot_iter_wide_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ot_wide_smem_bytes<16, 8>());
-    cudaFuncSetAttribute(ot_iter_wide_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ot_wide_smem_bytes<32, 6>());
+    cudaFuncSetAttribute(ot_iter_wide_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         ot_wide_smem_bytes<8, 16>());
+    cudaFuncSetAttribute(ot_iter_wide_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         ot_wide_smem_bytes<16, 12>());
     attr_set = true;
   }
   const int wide = p.M <= kOtFusedMaxM ? 0 : (p.M <= 2048 ? 1 : 2);
@@ -543,7 +561,7 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
   max_parts = std::min(max_parts, cdiv(p.N + 1, 24));
   if (!wide) max_parts = ot_fused_parts(p.B, p.N, num_sms);
   const int ld_part = round_up(p.M + 1, 4);
-  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 24);                      // a multiple of 8 and of 6 warps
+  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 24);                      // a multiple of 8 and of the 6 / 8 row teams
   int* tickets = reinterpret_cast<int*>(scratch);
   float* partials = scratch + round_up(p.B, 64);
   cudaMemsetAsync(tickets, 0, sizeof(int) * p.B, ctx.stream);
@@ -554,10 +572,10 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
       ot_iter_kernel<<<grid, 256, kOtSmemBytes, ctx.stream>>>(p, partials, tickets, max_parts, ld_part, rows_per_cta,
                                                               it == 0);
     else if (wide == 1)
-      ot_iter_wide_kernel<16, 8><<<grid, 256, ot_wide_smem_bytes<16, 8>(), ctx.stream>>>(
+      ot_iter_wide_kernel<8, 16><<<grid, 512, ot_wide_smem_bytes<8, 16>(), ctx.stream>>>(
           p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
     else
-      ot_iter_wide_kernel<32, 6><<<grid, 192, ot_wide_smem_bytes<32, 6>(), ctx.stream>>>(
+      ot_iter_wide_kernel<16, 12><<<grid, 384, ot_wide_smem_bytes<16, 12>(), ctx.stream>>>(
           p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
     B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
   }
