@@ -184,6 +184,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: NCCL's own messages (its version banner, NCCL_DEBUG=INFO output) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
     torch.cuda.set_device(local)
