@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_RESULT_LINE = []              # the one JSON line, printed by main() after stdout is restored
 
 H, W, MAX_KP, D = 480, 640, 1024, 128
 KENC = [32, 64, 128]
@@ -163,7 +164,7 @@ def run_reference(args):
                              "sample": f"{args.steps} steps x 1 pair (640x480, 1024 kpts) through the torch-CPU oracle port "
                                        "(oracle/matching_oracle_torch.py)"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _RESULT_LINE.append(json.dumps(line))
 
 
 def workload_config(batch_per_gpu, sp_name):
@@ -184,8 +185,6 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly ONE JSON line: NCCL's own messages (its version banner, NCCL_DEBUG=INFO output) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
     torch.cuda.set_device(local)
@@ -422,7 +421,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": blas_threads(), "kind": "port",
                                     "sample": f"{args.cpu_pairs} pairs of the same workload through the torch-CPU "
                                               f"oracle port ({dt:.1f} s)"}
-        print(json.dumps(line), flush=True)
+        _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -438,10 +437,22 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=16, help="pairs timed through the CPU oracle (cpu_baseline)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so whatever a
+    # library prints to stdout from C code (NCCL's version banner under NCCL_DEBUG=VERSION, for one) cannot precede it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":
