@@ -31,10 +31,12 @@ KENC = [32, 64, 128]
 SINKHORN = 30
 GF_PAIR_TOTAL = 135.43        # algorithmic GFLOP per pair (C1/C2/C4)
 GF_PAIR_QK = 9.664            # attention QK^T only
-# dram__bytes_read+write of the dominant conv launch (fused stem + 64->64 layer at 480x640, 16-image micro-batch) from
-# profiles/r01_ncu_tc_conv_stem.txt: 19.8 MB read + 262.2 MB written; algorithmic = 19.7 MB images in + 314.6 MB of
-# pooled fp16 hi/lo planes out (part of the output is still in L2 when the kernel ends)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 282.0e6   # per 16-image launch (17.6 MB / image; scaled by the images one launch covers)
+# dram__bytes_read+write of the dominant conv launch (fused stem + 64->64 layer at 480x640, 64-image micro-batch) from
+# profiles/r01_ncu_step_per_kernel.txt / the ncu run behind it: 78.9 MB read (= the 64 images, compulsory) + 1204 MB
+# written; algorithmic = 78.6 MB images in + 1258 MB of pooled fp16 hi/lo planes out (a little of the output is still in
+# L2 when the kernel ends): no wasted re-reads
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 1283.0e6   # per 64-image launch (20.0 MB / image; scaled by the images one launch covers)
+NCU_CONV_IMAGES_PER_LAUNCH = 64
 GF_IMG_CONV3 = 51.79 - 0.354 - 0.472   # the eight 3x3 conv layers with Cin >= 64 (all but the Cin=1 stem and the two 1x1 heads)
 GF_IMG_CONV1 = 0.354                   # the Cin=1 stem, computed inside the fused first tc_conv launch
 GF_IMG_C1B = 2 * 9 * 64 * 64 * H * W / 1e9   # the 64->64 3x3 conv at full resolution (22.65 GF / image)
@@ -377,7 +379,7 @@ def run_b200(args):
                               "tcgen05, fp16 hi/lo operand split, weights resident in shared memory)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sustained"],
-                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH * (2 * B / max(n_launch, 1)) / 16,
+                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH * (2 * B / max(n_launch, 1)) / NCU_CONV_IMAGES_PER_LAUNCH,
                     "peak_source": pk["source"] + " bf16 dense sustained (kernel timed inside a long step)",
                     "flops_per_launch": flops_step / max(n_launch, 1), "avg_launch_ms": conv_ms / max(n_launch, 1),
                     "algorithmic_bytes_per_launch": int(2 * B / max(n_launch, 1) * (H * W * 4 + 64 * (H // 2) * (W // 2) * 2 * 2)),
@@ -389,7 +391,7 @@ def run_b200(args):
                     "note": "achieved counts algorithmic FLOPs once; the kernel issues 3 fp16 products per algorithmic "
                             "product (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32-class accuracy: 0 keypoint flips vs the "
                             "reference), i.e. %.0f TFLOP/s of fp16 tensor work against the bf16/fp16 dense peak; "
-                            "traffic = dram bytes per launch from ncu (profiles/r01_ncu_tc_conv_stem.txt)" % (3 * ach)}
+                            "traffic = dram bytes per launch from ncu (profiles/r01_ncu_step_per_kernel.txt)" % (3 * ach)}
         line = {"metric": "image-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
