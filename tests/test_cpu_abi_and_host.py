@@ -79,6 +79,19 @@ def test_shim_mirrors_reference_interface():
     assert (out["matches1"] == -1).all()
 
 
+def test_registration_wrappers_validate_and_have_no_cpu_fallback():
+    """image_matching_b200.registration (superpoint_glue_test.py:83-92,101 on the GPU): CPU tensors raise, bad dtypes raise."""
+    from image_matching_b200 import estimate_affine_partial_2d, warp_affine, register_pairs
+    m = object()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        estimate_affine_partial_2d(m, torch.zeros(1, 4, 2), torch.zeros(1, 4, 2), torch.zeros(1, 4, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        warp_affine(m, torch.zeros(8, 8), torch.eye(2, 3, dtype=torch.float64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        register_pairs(m, {"keypoints0": [torch.zeros(4, 2)], "keypoints1": [torch.zeros(4, 2)],
+                           "matches0": torch.zeros(1, 4, dtype=torch.int64)})
+
+
 def test_product_path_does_not_import_oracle():
     import subprocess
     code = ("import sys; sys.path.insert(0, %r); import image_matching_b200; "
