@@ -3,7 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import __graft_entry__ as g
-g.smoke()
+if os.environ.get('SANITIZE_SKIP_SMOKE') != '1':
+    g.smoke()
 from image_matching_b200 import Matching, stages, synth, estimate_affine_partial_2d, warp_affine
 cfg = {"superpoint": {"descriptor_dim": 128, "nms_radius": 4, "keypoint_threshold": 0.005, "max_keypoints": 1024, "remove_borders": 4, "weights": None},
        "superglue": {"descriptor_dim": 128, "keypoint_encoder": [32, 64, 128], "GNN_layers": ["self", "cross"] * 9, "sinkhorn_iterations": 3, "match_threshold": 0.2, "weights": ""}}
