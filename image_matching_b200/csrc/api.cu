@@ -104,6 +104,18 @@ struct b200m_handle {
 
 namespace {
 
+// Every entry point runs on the handle's device and leaves the caller's current device untouched.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 LaunchCtx make_ctx(b200m_handle* h, void* stream) {
   LaunchCtx c;
   c.stream = (cudaStream_t)stream;
@@ -436,8 +448,9 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
   launch_conv(ctx, p, L.ks, pool);
 }
 
-// One 3x3 layer on the tensor cores; falls back to the fp32 CUDA-core kernel if the launch is refused.
-// in/out are (hi, lo) plane pairs; out_lo == nullptr -> full-precision output in out_hi.
+// One 3x3 / 1x1 layer on the tensor cores.  in/out are (hi, lo) plane pairs; out_lo == nullptr -> full-precision output
+// in out_hi.  A declined launch (no cuTensorMapEncodeTiled entry point, tensor-map or attribute failure) is an ERROR
+// surfaced through finish(): the output buffer would otherwise be consumed unwritten.
 void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
                  float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow,
                  bool relu = true, int in_c8_total = 0, int in_c8_off = 0) {
@@ -450,7 +463,10 @@ void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const floa
     p.bias_in_params = 1;
     memcpy(p.bias_c, L.bias_host.data(), sizeof(float) * L.cout_pad);
   }
-  launch_tc_conv(ctx, p, h->num_sms);
+  if (!launch_tc_conv(ctx, p, h->num_sms) && ctx.err == cudaSuccess) {
+    ctx.err = cudaErrorLaunchFailure;
+    *ctx.err_where = "tc_conv (launch declined; B200M_CONV_IMPL=simt selects the fp32 CUDA-core path)";
+  }
 }
 
 // encoder + heads for `n` images (n <= micro-batch): fills w.semi (C4, 32 groups) and w.draw (C4, dpad/4 groups)
@@ -517,6 +533,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool 
   Arena A(ws, ws_bytes);
   SpWs w;
   if (!sp_carve(h, d, mb, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperPoint workspace too small: need %zu bytes", A.off);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), ctx.stream);
   for (int i0 = 0; i0 < n_images; i0 += mb) {
@@ -791,7 +808,6 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10)
     return fail(B200M_ERR_CUDA, "libb200match is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
-  cudaSetDevice(device);
   b200m_handle* h = new b200m_handle();
   h->cfg = *cfg;
   h->device = device;
@@ -814,6 +830,7 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
 
 void b200m_destroy(b200m_handle* h) {
   if (!h) return;
+  DeviceGuard dev_guard__(h->device);
   if (h->d_w) cudaFree(h->d_w);
   delete h;
 }
@@ -832,13 +849,14 @@ int b200m_set_tensor(b200m_handle* h, const char* name, const float* data_host, 
 
 int b200m_pack(b200m_handle* h, void* stream) {
   if (!h) return fail(B200M_ERR_INVALID, "null handle");
-  cudaSetDevice(h->device);
+  DeviceGuard dev_guard__(h->device);
   return do_pack(h, (cudaStream_t)stream);
 }
 
 int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* in, float* out, int n, int H,
                            int W, void* stream) {
   if (!h || !h->packed_sp || !in || !out) return fail(B200M_ERR_INVALID, "bad argument / SuperPoint not packed");
+  DeviceGuard dev_guard0__(h->device);
   const ConvLayer* Ls[8] = {&h->c1b, &h->c2a, &h->c2b, &h->c3a, &h->c3b, &h->c4a, &h->c4b, &h->heads};
   const bool pools[8] = {true, false, true, false, true, false, false, false};
   if (layer < 0 || layer >= 8) return fail(B200M_ERR_INVALID, "layer must be in [0,8)");
@@ -851,6 +869,7 @@ int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* 
   if (cudaMallocAsync(&buf, (3 * in_f + 2 * out_f) * sizeof(float), st) != cudaSuccess)
     return fail(B200M_ERR_CUDA, "scratch allocation failed");
   float *a = buf, *a_hi = a + in_f, *a_lo = a_hi + in_f, *o_hi = a_lo + in_f, *o_lo = o_hi + out_f;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (use_tc) {
     launch_nchw_to_c8_split(ctx, in, L.cin, a_hi, a_lo, n, H, W);
@@ -873,6 +892,7 @@ int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, 
   if (!h || !qkv || !msg) return fail(B200M_ERR_INVALID, "null argument");
   const int D = h->cfg.descriptor_dim;
   const size_t rows = (size_t)2 * B * Np, n = rows * 3 * D;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (use_tc) {
     float* planes = nullptr;      // fp16 planes: hi, lo (rows x 3D) and V^T hi, lo (rows x D), stored in a float buffer
@@ -906,6 +926,7 @@ int b200m_profile_begin(b200m_handle* h, int max_records) {
 int b200m_profile_end(b200m_handle* h, char* json, size_t json_cap) {
   if (!h || !json || json_cap < 3) return fail(B200M_ERR_INVALID, "bad argument");
   h->prof.enabled = false;
+  DeviceGuard dev_guard__(h->device);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(B200M_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
   std::map<std::string, std::pair<double, long long>> acc;
@@ -986,6 +1007,7 @@ int b200m_detector_post(b200m_handle* h, const float* semi, int n_images, int hc
   int* cc = A.take<int>(n_images + 2);
   unsigned char* nms_scr = A.take<unsigned char>(nms_scratch_bytes(n_images, d.H8, d.W8));
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "detector_post workspace too small: need %zu bytes", A.off);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_nchw_to_c4(ctx, semi, 65, semi_c4, 32, n_images, hc, wc);
   float* hp = heat ? heat : heat_ws;
@@ -1005,9 +1027,11 @@ int b200m_sample_descriptors(b200m_handle* h, const float* keypoints, const int*
   if (!h || !keypoints || !desc || !descriptors) return fail(B200M_ERR_INVALID, "null argument");
   const int D = h->cfg.descriptor_dim;
   // the stage API receives the reference-layout (n,D,h,w) map; the kernel wants C4-planar
+  DeviceGuard dev_guard0__(h->device);
   float* tmp = nullptr;
   if (cudaMallocAsync(&tmp, (size_t)n_images * D * hc * wc * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
     return fail(B200M_ERR_CUDA, "scratch allocation failed");
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_nchw_to_c4(ctx, desc, D, tmp, D / 4, n_images, hc, wc);
   launch_sample_descriptors(ctx, tmp, D / 4, D, n_images, hc, wc, keypoints, counts, cap, h->cfg.align_corners,
@@ -1021,6 +1045,7 @@ int b200m_knn_ratio_match(b200m_handle* h, const float* desc0, const float* desc
                           float* dist2, void* stream) {
   if (!h || !desc0 || !desc1 || !matches || !dist1 || !dist2) return fail(B200M_ERR_INVALID, "null argument");
   if (M <= 0 && N > 0) return fail(B200M_ERR_INVALID, "empty train set");
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (!launch_knn_ratio(ctx, desc0, desc1, counts0, counts1, B, h->cfg.descriptor_dim, N, M, ratio,
                         (long long*)matches, dist1, dist2))
@@ -1035,6 +1060,7 @@ int b200m_estimate_affine_partial(b200m_handle* h, const float* kpts0, const flo
   if (!h || !kpts0 || !kpts1 || !matches0 || !matrices || !inlier0 || !info)
     return fail(B200M_ERR_INVALID, "null argument");
   if (B < 0 || N < 0 || M < 0) return fail(B200M_ERR_INVALID, "negative size");
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (!launch_ransac_affine_partial(ctx, kpts0, kpts1, (const long long*)matches0, counts0, B, N, M,
                                     ransac_reproj_threshold, max_iters, confidence, refine_iters > 0, matrices,
@@ -1048,6 +1074,7 @@ int b200m_warp_affine(b200m_handle* h, const void* src, int dtype, int B, int sr
   if (!h || !src || !matrices || !dst) return fail(B200M_ERR_INVALID, "null argument");
   if (src_h <= 0 || src_w <= 0 || src_h > 32767 || src_w > 32767)
     return fail(B200M_ERR_INVALID, "source size %dx%d outside [1, 32767] (cv2's short coordinate maps)", src_h, src_w);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (!launch_warp_affine(ctx, src, dtype, B, src_h, src_w, matrices, dst, dst_h, dst_w))
     return fail(B200M_ERR_INVALID, "dtype %d not supported (0 = uint8, 1 = float32, 2 = float64)", dtype);
@@ -1071,6 +1098,7 @@ int b200m_superglue_forward(b200m_handle* h, const float* kpts0, const float* sc
   if (!h) return fail(B200M_ERR_INVALID, "null handle");
   if (!h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed (b200m_set_tensor + b200m_pack)");
   if (B <= 0) return B200M_OK;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   if (N == 0 || M == 0) {   // superglue_test.py:235-242
     launch_match_select(ctx, nullptr, nullptr, nullptr, 0, nullptr, nullptr, B, N, M, 0.f, (long long*)matches0,
@@ -1096,6 +1124,7 @@ int b200m_keypoint_encode(b200m_handle* h, const float* kpts, const float* score
   Arena A(ws, ws_bytes);
   SgWs w;
   if (!sg_carve(h, B, N, N, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_bcn_to_tokens(ctx, desc, B, D, N, w.X, w.Np, 2 * D);
   sg_kenc(h, ctx, w, 0, kpts, scores, B, N, H, W);
@@ -1114,6 +1143,7 @@ int b200m_gnn(b200m_handle* h, const float* desc0, const float* desc1, const int
   SgWs w;
   if (!sg_carve(h, B, N, M, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
   const size_t rows = (size_t)B * w.Np;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_bcn_to_tokens(ctx, desc0, B, D, N, w.X, w.Np, 2 * D);
   launch_bcn_to_tokens(ctx, desc1, B, D, M, w.X + rows * 2 * D, w.Np, 2 * D);
@@ -1131,6 +1161,7 @@ int b200m_score_matrix(b200m_handle* h, const float* desc0, const float* desc1, 
   SgWs w;
   if (!sg_carve(h, B, N, M, A, w)) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
   const size_t rows = (size_t)B * w.Np;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_bcn_to_tokens(ctx, desc0, B, D, N, w.X, w.Np, 2 * D);
   launch_bcn_to_tokens(ctx, desc1, B, D, M, w.X + rows * 2 * D, w.Np, 2 * D);
@@ -1151,6 +1182,7 @@ int b200m_sinkhorn(b200m_handle* h, const float* S, int B, int N, int M, int ite
   w.v = A.take<float>((size_t)B * w.ld_uv);
   w.ot_part = A.take<float>(ot_part_floats(B, N, M, M));
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   OtParams p = ot_params(h, w, S, M, (long long)N * M, B, N, M, nullptr, nullptr);
   sg_sinkhorn(h, ctx, p, iters, w.ot_part);
@@ -1167,6 +1199,7 @@ int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M, int
   int* idx0 = A.take<int>((size_t)B * ld);
   int* idx1 = A.take<int>((size_t)B * ld);
   if (!A.ok) return fail(B200M_ERR_WORKSPACE, "workspace too small: need %zu bytes", A.off);
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   launch_dense_argmax(ctx, Z, B, N, M, idx0, max0, idx1, ld);
   launch_match_select(ctx, idx0, max0, idx1, ld, nullptr, nullptr, B, N, M, h->cfg.match_threshold,
@@ -1189,6 +1222,7 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   if (!h->packed_sp || !h->packed_sg) return fail(B200M_ERR_WEIGHTS, "both SuperPoint and SuperGlue weights must be packed");
   if (B <= 0) return B200M_OK;
   if (cap < b200m_keypoint_capacity(h, H, W) || cap <= 0) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
+  DeviceGuard dev_guard0__(h->device);
   const int D = h->cfg.descriptor_dim;
   const size_t sp_bytes = align_up(sp_ws_bytes(h, B, H, W), 256);
   if (ws_bytes < sp_bytes) return fail(B200M_ERR_WORKSPACE, "matching workspace too small");
@@ -1207,6 +1241,7 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   rc = sp_forward_impl(h, stream, image1, images_u8, B, H, W, keypoints1, scores1, descriptors1, counts1, cap, nullptr,
                        nullptr, w.X + rows * 2 * D, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
   if (rc) return rc;
+  DeviceGuard dev_guard__(h->device);
   LaunchCtx ctx = make_ctx(h, stream);
   sg_core(h, ctx, w, keypoints0, scores0, counts0, keypoints1, scores1, counts1, B, cap, cap, H, W, H, W, matches0,
           matches1, mscores0, mscores1);

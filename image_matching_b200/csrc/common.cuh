@@ -39,6 +39,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one of these per kernel (function-local
+// static) remembers the devices it was set on, so a second GPU in the same process gets its own opt-in.
+struct SmemOptIn {
+  unsigned long long done = 0;
+  template <typename K>
+  bool ensure(K kern, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (dev < 64 && ((done >> dev) & 1ull)) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    if (dev < 64) done |= 1ull << dev;
+    return true;
+  }
+};
+
 // Launch bookkeeping: every launch goes through LAUNCH_CHECK so errors surface with a name and
 // the handle's launch counter (bench.py "gpu_launches") stays truthful.
 struct ProfRecord { const char* name; cudaEvent_t start, stop; };

@@ -177,12 +177,9 @@ template <int HD>
 static void launch_attention_t(LaunchCtx& ctx, const float* qkv, float* msg, int B, int Np, int D, int heads,
                                const int* c0, const int* c1, int nf0, int nf1, bool cross) {
   ProfScope prof__(ctx, "attention");
-  static bool attr_set = false;
+  static SmemOptIn opt;
   auto kern = attention_kernel<HD>;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttnSmem<HD>::BYTES);
-    attr_set = true;
-  }
+  opt.ensure(kern, (int)AttnSmem<HD>::BYTES);
   dim3 grid(cdiv(Np, kAttQ), heads, 2 * B);
   float scale = 1.f / sqrtf((float)HD);
   kern<<<grid, 128, AttnSmem<HD>::BYTES, ctx.stream>>>(qkv, msg, B, Np, D, c0, c1, nf0, nf1, cross ? 1 : 0, scale);

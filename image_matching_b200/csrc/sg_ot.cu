@@ -547,15 +547,10 @@ size_t ot_fused_scratch_floats(int pairs, int N, int M) {
 // p.u / p.v.  One launch per iteration over all pairs.
 void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, float* scratch, int num_sms) {
   if (iters <= 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ot_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOtSmemBytes);
-    cudaFuncSetAttribute(ot_iter_wide_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ot_wide_smem_bytes<8, 16>());
-    cudaFuncSetAttribute(ot_iter_wide_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ot_wide_smem_bytes<16, 12>());
-    attr_set = true;
-  }
+  static SmemOptIn opt_a, opt_b, opt_c;
+  opt_a.ensure(ot_iter_kernel, kOtSmemBytes);
+  opt_b.ensure(ot_iter_wide_kernel<8, 16>, ot_wide_smem_bytes<8, 16>());
+  opt_c.ensure(ot_iter_wide_kernel<16, 12>, ot_wide_smem_bytes<16, 12>());
   const int wide = p.M <= kOtFusedMaxM ? 0 : (p.M <= 2048 ? 1 : 2);
   int max_parts = std::max(1, std::min(kOtWideMaxParts, num_sms / std::max(p.B, 1)));   // one CTA per SM, one wave
   max_parts = std::min(max_parts, cdiv(p.N + 1, 24));
@@ -630,7 +625,8 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(ZSource z, const int* c
     int oj = __shfl_xor_sync(0xffffffffu, bj, o);
     if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
   }
-  if (lane == 0) { idx0[(size_t)b * ld + i] = bj; max0[(size_t)b * ld + i] = best; }
+  // (an all-NaN row never beats -inf and keeps the sentinel: report index 0 so match_select stays in bounds)
+  if (lane == 0) { idx0[(size_t)b * ld + i] = bj == 0x7fffffff ? 0 : bj; max0[(size_t)b * ld + i] = best; }
 }
 
 __global__ void __launch_bounds__(256) col_argmax_kernel(ZSource z, const int* counts0, const int* counts1,
@@ -659,7 +655,7 @@ __global__ void __launch_bounds__(256) col_argmax_kernel(ZSource z, const int* c
       int oi = ri[k][lane];
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    idx1[(size_t)b * ld + j] = bi;
+    idx1[(size_t)b * ld + j] = bi == 0x7fffffff ? 0 : bi;
   }
 }
 

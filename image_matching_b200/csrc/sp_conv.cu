@@ -269,12 +269,9 @@ __global__ void __launch_bounds__(256, 2) conv_c4_kernel(ConvParams p) {
 template <int KS, bool POOL>
 static void launch_conv_t(LaunchCtx& ctx, const ConvParams& p) {
   ProfScope prof__(ctx, KS == 3 ? "conv3x3_c4" : "conv1x1_c4");
-  static bool attr_set = false;
+  static SmemOptIn opt;
   auto kern = conv_c4_kernel<KS, POOL>;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvSmem<KS>::BYTES);
-    attr_set = true;
-  }
+  opt.ensure(kern, (int)ConvSmem<KS>::BYTES);
   dim3 grid(cdiv(p.W, 16) * cdiv(p.H, 16), p.cout_pad / 64, p.n);
   kern<<<grid, 256, ConvSmem<KS>::BYTES, ctx.stream>>>(p);
   B200M_LAUNCH_CHECK(ctx, "conv_c4");

@@ -313,12 +313,9 @@ template <int T, int NT>
 static void launch_nms_fused_r4_t(LaunchCtx& ctx, const float* heat, float* nms_dense, int n, int H8, int W8, float thr,
                                   int border, unsigned long long* cand_keys, int* cand_counts, int cand_cap,
                                   int* overflow_flag) {
-  static bool attr_set = false;
+  static SmemOptIn opt;
   auto kern = nms_fused_r4_kernel<T, NT>;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsFusedSmem<T>));
-    attr_set = true;
-  }
+  opt.ensure(kern, (int)sizeof(NmsFusedSmem<T>));
   dim3 grid(cdiv(W8, T), cdiv(H8, T), n);
   kern<<<grid, NT, sizeof(NmsFusedSmem<T>), ctx.stream>>>(heat, nms_dense, H8, W8, thr, border, cand_keys, cand_counts,
                                                          cand_cap, overflow_flag);
@@ -480,12 +477,9 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
                              int cand_cap, int n, int W8, int max_kp, float* keypoints, float* scores,
                              int* counts, int cap) {
   ProfScope prof__(ctx, "select_keypoints");
-  static bool attr_set = false;
+  static SmemOptIn opt;
   size_t bytes = (size_t)kSelectSmemKeys * sizeof(unsigned long long);
-  if (!attr_set) {
-    cudaFuncSetAttribute(select_keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    attr_set = true;
-  }
+  opt.ensure(select_keypoints_kernel, (int)bytes);
   select_keypoints_kernel<<<n, 1024, bytes, ctx.stream>>>(cand_keys, cand_counts, cand_cap, W8, max_kp,
                                                         keypoints, scores, counts, cap);
   B200M_LAUNCH_CHECK(ctx, "select_keypoints");

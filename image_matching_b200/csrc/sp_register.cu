@@ -327,11 +327,8 @@ bool launch_ransac_affine_partial(LaunchCtx& ctx, const float* kpts0, const floa
   const size_t smem = ransac_smem_bytes(N);
   if (smem > 200 * 1024) return false;
   if (B <= 0) return true;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ransac_affine_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  static SmemOptIn opt;
+  opt.ensure(ransac_affine_partial_kernel, 200 * 1024);
   {
     ProfScope ps(ctx, "ransac_affine_partial");
     ransac_affine_partial_kernel<<<B, kRansacThreads, smem, ctx.stream>>>(

@@ -442,12 +442,9 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
       !make_f16_map(&mv_hi, vt_hi, (size_t)2 * B * D, Np, Np, KT, HD) || !make_f16_map(&mv_lo, vt_lo, (size_t)2 * B * D, Np, Np, KT, HD))
     return false;
   using SM = TcAttnSmem<HD, KT>;
-  static bool attr_set = false;
+  static SmemOptIn opt;
   auto kern = tc_attention_kernel<HD, KT>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess) return false;
-    attr_set = true;
-  }
+  if (!opt.ensure(kern, (int)SM::BYTES)) return false;
   TcAttnParams p;
   p.msg = msg; p.msg_hi = reinterpret_cast<__half*>(msg_hi); p.msg_lo = reinterpret_cast<__half*>(msg_lo); p.B = B; p.Np = Np; p.D = D; p.counts0 = c0; p.counts1 = c1; p.n_full0 = nf0; p.n_full1 = nf1;
   p.cross = cross ? 1 : 0;

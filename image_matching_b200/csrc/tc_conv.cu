@@ -423,13 +423,9 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
     if (!make_act_map(&tm_hi, p.in_hi, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
     if (!make_act_map(&tm_lo, p.in_lo, p.n, c8_total, p.H, p.W, SM::HALO)) return false;
   }
-  static bool attr_set = false;
+  static SmemOptIn opt;
   auto kern = tc_conv_kernel<NB, POOL, KS, FUSE1, RESIDENT>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess)
-      return false;
-    attr_set = true;
-  }
+  if (!opt.ensure(kern, (int)SM::BYTES)) return false;
   const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
   const int grid = total < num_sms ? total : num_sms;
   kern<<<grid, SM::THREADS, SM::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);

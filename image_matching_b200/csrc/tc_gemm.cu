@@ -291,12 +291,8 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   if (!make_sw128_map2(&ma, p.A, a_rows, p.K, p.lda, 128) ||
       !make_sw128_map_f16(&mh, w_hi, w_rows, p.K, ldw, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, w_rows, p.K, ldw, kGemmNT))
     return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) != cudaSuccess)
-      return false;
-    attr_set = true;
-  }
+  static SmemOptIn opt;
+  if (!opt.ensure(tc_gemm_kernel, (int)kGemmSmem)) return false;
   const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT) * p.batch;
   const int grid = total < num_sms ? total : num_sms;
   tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);

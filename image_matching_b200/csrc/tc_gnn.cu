@@ -496,12 +496,8 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
       !gn_map_f16(&mq_hi, p.qkv_hi, (size_t)p.rows, 384, 384) || !gn_map_f16(&mq_lo, p.qkv_lo, (size_t)p.rows, 384, 384) ||
       !gn_map_f16(&mv_hi, p.vt_hi, vt_rows, p.vt_np, p.vt_np) || !gn_map_f16(&mv_lo, p.vt_lo, vt_rows, p.vt_np, p.vt_np))
     return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSmem) != cudaSuccess)
-      return false;
-    attr_set = true;
-  }
+  static SmemOptIn opt;
+  if (!opt.ensure(tc_gnn_layer_kernel, (int)kGnSmem)) return false;
   const int ntiles = cdiv(p.rows, 128);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);

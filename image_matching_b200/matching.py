@@ -36,6 +36,9 @@ def _image(x: torch.Tensor) -> torch.Tensor:
     """(B,1,H,W) image batch as the library takes it: fp32 in [0,1] (the reference's contract), or -- extension,
     SURVEY.md 8 f2 -- the raw uint8 pixels, normalised by 255 on the device exactly like datasets/SSHIDataset.py:26-29
     followed by `.float()`, so the 8-bit image can be uploaded instead of a 4x (float64: 8x) larger tensor."""
+    if x.dim() != 4 or x.shape[1] != 1:
+        # the reference's first Conv2d(1, 64) raises on anything but one channel; never read a (B,C>1,H,W) buffer as B*H*W
+        raise ValueError(f"expected a (B,1,H,W) grayscale image batch, got shape {tuple(x.shape)}")
     return x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
 
 
@@ -80,6 +83,7 @@ class _Engine:
         self.cfg_key = None
         self.dirty = True
         self.ws = None
+        self.packed = {}        # module id -> _weights_version this engine last packed
 
     def close(self):
         if self.handle is not None:
@@ -128,7 +132,11 @@ class _Engine:
             idx = device.index if device.index is not None else torch.cuda.current_device()
             _lib.check(L.b200m_create(C.byref(cfg), idx, C.byref(hp)), "b200m_create")
             self.handle, self.device, self.cfg_key, self.dirty = hp, device, key, True
-        if self.dirty or (sp is not None and sp._dirty) or (sg is not None and sg._dirty):
+            self.packed = {}
+        # every engine remembers the weight version IT packed: a module shared by two engines (its own and Matching's)
+        # is repacked by each of them when its weights change
+        stale = [mod for mod in (sp, sg) if mod is not None and self.packed.get(id(mod)) != mod._weights_version]
+        if self.dirty or stale:
             for prefix, mod in (("superpoint.", sp), ("superglue.", sg)):
                 if mod is None:
                     continue
@@ -139,10 +147,8 @@ class _Engine:
                     shp = (C.c_int64 * max(a.ndim, 1))(*a.shape)
                     _lib.check(L.b200m_set_tensor(self.handle, (prefix + k).encode(),
                                                   a.ctypes.data_as(C.c_void_p), shp, a.ndim), "b200m_set_tensor")
-                mod._dirty = False
-            with torch.cuda.device(device):
-                _lib.check(L.b200m_pack(self.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                           "b200m_pack")
+                self.packed[id(mod)] = mod._weights_version
+            _lib.check(L.b200m_pack(self.handle, _stream(device)), "b200m_pack")
             self.dirty = False
         return L
 
@@ -156,22 +162,29 @@ class _Engine:
         return int(_lib.load().b200m_launch_count(self.handle)) if self.handle is not None else 0
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device):
+    """torch's current stream ON THE TENSORS' DEVICE (not the process's current device); the C entry points switch to
+    the handle's device themselves and restore the caller's."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class _B200Module(nn.Module):
     def __init__(self):
         super().__init__()
-        self._dirty = True
+        self._weights_version = 0
         self._engine = _Engine()
 
+    def mark_dirty(self):
+        """Tell every engine using this module that its weights changed.  load_state_dict() does this itself; call it
+        after editing parameters in place (``p.data.copy_()``, ``bin_score.fill_()``), which torch does not report."""
+        self._weights_version += 1
+
     def _load_from_state_dict(self, *a, **k):   # weights changed -> repack on next forward
-        self._dirty = True
+        self._weights_version += 1
         return super()._load_from_state_dict(*a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._dirty = True
+        self._weights_version += 1
         return super().load_state_dict(*a, **k)
 
     def _engine_state(self):
@@ -222,7 +235,7 @@ class SuperPoint(_B200Module):
         ws = engine.workspace(nbytes, dev)
         fn = L.b200m_superpoint_forward_u8 if x.dtype == torch.uint8 else L.b200m_superpoint_forward
         _lib.check(fn(engine.handle, _ptr(x), B, H, W, _ptr(kp), _ptr(sc), _ptr(de),
-                      _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream()), "b200m_superpoint_forward")
+                      _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream(dev)), "b200m_superpoint_forward")
         return kp, sc, de, cnt
 
     @staticmethod
@@ -270,7 +283,7 @@ def knn_ratio_match(superpoint: "SuperPoint", desc0: torch.Tensor, desc1: torch.
     e1 = torch.empty((B, N), dtype=torch.float32, device=d0.device)
     e2 = torch.empty((B, N), dtype=torch.float32, device=d0.device)
     _lib.check(L.b200m_knn_ratio_match(superpoint._engine.handle, _ptr(d0), _ptr(d1), None, None, B, N, M,
-                                       float(ratio), _ptr(match), _ptr(e1), _ptr(e2), _stream()), "b200m_knn_ratio_match")
+                                       float(ratio), _ptr(match), _ptr(e1), _ptr(e2), _stream(d0.device)), "b200m_knn_ratio_match")
     return (match[0], e1[0], e2[0]) if single else (match, e1, e2)
 
 
@@ -374,7 +387,7 @@ class SuperGlue(_B200Module):
         _lib.check(L.b200m_superglue_forward(engine.handle, _ptr(kpts0), _ptr(sc0), _ptr(desc0), _ptr(counts0),
                                              _ptr(kpts1), _ptr(sc1), _ptr(desc1), _ptr(counts1),
                                              B, N, M, H0, W0, H1, W1, _ptr(m0), _ptr(m1), _ptr(s0), _ptr(s1),
-                                             _ptr(ws), ws.numel(), _stream()), "b200m_superglue_forward")
+                                             _ptr(ws), ws.numel(), _stream(dev)), "b200m_superglue_forward")
         return m0, m1, s0, s1
 
     def forward(self, data, _engine=None):
@@ -423,6 +436,8 @@ class Matching(nn.Module):
         B, _, H, W = image0.shape
         dev = image0.device
         D = self.superpoint.config["descriptor_dim"]
+        if self.superpoint.config["max_keypoints"] < 0:
+            return self._forward_device_unbounded(L, image0, image1)
         cap = int(L.b200m_keypoint_capacity(e.handle, H, W))
         f32, i64 = torch.float32, torch.int64
         out = {
@@ -447,7 +462,38 @@ class Matching(nn.Module):
             _ptr(out["keypoints0"]), _ptr(out["scores0"]), _ptr(out["descriptors0"]), _ptr(c0),
             _ptr(out["keypoints1"]), _ptr(out["scores1"]), _ptr(out["descriptors1"]), _ptr(c1), cap,
             _ptr(out["matches0"]), _ptr(out["matches1"]), _ptr(out["matching_scores0"]),
-            _ptr(out["matching_scores1"]), _ptr(ws), ws.numel(), _stream()), "b200m_matching_forward")
+            _ptr(out["matching_scores1"]), _ptr(ws), ws.numel(), _stream(dev)), "b200m_matching_forward")
+        return out
+
+    def _forward_device_unbounded(self, L, image0, image1):
+        """``max_keypoints = -1`` (the default of SuperPoint.default_config and of superpoint_glue_test.py:29): the
+        keypoint count is only bounded by the NMS capacity (16384 at 640x480, 65536 at 1280x960), and padding SuperGlue
+        to that bound would cost cap^2 score matrices (1 GiB / 17 GiB per pair) and 8-16x redundant GNN work.  So this
+        configuration runs in two phases: SuperPoint, ONE host read of the per-image counts, then SuperGlue sized to the
+        largest count actually found.  Same output dict as forward_device, padded to that count."""
+        e = self._engine
+        B = image0.shape[0]
+        dev = image0.device
+        kp0, sc0, de0, c0 = self.superpoint._run(e, L, image0)
+        kp1, sc1, de1, c1 = self.superpoint._run(e, L, image1)
+        counts = torch.stack([c0, c1])
+        nmax = counts.max(dim=1).values.cpu().tolist()          # the host sync of this configuration
+        n, m = max(int(nmax[0]), 0), max(int(nmax[1]), 0)
+        out = {"keypoints0": kp0[:, :n].contiguous(), "scores0": sc0[:, :n].contiguous(),
+               "descriptors0": de0[:, :, :n].contiguous(),
+               "keypoints1": kp1[:, :m].contiguous(), "scores1": sc1[:, :m].contiguous(),
+               "descriptors1": de1[:, :, :m].contiguous(), "counts": counts}
+        if n == 0 or m == 0:
+            out.update({"matches0": torch.full((B, n), -1, dtype=torch.int64, device=dev),
+                        "matches1": torch.full((B, m), -1, dtype=torch.int64, device=dev),
+                        "matching_scores0": torch.zeros((B, n), device=dev),
+                        "matching_scores1": torch.zeros((B, m), device=dev)})
+            return out
+        data = {"image0": image0, "image1": image1, "keypoints0": out["keypoints0"], "scores0": out["scores0"],
+                "descriptors0": out["descriptors0"], "keypoints1": out["keypoints1"], "scores1": out["scores1"],
+                "descriptors1": out["descriptors1"]}
+        m0, m1, s0, s1 = self.superglue._run(e, L, data, counts0=c0, counts1=c1)
+        out.update({"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1})
         return out
 
     def forward(self, data):

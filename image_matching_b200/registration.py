@@ -56,7 +56,7 @@ def estimate_affine_partial_2d(owner, kpts0: torch.Tensor, kpts1: torch.Tensor, 
         counts0 = counts0.contiguous().to(torch.int32)
     _lib.check(L.b200m_estimate_affine_partial(h, _ptr(k0), _ptr(k1), _ptr(m0), _ptr(counts0), B, N, M,
                                                float(ransac_reproj_threshold), int(max_iters), float(confidence),
-                                               int(refine_iters), _ptr(mats), _ptr(inl), _ptr(info), _stream()),
+                                               int(refine_iters), _ptr(mats), _ptr(inl), _ptr(info), _stream(dev)),
                "b200m_estimate_affine_partial")
     return mats, inl, info
 
@@ -78,7 +78,7 @@ def warp_affine(owner, src: torch.Tensor, matrices: torch.Tensor, dsize: tuple[i
     dw, dh = (W, H) if dsize is None else (int(dsize[0]), int(dsize[1]))
     L, h = _handle(owner, s.device)
     dst = torch.empty((B, dh, dw), dtype=s.dtype, device=s.device)
-    _lib.check(L.b200m_warp_affine(h, _ptr(s), _DTYPES[s.dtype], B, H, W, _ptr(m), _ptr(dst), dh, dw, _stream()),
+    _lib.check(L.b200m_warp_affine(h, _ptr(s), _DTYPES[s.dtype], B, H, W, _ptr(m), _ptr(dst), dh, dw, _stream(s.device)),
                "b200m_warp_affine")
     return dst[0] if single else dst
 

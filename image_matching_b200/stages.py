@@ -26,7 +26,7 @@ def superpoint_dense(m: Matching, images: torch.Tensor):
     desc = torch.empty((n, D, hc, wc), device=images.device)
     ws = e.workspace(L.b200m_superpoint_workspace_bytes(e.handle, n, H, W), images.device)
     _lib.check(L.b200m_superpoint_dense(e.handle, _ptr(images), n, H, W, _ptr(semi), _ptr(desc), _ptr(ws),
-                                        ws.numel(), _stream()), "b200m_superpoint_dense")
+                                        ws.numel(), _stream(images.device)), "b200m_superpoint_dense")
     return semi, desc
 
 
@@ -45,7 +45,7 @@ def detector_post(m: Matching, semi: torch.Tensor):
     cnt = torch.empty((n,), dtype=torch.int32, device=dev)
     ws = e.workspace(L.b200m_superpoint_workspace_bytes(e.handle, n, hc * 8, wc * 8), dev)
     _lib.check(L.b200m_detector_post(e.handle, _ptr(semi), n, hc, wc, _ptr(heat), _ptr(nms), _ptr(kp), _ptr(sc),
-                                     _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream()), "b200m_detector_post")
+                                     _ptr(cnt), cap, _ptr(ws), ws.numel(), _stream(semi.device)), "b200m_detector_post")
     return heat, nms, kp, sc, cnt
 
 
@@ -58,7 +58,7 @@ def sample_descriptors(m: Matching, keypoints: torch.Tensor, counts, desc: torch
     cap = keypoints.shape[1]
     out = torch.empty((n, D, cap), device=desc.device)
     _lib.check(L.b200m_sample_descriptors(e.handle, _ptr(keypoints), _ptr(counts), _ptr(desc), n, hc, wc, cap,
-                                          _ptr(out), _stream()), "b200m_sample_descriptors")
+                                          _ptr(out), _stream(desc.device)), "b200m_sample_descriptors")
     return out
 
 
@@ -74,7 +74,7 @@ def keypoint_encode(m: Matching, kpts, scores, desc, H, W):
     out = torch.empty_like(desc)
     ws = _sg_ws(L, e, B, N, N, desc.device)
     _lib.check(L.b200m_keypoint_encode(e.handle, _ptr(kpts), _ptr(scores), _ptr(desc), B, N, H, W, _ptr(out),
-                                       _ptr(ws), ws.numel(), _stream()), "b200m_keypoint_encode")
+                                       _ptr(ws), ws.numel(), _stream(desc.device)), "b200m_keypoint_encode")
     return out
 
 
@@ -89,7 +89,7 @@ def gnn(m: Matching, desc0, desc1, layer_begin=0, layer_end=None, counts0=None, 
     o0, o1 = torch.empty_like(desc0), torch.empty_like(desc1)
     ws = _sg_ws(L, e, B, N, M, desc0.device)
     _lib.check(L.b200m_gnn(e.handle, _ptr(desc0), _ptr(desc1), _ptr(counts0), _ptr(counts1), B, N, M,
-                           layer_begin, layer_end, _ptr(o0), _ptr(o1), _ptr(ws), ws.numel(), _stream()),
+                           layer_begin, layer_end, _ptr(o0), _ptr(o1), _ptr(ws), ws.numel(), _stream(desc0.device)),
                "b200m_gnn")
     return o0, o1
 
@@ -103,7 +103,7 @@ def score_matrix(m: Matching, desc0, desc1):
     S = torch.empty((B, N, M), device=desc0.device)
     ws = _sg_ws(L, e, B, N, M, desc0.device)
     _lib.check(L.b200m_score_matrix(e.handle, _ptr(desc0), _ptr(desc1), B, N, M, _ptr(S), _ptr(ws), ws.numel(),
-                                    _stream()), "b200m_score_matrix")
+                                    _stream(desc0.device)), "b200m_score_matrix")
     return S
 
 
@@ -116,7 +116,7 @@ def sinkhorn(m: Matching, S, iters=None):
         iters = m.superglue.config["sinkhorn_iterations"]
     Z = torch.empty((B, N + 1, M + 1), device=S.device)
     ws = _sg_ws(L, e, B, N, M, S.device)
-    _lib.check(L.b200m_sinkhorn(e.handle, _ptr(S), B, N, M, iters, _ptr(Z), _ptr(ws), ws.numel(), _stream()),
+    _lib.check(L.b200m_sinkhorn(e.handle, _ptr(S), B, N, M, iters, _ptr(Z), _ptr(ws), ws.numel(), _stream(S.device)),
                "b200m_sinkhorn")
     return Z
 
@@ -134,7 +134,7 @@ def match_select(m: Matching, Z):
     s1 = torch.empty((B, M), device=dev)
     ws = _sg_ws(L, e, B, N, M, dev)
     _lib.check(L.b200m_match_select(e.handle, _ptr(Z), B, N, M, _ptr(m0), _ptr(m1), _ptr(s0), _ptr(s1), _ptr(ws),
-                                    ws.numel(), _stream()), "b200m_match_select")
+                                    ws.numel(), _stream(Z.device)), "b200m_match_select")
     return m0, m1, s0, s1
 
 
@@ -147,7 +147,7 @@ def debug_conv_layer(m: Matching, layer: int, use_tc: bool, x: torch.Tensor):
     pool = layer in (0, 2, 4)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     out = torch.empty((n, cout, Ho, Wo), device=x.device)
-    _lib.check(L.b200m_debug_conv_layer(e.handle, layer, int(use_tc), _ptr(x), _ptr(out), n, H, W, _stream()),
+    _lib.check(L.b200m_debug_conv_layer(e.handle, layer, int(use_tc), _ptr(x), _ptr(out), n, H, W, _stream(x.device)),
                "b200m_debug_conv_layer")
     return out
 
@@ -159,5 +159,5 @@ def debug_attention(m: Matching, qkv: torch.Tensor, B: int, Np: int, n0: int, n1
     D = qkv.shape[1] // 3
     out = torch.zeros((qkv.shape[0], D), device=qkv.device)
     _lib.check(L.b200m_debug_attention(e.handle, _ptr(qkv), _ptr(out), B, Np, n0, n1, int(cross), int(use_tc),
-                                       _stream()), "b200m_debug_attention")
+                                       _stream(qkv.device)), "b200m_debug_attention")
     return out

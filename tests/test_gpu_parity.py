@@ -3,8 +3,9 @@
  (b) the numpy oracle on freshly seeded inputs.
 Tolerances: integer / index outputs exact given identical inputs; fp32 tensors within the
 budgets of SURVEY.md 8(d): semi/heat-level 1e-6..5e-4 (stated per assert), descriptors / S / Z 1e-3.
-End-to-end keypoint / match equality is ill-conditioned (adjacent score gaps ~6e-8), so it is
-asserted on order-canonical sets with the flip count printed.
+End-to-end gates are north_star's: keypoint-SET equality and match-pair equality (matches mapped to
+coordinate pairs, so a swap of two equal-score keypoints in the top-k order is not a difference), with
+the flip counts printed (run with -rP; the log of the last GPU run is committed under profiles/).
 """
 import numpy as np
 import pytest
@@ -205,8 +206,9 @@ def test_superglue_given_reference_features(stage):
     assert pred["matches0"].dtype == torch.int64 and m0.shape == g["matches0"].shape
     agree = (m0 == g["matches0"]).mean()
     valid_ref = g["matches0"] > -1
-    print(f"superglue: matches0 agreement {agree:.4f}, {valid_ref.sum()} valid in reference")
-    assert agree >= 0.99
+    print(f"FLIPS superglue on reference features: matches0 agreement {agree:.4f}, {valid_ref.sum()} valid in reference, "
+          f"{int((m0 != g['matches0']).sum())} differ")
+    assert np.array_equal(m0, g["matches0"])
     both = valid_ref & (m0 > -1)
     assert np.abs(pred["matching_scores0"].cpu().numpy() - g["matching_scores0"])[both].max() < 1e-3
 
@@ -225,15 +227,15 @@ def test_end_to_end_vs_reference(name):
         for side in "01":
             ref = kp_set(g[f"keypoints{side}_{i}"])
             got = kp_set(pred["keypoints" + side][i].cpu().numpy())
-            print(f"{name}[{i}] side{side}: {len(ref)} ref keypoints, {len(ref ^ got)} differ")
-            assert len(ref & got) >= 0.99 * len(ref)
+            print(f"FLIPS {name}[{i}] side{side}: {len(ref)} ref keypoints, {len(ref ^ got)} differ")
+            assert ref == got, f"{len(ref ^ got)} keypoint flips"
             assert pred["descriptors" + side][i].shape == (c["cfg"]["superpoint"]["descriptor_dim"], len(got))
         ref_pairs = match_pairs(g[f"keypoints0_{i}"], g[f"keypoints1_{i}"], g["matches0"][i])
         got_pairs = match_pairs(pred["keypoints0"][i].cpu().numpy(), pred["keypoints1"][i].cpu().numpy(),
                                 pred["matches0"][i].cpu().numpy())
-        print(f"{name}[{i}]: {len(ref_pairs)} ref matches, {len(ref_pairs & got_pairs)} identical, "
+        print(f"FLIPS {name}[{i}]: {len(ref_pairs)} ref matches, {len(ref_pairs & got_pairs)} identical, "
               f"{len(got_pairs - ref_pairs)} extra")
-        assert len(ref_pairs & got_pairs) >= 0.9 * len(ref_pairs)
+        assert ref_pairs == got_pairs, f"{len(ref_pairs ^ got_pairs)} match flips"
     if name == "ragged_hw":
         # max_keypoints = -1 -> row-major (y, then x) order as torch.nonzero produces
         k = pred["keypoints0"][0].cpu().numpy()
@@ -253,11 +255,13 @@ def test_against_oracle_fresh_seed():
     pred = m({"image0": _t(a[None, None]), "image1": _t(b[None, None])})
     for side in "01":
         ref, got = kp_set(r["keypoints" + side]), kp_set(pred["keypoints" + side][0].cpu().numpy())
-        assert len(ref & got) >= 0.98 * len(ref)
+        print(f"FLIPS fresh_seed side{side}: {len(ref)} oracle keypoints, {len(ref ^ got)} differ")
+        assert ref == got
     rp = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
     gp = match_pairs(pred["keypoints0"][0].cpu().numpy(), pred["keypoints1"][0].cpu().numpy(),
                      pred["matches0"][0].cpu().numpy())
-    assert len(rp & gp) >= 0.9 * len(rp)
+    print(f"FLIPS fresh_seed: {len(rp)} oracle matches, {len(rp ^ gp)} differ")
+    assert rp == gp
 
 
 def test_batch_equals_single():
@@ -392,8 +396,8 @@ def test_config5_external_features_vs_oracle():
     m0 = pred["matches0"][0].cpu().numpy()
     agree = (m0 == r["matches0"]).mean()
     nvalid = int((r["matches0"] > -1).sum())
-    print(f"config5: {nvalid} oracle matches, agreement {agree:.4f}")
-    assert nvalid > 200 and agree >= 0.995
+    print(f"FLIPS config5 (2048): {nvalid} oracle matches, agreement {agree:.4f}, {int((m0 != r['matches0']).sum())} differ")
+    assert nvalid > 200 and np.array_equal(m0, r["matches0"])
     both = (m0 > -1) & (r["matches0"] > -1)
     assert np.abs(pred["matching_scores0"][0].cpu().numpy() - r["matching_scores0"])[both].max() < 1e-3
 
