@@ -1207,6 +1207,27 @@ int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M, int
   return finish(h, ctx);
 }
 
+int b200m_pack_match_wire(b200m_handle* h, const int64_t* matches0, const float* mscores0, int B_valid, int B_wire,
+                          int N, int ld, int32_t* wire, void* stream) {
+  if (!h || !wire || (B_valid > 0 && (!matches0 || !mscores0))) return fail(B200M_ERR_INVALID, "null argument");
+  if (B_valid < 0 || B_wire < B_valid || N < 0 || ld < N) return fail(B200M_ERR_INVALID, "bad wire shape");
+  DeviceGuard dev_guard__(h->device);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_pack_match_wire(ctx, (const long long*)matches0, mscores0, B_valid, B_wire, N, ld, wire);
+  return finish(h, ctx);
+}
+
+int b200m_unpack_match_wire(b200m_handle* h, const int32_t* wire, int world, int B_wire, int n_pairs, int N,
+                            int64_t* matches0, float* mscores0, void* stream) {
+  if (!h || !wire || !matches0 || !mscores0) return fail(B200M_ERR_INVALID, "null argument");
+  if (world <= 0 || n_pairs < 0 || N < 0 || (long long)B_wire * world < n_pairs)
+    return fail(B200M_ERR_INVALID, "bad wire shape");
+  DeviceGuard dev_guard__(h->device);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_unpack_match_wire(ctx, wire, world, B_wire, n_pairs, N, (long long*)matches0, mscores0);
+  return finish(h, ctx);
+}
+
 size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W) {
   if (!h) return 0;
   int cap = b200m_keypoint_capacity(h, H, W);

@@ -190,4 +190,10 @@ void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, con
                          const int* counts0, const int* counts1, int B, int N, int M, float thr,
                          long long* matches0, long long* matches1, float* ms0, float* ms1);
 
+// multi-GPU gather wire format (one int32 buffer per rank: [pair][index row | score-bits row][N])
+void launch_pack_match_wire(LaunchCtx& ctx, const long long* matches, const float* scores, int B_valid, int B_wire,
+                            int N, int ld, int* wire);
+void launch_unpack_match_wire(LaunchCtx& ctx, const int* wire, int world, int bmax, int n_pairs, int N,
+                              long long* matches, float* scores);
+
 }  // namespace b200m

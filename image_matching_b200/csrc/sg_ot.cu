@@ -736,4 +736,47 @@ void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, con
   B200M_LAUNCH_CHECK(ctx, "match_select");
 }
 
+// ---- multi-GPU wire format of the final gather (image_matching_b200/dist.py): ONE int32 buffer per rank,
+// [pair][0][N] = match index (int64 -> int32), [pair][1][N] = matching score bits; pairs >= B_valid are padding (-1 / 0)
+__global__ void pack_match_wire_kernel(const long long* __restrict__ matches, const float* __restrict__ scores,
+                                       int B_valid, int N, int ld, int* __restrict__ wire, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t b = i / N, t = i - b * N;
+  const bool ok = (int)b < B_valid;
+  wire[(b * 2) * N + t] = ok ? (int)matches[b * ld + t] : -1;
+  wire[(b * 2 + 1) * N + t] = ok ? __float_as_int(scores[b * ld + t]) : 0;
+}
+// gathered wire (ranks x bmax pairs) -> (n_pairs, N) int64 matches + fp32 scores; rank r owns `base + (r < rem)` pairs
+__global__ void unpack_match_wire_kernel(const int* __restrict__ wire, int world, int bmax, int base, int rem, int N,
+                                         long long* __restrict__ matches, float* __restrict__ scores, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t g = i / N, t = i - g * N;                 // g = global pair index
+  // contiguous shards, remainder pairs on the first ranks (dist.shard_range)
+  const size_t big = (size_t)rem * (base + 1);
+  const size_t r = g < big ? g / (base + 1) : rem + (g - big) / (base > 0 ? base : 1);
+  const size_t lo = r < (size_t)rem ? r * (base + 1) : big + (r - rem) * base;
+  const size_t src = (r * bmax + (g - lo)) * 2;
+  matches[i] = wire[src * N + t];
+  scores[i] = __int_as_float(wire[(src + 1) * N + t]);
+}
+void launch_pack_match_wire(LaunchCtx& ctx, const long long* matches, const float* scores, int B_valid, int B_wire,
+                            int N, int ld, int* wire) {
+  const size_t total = (size_t)B_wire * N;
+  if (!total) return;
+  ProfScope prof__(ctx, "match_wire");
+  pack_match_wire_kernel<<<(unsigned)cdivz(total, 256), 256, 0, ctx.stream>>>(matches, scores, B_valid, N, ld, wire, total);
+  B200M_LAUNCH_CHECK(ctx, "pack_match_wire");
+}
+void launch_unpack_match_wire(LaunchCtx& ctx, const int* wire, int world, int bmax, int n_pairs, int N,
+                              long long* matches, float* scores) {
+  const size_t total = (size_t)n_pairs * N;
+  if (!total) return;
+  ProfScope prof__(ctx, "match_wire");
+  unpack_match_wire_kernel<<<(unsigned)cdivz(total, 256), 256, 0, ctx.stream>>>(wire, world, bmax, n_pairs / world,
+                                                                               n_pairs % world, N, matches, scores, total);
+  B200M_LAUNCH_CHECK(ctx, "unpack_match_wire");
+}
+
 }  // namespace b200m

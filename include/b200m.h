@@ -194,6 +194,16 @@ int b200m_matching_forward_u8(b200m_handle* h, const uint8_t* image0, const uint
                            int cap, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* Multi-GPU gather of the results (pairs are sharded over ranks, the only collective is the final gather
+ * of match indices): ONE int32 wire buffer per rank, (B_wire, 2, N) = per pair a row of match indices (int64 -> int32)
+ * and a row of matching-score bits, so a single all-gather moves both.  `pack` reads this rank's (B_valid, N) results
+ * with row pitch `ld` and pads pairs [B_valid, B_wire) with -1 / 0; `unpack` turns the gathered (world, B_wire, 2, N)
+ * buffer into (n_pairs, N) int64 matches + fp32 scores (contiguous shards, remainder pairs on the first ranks). */
+int b200m_pack_match_wire(b200m_handle* h, const int64_t* matches0, const float* mscores0, int B_valid, int B_wire,
+                          int N, int ld, int32_t* wire, void* stream);
+int b200m_unpack_match_wire(b200m_handle* h, const int32_t* wire, int world, int B_wire, int n_pairs, int N,
+                            int64_t* matches0, float* mscores0, void* stream);
+
 /* Test hook: run ONE packed 3x3 encoder/head layer (0=inc.conv[3], 1..2=down1, 3..4=down2, 5..6=down3, 7=convPa|convDa)
  * on `in` (n,cin,H,W) -> `out` (n,cout,H',W') with the tcgen05 fp16 hi/lo-split kernel (use_tc=1) or the fp32 CUDA-core
  * kernel (use_tc=0), so the two implementations can be compared layer by layer. */

@@ -161,9 +161,10 @@ def main():
     torch.Tensor.numpy = lambda self, *a, **k: to_host(self.detach().cpu(), *a, **k)   # the caller's .cpu().numpy()
     torch.set_default_device(dev)
     torch.set_grad_enabled(False)
-    sp, sg, sp_name = bench.load_weights()
-    cfg = bench.make_cfg()
-    pairs = [synth.make_pair(3000 + i, bench.H, bench.W) for i in range(args.pairs + 3)]
+    c2 = bench.CONFIGS["C2"]
+    sp, sg, sp_name = bench.load_weights(c2)
+    cfg = bench.make_cfg(c2)
+    pairs = [synth.make_pair(3000 + i, c2["H"], c2["W"]) for i in range(args.pairs + 3)]
     for a, b in pairs[:3]:
         out = O.matching_forward(a, b, sp, sg, cfg)
     sync()

@@ -14,8 +14,8 @@ import bench  # noqa: E402
 from image_matching_b200 import Matching, synth, lib  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-sp, sg, _ = bench.load_weights()
-cfg = bench.make_cfg()
+sp, sg, _ = bench.load_weights(bench.CONFIGS["C2"])
+cfg = bench.make_cfg(bench.CONFIGS["C2"])
 m = Matching({"superpoint": dict(cfg["superpoint"], weights=None), "superglue": dict(cfg["superglue"], weights="")}).eval()
 m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sp.items()})
 m.superglue.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sg.items()})

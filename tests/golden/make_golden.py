@@ -141,6 +141,43 @@ def convert_real_superpoint_weights():
     return sd
 
 
+def convert_coco256_superpoint_weights():
+    """The reference's D=256 SuperPoint checkpoint (superPointNet_coco_descriptor_256.pth.tar, the one SURVEY.md 8(c)
+    names for BASELINE config 3), converted like the D=128 one."""
+    ck = torch.load(os.path.join(REF, "superpoint/models/weights/superPointNet_coco_descriptor_256.pth.tar"),
+                    map_location="cpu")
+    sd = {(k[7:] if "module" in k else k): v.numpy() for k, v in ck["model_state_dict"].items()}
+    path = os.path.join(HERE, "superpoint_coco256_weights.npz")
+    np.savez_compressed(path, **sd)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    return sd
+
+
+def main_c3():
+    """BASELINE config 3 at its stated size: one 1280x960 pair, the reference's COCO D=256 SuperPoint checkpoint,
+    2048 keypoints, kenc [32,64,128,256], 18 layers, 30 Sinkhorn iterations.  Only the boundary outputs are kept
+    (keypoints, scores, matches, matching scores, every 16th descriptor column): the full descriptors would be 4 MB."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    sp = convert_coco256_superpoint_weights()
+    sg = synth.superglue_weights(1, 256, (32, 64, 128, 256))
+    cfg = make_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=2048, iters=30)
+    m = build_reference(cfg, sp, sg)
+    a, b = synth.make_pair_batch([1], 960, 1280)
+    pred = m({"image0": torch.from_numpy(a), "image1": torch.from_numpy(b)})
+    out = {"seeds": np.asarray([1]), "H": 960, "W": 1280}
+    for k, v in pred.items():
+        if isinstance(v, (list, tuple)):
+            for i, t in enumerate(v):
+                out[f"{k}_{i}"] = t.numpy()[:, ::16] if k.startswith("descriptors") else t.numpy()
+        else:
+            out[k] = v.numpy()
+    path = os.path.join(HERE, "c3_real.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", "kpts:", int(pred["keypoints0"][0].shape[0]),
+          int(pred["keypoints1"][0].shape[0]), "valid matches:", int((pred["matches0"][0] > -1).sum()))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -174,6 +211,9 @@ def main_official():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "official":
         main_official()      # only the fixture added for SURVEY.md 8(f3); the others are unchanged
+    elif len(sys.argv) > 1 and sys.argv[1] == "c3":
+        main_c3()            # only the config-3 fixture (round 2); the others are unchanged
     else:
         main()
         main_official()
+        main_c3()

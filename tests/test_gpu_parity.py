@@ -11,7 +11,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, golden_cfg, real_superpoint_weights, kp_set, match_pairs
+import os
+
+from conftest import load_golden, golden_cfg, real_superpoint_weights, kp_set, match_pairs, GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +51,10 @@ def _case(name):
     if name == "c1_pair":
         return dict(g=load_golden(name), cfg=golden_cfg(max_kp=1024), sp=synth.superpoint_weights(0, 128),
                     sg=synth.superglue_weights(0, 128), H=480, W=640, seeds=[1, 2])
+    if name == "c3_real":
+        return dict(g=load_golden(name), cfg=golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=2048, iters=30),
+                    sp=dict(np.load(os.path.join(GOLDEN, "superpoint_coco256_weights.npz"))),
+                    sg=synth.superglue_weights(1, 256, (32, 64, 128, 256)), H=960, W=1280, seeds=[1])
     if name == "c1_real":
         return dict(g=load_golden(name), cfg=golden_cfg(max_kp=1024), sp=real_superpoint_weights(),
                     sg=synth.superglue_weights(0, 128), H=480, W=640, seeds=[1])
@@ -213,7 +219,7 @@ def test_superglue_given_reference_features(stage):
     assert np.abs(pred["matching_scores0"].cpu().numpy() - g["matching_scores0"])[both].max() < 1e-3
 
 
-@pytest.mark.parametrize("name", ["ragged_hw", "c1_real", "c1_pair", "small_stages", "d256_small"])
+@pytest.mark.parametrize("name", ["ragged_hw", "c1_real", "c1_pair", "small_stages", "d256_small", "c3_real"])
 def test_end_to_end_vs_reference(name):
     from image_matching_b200 import synth
     c = _case(name)
@@ -230,6 +236,16 @@ def test_end_to_end_vs_reference(name):
             print(f"FLIPS {name}[{i}] side{side}: {len(ref)} ref keypoints, {len(ref ^ got)} differ")
             assert ref == got, f"{len(ref ^ got)} keypoint flips"
             assert pred["descriptors" + side][i].shape == (c["cfg"]["superpoint"]["descriptor_dim"], len(got))
+            # descriptors / scores within 1e-3 (north_star), rows matched by keypoint coordinate
+            gk, rk = pred["keypoints" + side][i].cpu().numpy().astype(np.int64), g[f"keypoints{side}_{i}"].astype(np.int64)
+            pos = {tuple(k): j for j, k in enumerate(gk.tolist())}
+            idx = np.array([pos[tuple(k)] for k in rk.tolist()])
+            rd = g[f"descriptors{side}_{i}"]
+            gd = pred["descriptors" + side][i].cpu().numpy()[:, idx]
+            if rd.shape[1] != gd.shape[1]:             # c3_real keeps every 16th descriptor column
+                gd = gd[:, ::16]
+            assert np.abs(gd - rd).max() < 1e-3
+            assert np.abs(pred["scores" + side][i].cpu().numpy()[idx] - g[f"scores{side}_{i}"]).max() < 1e-6
         ref_pairs = match_pairs(g[f"keypoints0_{i}"], g[f"keypoints1_{i}"], g["matches0"][i])
         got_pairs = match_pairs(pred["keypoints0"][i].cpu().numpy(), pred["keypoints1"][i].cpu().numpy(),
                                 pred["matches0"][i].cpu().numpy())
@@ -421,3 +437,93 @@ def test_config3_shape_runs():
     o1 = m.forward_device(_t(a[1:]), _t(b[1:]))
     assert torch.equal(o1["matches0"][0], out["matches0"][1])
     assert torch.equal(o1["keypoints1"][0], out["keypoints1"][1])
+
+
+def test_config5_full_size_vs_oracle():
+    """BASELINE config 5 AT ITS STATED SIZE: SuperGlue on supplied 128-d descriptors, N = M = 4096 keypoints per image,
+    100 Sinkhorn iterations -- attention, fused layers, score matrix, wide Sinkhorn and match selection at 4096 keys,
+    end to end against the torch-CPU oracle (pinned against the reference goldens in tests/test_oracle_golden.py)."""
+    import bench
+    from image_matching_b200 import synth
+    from oracle import matching_oracle_torch as OT
+    c = bench.CONFIGS["C5"]
+    cfg = bench.make_cfg(c)
+    sg = synth.superglue_weights(c["sg_seed"], 128)
+    m = _matching(cfg, synth.superpoint_weights(0, 128), sg)
+    H, W, N = c["H"], c["W"], c["K"]
+    kp0, sc0, de0, kp1, sc1, de1 = bench.c5_features(3, 1, c)
+    data = {"image0": torch.empty(1, 1, H, W, device=DEV), "image1": torch.empty(1, 1, H, W, device=DEV),
+            "keypoints0": _t(kp0), "scores0": _t(sc0), "descriptors0": _t(de0),
+            "keypoints1": _t(kp1), "scores1": _t(sc1), "descriptors1": _t(de1)}
+    pred = m(data)
+    tt = torch.from_numpy
+    r0, r1, rs0, rs1 = OT.superglue_forward(tt(kp0[0]), tt(sc0[0]), tt(de0[0]), tt(kp1[0]), tt(sc1[0]), tt(de1[0]),
+                                            H, W, sg, cfg)
+    m0, m1 = pred["matches0"][0].cpu().numpy(), pred["matches1"][0].cpu().numpy()
+    nvalid = int((r0 > -1).sum())
+    print(f"FLIPS config5 (4096): {nvalid} oracle matches, {int((m0 != r0).sum())} matches0 differ, "
+          f"{int((m1 != r1).sum())} matches1 differ")
+    assert nvalid > 500
+    assert np.array_equal(m0, r0) and np.array_equal(m1, r1)
+    both = (m0 > -1) & (r0 > -1)
+    assert np.abs(pred["matching_scores0"][0].cpu().numpy() - rs0)[both].max() < 1e-3
+
+
+def test_match_wire_roundtrip():
+    """dist.gather_matches' single-buffer wire format: pack -> (simulated) all-gather -> unpack equals the input, for
+    even and uneven shards, strided inputs and padding pairs."""
+    from image_matching_b200 import dist as D, synth
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    m._ensure(torch.device(DEV))
+    h = m._engine.handle
+    g = torch.Generator().manual_seed(0)
+    for n_pairs, world, N in ((8, 2, 64), (7, 3, 33), (5, 8, 1024)):
+        full_m = torch.randint(-1, N, (n_pairs, N + 8), generator=g).to(DEV)
+        full_s = torch.rand((n_pairs, N + 8), generator=g).to(DEV)
+        b_wire = (n_pairs + world - 1) // world
+        wires = []
+        for r in range(world):
+            lo, hi = D.shard_range(n_pairs, r, world)
+            wires.append(D._pack(full_m[lo:hi, :N], full_s[lo:hi, :N], b_wire, h))      # strided views (ld = N + 8)
+        gm, gs = D._unpack(torch.cat(wires), world, b_wire, n_pairs, h)
+        assert gm.dtype == torch.int64 and torch.equal(gm, full_m[:, :N]) and torch.equal(gs, full_s[:, :N])
+
+
+def test_unbounded_keypoints_two_phase():
+    """max_keypoints = -1 (the script's default): SuperGlue is sized to the keypoint counts actually found, not to the
+    NMS capacity; results equal the bounded configuration with a bound above the count."""
+    from image_matching_b200 import synth
+    c = _case("small_stages")
+    a, b = synth.make_pair_batch([1], 120, 160)
+    cfg_u = golden_cfg(max_kp=-1)
+    cfg_b = golden_cfg(max_kp=4096)
+    mu, mb = _matching(cfg_u, c["sp"], c["sg"]), _matching(cfg_b, c["sp"], c["sg"])
+    ou, ob = mu.forward_device(_t(a), _t(b)), mb.forward_device(_t(a), _t(b))
+    n0, n1 = int(ou["counts"][0, 0]), int(ou["counts"][1, 0])
+    assert ou["matches0"].shape == (1, n0) and ou["matches1"].shape == (1, n1) and n0 < 4096
+    assert int(ob["counts"][0, 0]) == n0
+    # the bounded model orders by score, the unbounded one row-major: compare as coordinate pairs
+    pu = match_pairs(ou["keypoints0"][0].cpu().numpy(), ou["keypoints1"][0].cpu().numpy(), ou["matches0"][0].cpu().numpy())
+    pb = match_pairs(ob["keypoints0"][0, :n0].cpu().numpy(), ob["keypoints1"][0, :n1].cpu().numpy(),
+                     ob["matches0"][0, :n0].cpu().numpy())
+    assert len(pu) > 10 and pu == pb
+
+
+def test_weights_version_tracking():
+    """A module shared by two engines is repacked by each of them when its weights change."""
+    from image_matching_b200 import synth
+    c = _case("small_stages")
+    m = _matching(c["cfg"], c["sp"], c["sg"])
+    a, _ = synth.make_pair_batch([1], 120, 160)
+    x = _t(a)
+    k_own = m.superpoint(x)["keypoints"][0].clone()           # the module's own engine packs the first weights
+    sp2 = synth.superpoint_weights(3, 128)
+    m.superpoint.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sp2.items()})
+    k_match = m.forward_device(x, x)["keypoints0"][0]         # Matching's engine repacks ...
+    k_own2 = m.superpoint(x)["keypoints"][0]                  # ... and so must the module's own engine
+    n = k_own2.shape[0]
+    assert torch.equal(k_own2, k_match[:n])
+    assert k_own.shape != k_own2.shape or not torch.equal(k_own, k_own2)
+    with pytest.raises(ValueError, match="grayscale"):
+        m.superpoint(torch.zeros(1, 3, 32, 32, device=DEV))

@@ -139,3 +139,44 @@ def test_official_variant_oracle_matches_reference_golden():
     ref_pairs = match_pairs(g["keypoints0_0"], g["keypoints1_0"], g["matches0"][0])
     got_pairs = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
     assert len(ref_pairs) > 20 and len(ref_pairs & got_pairs) >= 0.9 * len(ref_pairs), (len(ref_pairs & got_pairs), len(ref_pairs))
+
+
+def test_torch_cpu_oracle_config3_golden():
+    """BASELINE config 3 at its stated size (1280x960, the reference's COCO D=256 SuperPoint checkpoint, 2048 keypoints):
+    the torch-CPU oracle reproduces the reference-generated golden -- identical keypoints and matches."""
+    import os
+    from conftest import GOLDEN
+    from oracle import matching_oracle_torch as OT
+    g = load_golden("c3_real")
+    cfg = golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=2048, iters=30)
+    sp = dict(np.load(os.path.join(GOLDEN, "superpoint_coco256_weights.npz")))
+    sg = synth.superglue_weights(1, 256, (32, 64, 128, 256))
+    a, b = synth.make_pair(1, 960, 1280)
+    r = OT.matching_forward(a, b, sp, sg, cfg)
+    for side in "01":
+        assert np.array_equal(r["keypoints" + side], g[f"keypoints{side}_0"])
+        assert np.abs(r["descriptors" + side][:, ::16] - g[f"descriptors{side}_0"]).max() < 1e-5
+    assert np.array_equal(r["matches0"], g["matches0"][0]) and np.array_equal(r["matches1"], g["matches1"][0])
+
+
+def test_reference_copy_reproduces_goldens_and_port():
+    """oracle/_ref (the reference's own modules, copied by oracle/make_ref.py -- the CPU baseline bench.py times)
+    reproduces the committed golden bit for bit, and the torch-CPU port agrees with it on a fresh seed."""
+    import torch
+    from oracle import make_ref, matching_oracle_torch as OT
+    if not make_ref.available() and make_ref.make(verbose=False) is None:
+        pytest.skip("no reference checkout and no oracle/_ref copy")
+    g = load_golden("real_small_stages")
+    cfg = golden_cfg(max_kp=300)
+    sp, sg = real_superpoint_weights(), synth.superglue_weights(0, 128)
+    m = make_ref.load_matching(cfg, sp, sg)
+    a, b = synth.make_pair_batch([4], 160, 224)
+    pred = m({"image0": torch.from_numpy(a), "image1": torch.from_numpy(b)})
+    assert np.array_equal(pred["keypoints0"][0].numpy(), g["keypoints0_0"])
+    assert np.array_equal(pred["matches0"].numpy(), g["matches0"])
+    assert np.array_equal(pred["descriptors1"][0].numpy(), g["descriptors1_0"])
+    a, b = synth.make_pair_batch([77], 160, 224)
+    pred = m({"image0": torch.from_numpy(a), "image1": torch.from_numpy(b)})
+    r = OT.matching_forward(a[0, 0], b[0, 0], sp, sg, cfg)
+    assert np.array_equal(pred["keypoints1"][0].numpy(), r["keypoints1"])
+    assert np.array_equal(pred["matches0"][0].numpy(), r["matches0"])
