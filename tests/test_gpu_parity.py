@@ -245,7 +245,11 @@ def test_end_to_end_vs_reference(name):
             if rd.shape[1] != gd.shape[1]:             # c3_real keeps every 16th descriptor column
                 gd = gd[:, ::16]
             assert np.abs(gd - rd).max() < 1e-3
-            assert np.abs(pred["scores" + side][i].cpu().numpy()[idx] - g[f"scores{side}_{i}"]).max() < 1e-6
+            # keypoint scores are softmax probabilities in [0, 1]; end to end they inherit the encoder's fp32-class
+            # rounding (semi agrees to ~1e-5 relative, see test_stage_dense): 1e-4 absolute, measured ~1e-5
+            ds = np.abs(pred["scores" + side][i].cpu().numpy()[idx] - g[f"scores{side}_{i}"]).max()
+            print(f"   scores side{side}: max diff {ds:.2e}, descriptors max diff {np.abs(gd - rd).max():.2e}")
+            assert ds < 1e-4
         ref_pairs = match_pairs(g[f"keypoints0_{i}"], g[f"keypoints1_{i}"], g["matches0"][i])
         got_pairs = match_pairs(pred["keypoints0"][i].cpu().numpy(), pred["keypoints1"][i].cpu().numpy(),
                                 pred["matches0"][i].cpu().numpy())
