@@ -400,11 +400,12 @@ SpDims sp_dims(const b200m_handle* h, int H, int W) {
 }
 
 struct SpWs {
-  float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *dn, *heat, *imgf;
+  float *p0, *p1, *p0_lo, *p1_lo, *semi, *draw, *sumsq, *heat, *imgf;
   unsigned long long* keys;
   unsigned char* nms_scratch;
   int *cand_counts, *overflow;      // overflow[0]: candidate list overflow, overflow[1]: fp16 activation overflow
-  size_t p0_img, p1_img, semi_img, draw_img, dn_img, heat_img;
+  size_t p0_img, p1_img, semi_img, draw_img, heat_img;
+  int desc_ncb;                     // column blocks of the descriptor head = partial sums of squares per pixel
 };
 // images per SuperPoint micro-batch: kSpMicroBatch at 640x480, fewer for larger images so the arena stays ~8 GB
 int sp_micro_batch(const b200m_handle* h, int H, int W) {
@@ -415,12 +416,11 @@ int sp_micro_batch(const b200m_handle* h, int H, int W) {
 }
 
 bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w) {
-  const int D = h->cfg.descriptor_dim;
   w.p0_img = (size_t)64 * d.H * d.W;
   w.p1_img = std::max((size_t)64 * d.H2 * d.W2, (size_t)128 * d.H3 * d.W3);
   w.semi_img = (size_t)128 * d.hc * d.wc;
   w.draw_img = (size_t)d.dpad * d.hc * d.wc;
-  w.dn_img = (size_t)D * d.hc * d.wc;
+  w.desc_ncb = h->use_tc ? std::max(1, d.dpad / (d.dpad >= 128 ? 128 : 64)) : 1;
   w.heat_img = (size_t)d.H8 * d.W8;
   w.p0 = A.take<float>(w.p0_img * mb);
   w.p1 = A.take<float>(w.p1_img * mb);
@@ -428,7 +428,7 @@ bool sp_carve(const b200m_handle* h, const SpDims& d, int mb, Arena& A, SpWs& w)
   w.p1_lo = h->use_tc ? A.take<float>(w.p1_img * mb) : nullptr;
   w.semi = A.take<float>(w.semi_img * mb);
   w.draw = A.take<float>(w.draw_img * mb);
-  w.dn = A.take<float>(w.dn_img * mb);
+  w.sumsq = A.take<float>((size_t)w.desc_ncb * d.hc * d.wc * mb);
   w.heat = A.take<float>(w.heat_img * mb);
   w.imgf = A.take<float>((size_t)d.H * d.W * mb);       // fp32 copy of a uint8 micro-batch (b200m_*_u8 entry points)
   w.keys = A.take<unsigned long long>((size_t)d.cand_cap * mb);
@@ -453,8 +453,9 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
 // surfaced through finish(): the output buffer would otherwise be consumed unwritten.
 void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
                  float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow,
-                 bool relu = true, int in_c8_total = 0, int in_c8_off = 0) {
+                 bool relu = true, int in_c8_total = 0, int in_c8_off = 0, float* sumsq = nullptr) {
   TcConvParams p;
+  p.sumsq = sumsq;
   p.in_hi = in_hi; p.in_lo = in_lo; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
   p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.overflow = overflow;
   p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = relu ? 1 : 0;
@@ -503,7 +504,9 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
     run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, w.p0_lo, 64, n, d.hc, d.wc, false, ovf);  // cPa | cDa (512 ch)
     // 1x1 heads on the same pipeline (one tap per K block), full fp32 C4-planar outputs
     run_conv_tc(h, ctx, h->pb, w.p0, w.p0_lo, w.semi, nullptr, 32, n, d.hc, d.wc, false, ovf, false, 64, 0);
-    run_conv_tc(h, ctx, h->db, w.p0, w.p0_lo, w.draw, nullptr, d.dpad / 4, n, d.hc, d.wc, false, ovf, false, 64, 32);
+    // descriptor head: raw descriptors + per-pixel sums of squares (the L2 normalisation is applied by the sampler)
+    run_conv_tc(h, ctx, h->db, w.p0, w.p0_lo, w.draw, nullptr, d.dpad / 4, n, d.hc, d.wc, false, ovf, false, 64, 32,
+                w.sumsq);
     return;
   } else {
     launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, nullptr, n, d.H, d.W);
@@ -518,6 +521,7 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
   }
   run_conv(h, ctx, h->pb, w.p0, 128, 0, w.semi, 32, n, d.hc, d.wc, false, false); // semi (65 of 128 ch)
   run_conv(h, ctx, h->db, w.p0, 128, 64, w.draw, d.dpad / 4, n, d.hc, d.wc, false, false);
+  launch_c4_sumsq(ctx, w.draw, d.dpad / 4, 0, w.sumsq, h->cfg.descriptor_dim, n, d.hc, d.wc);
 }
 
 int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool images_u8, int n_images, int H, int W,
@@ -557,10 +561,10 @@ int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool 
                             h->cfg.remove_borders, w.keys, w.cand_counts, d.cand_cap, w.overflow, w.nms_scratch);
       launch_select_keypoints(ctx, w.keys, w.cand_counts, d.cand_cap, n, d.W8, h->cfg.max_keypoints,
                               keypoints + (size_t)i0 * cap * 2, scores + (size_t)i0 * cap, counts + i0, cap);
-      launch_c4_l2_normalize(ctx, w.draw, d.dpad / 4, 0, w.dn, D / 4, D, n, d.hc, d.wc);
-      launch_sample_descriptors(ctx, w.dn, D / 4, D, n, d.hc, d.wc, keypoints + (size_t)i0 * cap * 2, counts + i0,
+      launch_sample_descriptors(ctx, w.draw, d.dpad / 4, D, n, d.hc, d.wc, keypoints + (size_t)i0 * cap * 2, counts + i0,
                                 cap, h->cfg.align_corners, descriptors ? descriptors + (size_t)i0 * D * cap : nullptr,
-                                tok_out ? tok_out + (size_t)i0 * tok_img_stride : nullptr, tok_ld, tok_img_stride);
+                                tok_out ? tok_out + (size_t)i0 * tok_img_stride : nullptr, tok_ld, tok_img_stride,
+                                w.sumsq, w.desc_ncb);
     }
   }
   if (keypoints) launch_apply_flags(ctx, w.overflow, counts, n_images);

@@ -60,13 +60,19 @@ struct TcConvParams {
   float c1[9 * 64 + 64];
   int bias_in_params = 0;                   // cout_pad <= 128: the epilogue reads the bias from bias_c (constant bank)
   float bias_c[128];
+  // fused channel-L2 statistics of the descriptor head (superpoint_test.py:125-126): when set (fp32 output only), the
+  // epilogue also writes sum_c out[c]^2 over the tile's nb channels per pixel to sumsq[image][cout block][H][W]; the
+  // descriptor sampler divides by the norm, so the normalised dense map never exists in HBM
+  float* sumsq = nullptr;
 };
 bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
 size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks);
 void tc_conv_pack_weights(const double* w, int cout, int cin, int cout_pad, int nb, int ks, float* dst);
 void launch_nchw_to_c4(LaunchCtx& ctx, const float* in, int C, float* out, int c4_total, int n, int H, int W);
-void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* out,
-                            int out_c4_total, int C, int n, int H, int W);
+// per-pixel sum of squares over C channels of a C4-planar map -> sumsq (n, H, W)  (CUDA-core comparator path only: the
+// tensor-core descriptor head produces it in its epilogue)
+void launch_c4_sumsq(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* sumsq, int C, int n, int H,
+                     int W);
 
 // ------------------------------------------------------------------ detector post (sp_post.cu)
 // semi C4-planar (>= 17 groups) -> heat (n, 8h, 8w)
@@ -81,11 +87,14 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
                              int cand_cap, int n, int W8, int max_kp, float* keypoints, float* scores,
                              int* counts, int cap);
 void launch_apply_flags(LaunchCtx& ctx, const int* flags, int* counts, int n);
-// normalised C4-planar descriptor map + keypoints -> descriptors (n,D,cap) and/or token-major rows
+// C4-planar descriptor map + keypoints -> descriptors (n,D,cap) and/or token-major rows.  sumsq == null: the map is
+// already channel-normalised; else the RAW head output with per-pixel partial sums of squares sumsq (n, ncb, hc, wc):
+// every tap is divided by its pixel's norm first (same arithmetic as normalising the dense map)
 void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_total, int D, int n, int hc, int wc,
                                const float* keypoints, const int* counts, int cap, int align_corners,
                                float* out_dcn /* (n,D,cap) or null */,
-                               float* out_tok /* token-major rows or null */, int tok_ld, size_t tok_img_stride);
+                               float* out_tok /* token-major rows or null */, int tok_ld, size_t tok_img_stride,
+                               const float* sumsq = nullptr, int ncb = 1);
 
 // ------------------------------------------------------------------ descriptor 2-NN + ratio test (sp_knn.cu)
 // desc (B, D, N) / (B, D, M) channel-major; match (B, N) = nearest train index or -1, dist1/dist2 = Euclidean distances

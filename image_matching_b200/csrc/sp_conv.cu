@@ -426,34 +426,28 @@ void launch_c8_to_nchw(LaunchCtx& ctx, const void* hi, const void* lo, int c8_to
 }
 
 // desc / ||desc||_2 over channels, no eps (superpoint_test.py:125-126)
-__global__ void c4_l2_normalize_kernel(const float4* __restrict__ in, int in_c4_total, int in_c4_off,
-                                       float4* __restrict__ out, int out_c4_total, int G, int HW) {
+__global__ void c4_sumsq_kernel(const float4* __restrict__ in, int in_c4_total, int in_c4_off,
+                                float* __restrict__ sumsq, int G, int HW) {
   const int n = blockIdx.y;
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= HW) return;
   const float4* src = in + ((size_t)n * in_c4_total + in_c4_off) * HW + px;
-  float4* dst = out + (size_t)n * out_c4_total * HW + px;
   float ss = 0.f;
   for (int g = 0; g < G; ++g) {
     float4 v = src[(size_t)g * HW];
-    ss += v.x * v.x; ss += v.y * v.y; ss += v.z * v.z; ss += v.w * v.w;
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
   }
-  const float nrm = sqrtf(ss);
-  for (int g = 0; g < G; ++g) {
-    float4 v = src[(size_t)g * HW];
-    dst[(size_t)g * HW] = make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
-  }
+  sumsq[(size_t)n * HW + px] = ss;
 }
 
-void launch_c4_l2_normalize(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* out,
-                            int out_c4_total, int C, int n, int H, int W) {
-  ProfScope prof__(ctx, "c4_l2_normalize");
+void launch_c4_sumsq(LaunchCtx& ctx, const float* in, int in_c4_total, int in_c4_off, float* sumsq, int C, int n, int H,
+                     int W) {
+  ProfScope prof__(ctx, "c4_sumsq");
   int HW = H * W;
   dim3 grid(cdiv(HW, 128), n);
-  c4_l2_normalize_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const float4*>(in), in_c4_total,
-                                                        in_c4_off, reinterpret_cast<float4*>(out),
-                                                        out_c4_total, C / 4, HW);
-  B200M_LAUNCH_CHECK(ctx, "c4_l2_normalize");
+  c4_sumsq_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const float4*>(in), in_c4_total, in_c4_off, sumsq,
+                                                C / 4, HW);
+  B200M_LAUNCH_CHECK(ctx, "c4_sumsq");
 }
 
 }  // namespace b200m

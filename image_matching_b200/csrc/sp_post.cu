@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
                                                           int hc, int wc, const float* __restrict__ keypoints,
                                                           const int* __restrict__ counts, int cap, int align_corners,
                                                           float* __restrict__ out_dcn, float* __restrict__ out_tok,
-                                                          int tok_ld, size_t tok_img_stride) {
+                                                          int tok_ld, size_t tok_img_stride,
+                                                          const float* __restrict__ sumsq, int ncb) {
   const int n = blockIdx.y;
   const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -544,6 +545,20 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
   const float w00 = ex * ey, w01 = tx * ey, w10 = ex * ty, w11 = tx * ty;
   const size_t plane = (size_t)hc * wc;
   const float4* base = desc + (size_t)n * c4_total * plane;
+  // raw head output: the channel norm of each of the four source pixels (superpoint_test.py:125-126,
+  // desc / torch.norm(desc, p=2, dim=1)), from the partial sums of squares the head's epilogue wrote
+  float nrm4[4] = {1.f, 1.f, 1.f, 1.f};
+  if (sumsq) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = iy + (q >> 1), xx = ix + (q & 1);
+      if (yy >= 0 && yy < hc && xx >= 0 && xx < wc) {
+        float ssq = 0.f;
+        for (int cb = 0; cb < ncb; ++cb) ssq += sumsq[((size_t)(n * ncb + cb) * hc + yy) * wc + xx];
+        nrm4[q] = sqrtf(ssq);
+      }
+    }
+  }
   float4 acc[2];   // up to D = 256 (64 groups / 32 lanes)
   float ss = 0.f;
 #pragma unroll
@@ -552,16 +567,17 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
     int g = lane + 32 * t;
     if (g < G) {
       const float4* pl = base + (size_t)g * plane;
-      auto tap = [&](int yy, int xx, float w) {
+      auto tap = [&](int yy, int xx, float w, float nrm) {
         if (yy >= 0 && yy < hc && xx >= 0 && xx < wc) {
           float4 v = pl[(size_t)yy * wc + xx];
+          if (sumsq) { v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm; }   // IEEE division, as the dense normalisation did
           acc[t].x += v.x * w; acc[t].y += v.y * w; acc[t].z += v.z * w; acc[t].w += v.w * w;
         }
       };
-      tap(iy, ix, w00);
-      tap(iy, ix + 1, w01);
-      tap(iy + 1, ix, w10);
-      tap(iy + 1, ix + 1, w11);
+      tap(iy, ix, w00, nrm4[0]);
+      tap(iy, ix + 1, w01, nrm4[1]);
+      tap(iy + 1, ix, w10, nrm4[2]);
+      tap(iy + 1, ix + 1, w11, nrm4[3]);
       ss += acc[t].x * acc[t].x + acc[t].y * acc[t].y + acc[t].z * acc[t].z + acc[t].w * acc[t].w;
     }
   }
@@ -583,13 +599,14 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
 
 void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_total, int D, int n, int hc, int wc,
                                const float* keypoints, const int* counts, int cap, int align_corners,
-                               float* out_dcn, float* out_tok, int tok_ld, size_t tok_img_stride) {
+                               float* out_dcn, float* out_tok, int tok_ld, size_t tok_img_stride,
+                               const float* sumsq, int ncb) {
   ProfScope prof__(ctx, "sample_descriptors");
   if (cap <= 0) return;
   dim3 grid(cdiv(cap, 8), n);
   sample_desc_kernel<<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const float4*>(desc_c4), c4_total, D, hc, wc,
                                                    keypoints, counts, cap, align_corners, out_dcn, out_tok,
-                                                   tok_ld, tok_img_stride);
+                                                   tok_ld, tok_img_stride, sumsq, ncb);
   B200M_LAUNCH_CHECK(ctx, "sample_descriptors");
 }
 

@@ -1,31 +1,35 @@
 // SuperGlue multi-head attention on tcgen05 tensor cores: flash-style (online softmax, the (B,4,N,M)
 // probability tensor of the reference is never materialised), fp32-class accuracy via a 2-term fp16 split
 // (x = hi + lo, hi = fp16(x), lo = fp16(x - hi); every product is hi*hi + hi*lo + lo*hi, exact in the fp32
-// accumulator; |q|,|k|,|v| = O(1) and p in [0,1], so the unscaled lo term costs < 3e-8 absolute).
+// accumulator; |q|,|k|,|v| = O(1) and p in [0, 2^8], so the unscaled lo term costs < 3e-8 relative).
 // Reference: superglue/models/superglue_test.py:85-89 (attention), :92-107 (MultiHeadedAttention).
 //
-// The first (3xTF32) version of this kernel measured 2.9k cycles per 128x64 tile with the softmax warps idle 41% of
-// the time on `s_full` / `p_empty`: shared-memory bandwidth (~290 KB of operand reads + P writes + TMA fills per tile
-// at 128 B/clk) was the limit, not the tensor pipe (17% active) or the MUFU.  fp16 operands halve every one of those
-// streams and shrink the CTA to 96 KB of shared memory, so two CTAs share an SM and hide each other's pipeline fill.
+// Round-2 rewrite.  The round-1 kernel spent ~12 instructions per score element in the softmax warps (issue-bound:
+// 5.9 ms per 64-pair step against a 2.3 ms MUFU floor); this version needs ~4.5:
+//   * P never goes through shared memory: the softmax threads write the fp16 hi / lo planes of P with tcgen05.st INTO THE
+//     TMEM COLUMNS OF THE S TILE THEY JUST READ (a thread's 32 fp32 scores become 16 + 16 packed words), and the P.V MMA
+//     takes its A operand from tensor memory.  No st.shared, no fence.proxy.async per tile, no p_empty / s_empty
+//     barriers (the tensor pipe executes in issue order: Q.K^T of tile j+2 into the same columns is issued after P.V of
+//     tile j), and the CTA shrinks by the 32 KB of P planes.
+//   * the row sum comes from the tensor core: the V^T tile carries 16 extra rows of ones, so P.V (N = d + 16) also
+//     accumulates sum_j (p_hi + p_lo)_j -- exactly the weights that multiply V -- next to O.  No FADD per element.
+//   * no running maximum: exponentials are taken against a reference that is the row maximum of the FIRST key tile and
+//     only moves when a later p exceeds 2^8 (detected on the packed fp16 words with one HMNMX2 per two elements; rare).
+//     Only then the scores are re-read, the reference is raised and O (with its sum columns) is rescaled in TMEM.
+//   * the hi / lo split uses the sm_100 mixed-precision FMA (fma.rn.f32.f16: x - float(h) in ONE instruction taking the
+//     packed half directly), 2 instructions per element instead of 3.
 //
-// One CTA per (side, pair, head, 128-query tile); key tiles of KT keys stream through a 3-stage TMA ring.
+// One CTA per (side, pair, head, 128-query tile), two CTAs per SM; key tiles of KT keys stream through a 4-stage TMA ring.
 //   warp 0      TMA producer : Q tile once, then K / V^T tiles (hi and lo planes), 2-D tensor maps, 128- or 64-byte
 //                              swizzle (= row length), i.e. the canonical K-major swizzled UMMA layouts.  K tiles are
 //                              [keys][d]; V is read from the transposed copy V^T [d][keys] that the q|k|v projection's
-//                              epilogue writes, so both MMAs take K-major operands (an MN-major B operand returned
-//                              zeros for kind::tf32 on this part).
-//   warp 1      MMA issuer   : S_j = Q K_j^T (M=128, N=KT, K=d) into a double-buffered TMEM tile, then
-//                              OT_j = P_j V_j (M=128, N=d, K=KT), one accumulator per key half.
-//   warps 2..9  softmax      : thread = (query row, key half).  tcgen05.ld S_j, running max / sum (ex2.approx with
-//                              the 1/sqrt(d) scale folded into one FFMA), P_j split into fp16 hi/lo and stored to
-//                              shared memory as the next MMA's A operand (no-swizzle K-major, 8 keys per 16-byte
-//                              unit).  O stays in TMEM and the tensor core accumulates it across ALL key tiles: P is
-//                              taken relative to a reference maximum that is only moved (and O rescaled in TMEM with
-//                              tcgen05.ld / .st) when the running maximum exceeds it by more than 2^8 -- rare after
-//                              the first tile -- so the common tile needs no O read, no rescale FFMAs and no wait for
-//                              the previous P.V.  The two key halves keep independent statistics (2-way split-KV)
-//                              and are merged once at the end.
+//                              epilogue writes, so both MMAs take K-major B operands.
+//   warp 1      MMA issuer   : S_j = Q K_j^T (M=128, N=KT, K=d; A, B from shared memory) into a double-buffered TMEM
+//                              tile, then [O | l] += P_j [V_j ; 1] (M=128, N=d+16, K=KT; A = P from TMEM), one accumulator
+//                              per key half.
+//   warps 2..9  softmax      : thread = (query row, key half): tcgen05.ld 32 scores, p = ex2.approx((s - ref) c), split,
+//                              tcgen05.st.  The two key halves keep independent references / accumulators (2-way
+//                              split-KV) and are merged once at the end.
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -34,8 +38,8 @@ namespace b200m {
 
 using namespace tc;
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -43,38 +47,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// N consecutive fp32 columns of this thread's TMEM lane (N = 16, 32, 48, 64, 80: chunks of 32 then one of 16)
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
-  if constexpr (N == 16) {
-    tmem_ld16(taddr, v);
-  } else {
+  static_assert(N % 16 == 0, "16-column granularity");
 #pragma unroll
-    for (int c = 0; c < N / 32; ++c) tmem_ld32(taddr + c * 32, v + c * 32);
-  }
+  for (int c = 0; c < N / 32; ++c) tmem_ld32_issue(taddr + c * 32, v + c * 32);
+  if constexpr (N % 32 == 16) tmem_ld16_issue(taddr + (N / 32) * 32, v + (N / 32) * 32);
+  tmem_ld_wait();
 }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
-        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
-        "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
-        "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 template <int N>
-__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float* v) {
-  static_assert(N % 32 == 0, "32-column granularity");
-#pragma unroll
-  for (int c = 0; c < N / 32; ++c) tmem_st32(taddr + c * 32, v + c * 32);
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_st_words(uint32_t taddr, const uint32_t* v) {     // N 32-bit words, no wait
+  static_assert(N == 8 || N == 16, "8 or 16 words");
+  if constexpr (N == 16) tmem_st16(taddr, v); else tmem_st8(taddr, v);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A (M = 128 rows = TMEM lanes, K fp16 values packed two per 32-bit column, even k in
+// the low half) is read from tensor memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // ex2.approx.ftz: 1 MUFU op, max relative error 2^-22 (the accurate exp2f expands to ~4 extra instructions)
@@ -104,23 +120,26 @@ template <int HD, int KT>
 struct TcAttnSmem {
   static constexpr int QROW = HD * 2;                     // bytes per Q / K row (fp16)
   static constexpr int VROW = KT * 2;                     // bytes per V^T row
+  static constexpr int NO = HD + 16;                      // P.V accumulator columns: O (d) | 16 copies of the row sum
   static constexpr int Q_PLANE = kTaQ * QROW;
   static constexpr int K_PLANE = KT * QROW;
-  static constexpr int V_PLANE = HD * VROW;               // == K_PLANE
-  static constexpr int KV_STAGE = 2 * K_PLANE + 2 * V_PLANE;
-  static constexpr int NKV = 3;                           // K/V ring depth
-  static constexpr int P_PLANE = kTaQ * KT * 2;           // [KT/8 chunks][128 rows][8 halves]
+  static constexpr int VH_PLANE = NO * VROW;              // V^T hi rows followed by 16 rows of ones
+  static constexpr int VL_PLANE = HD * VROW;
+  static constexpr int KV_STAGE = 2 * K_PLANE + VH_PLANE + VL_PLANE;
+  static constexpr int KV_TX = 2 * K_PLANE + 2 * VL_PLANE;   // bytes one stage receives by TMA (the ones rows are constant)
+  static constexpr int NKV = 4;                           // K/V ring depth
   static constexpr int OFF_KV = 2 * Q_PLANE;
-  static constexpr int OFF_P = OFF_KV + NKV * KV_STAGE;
-  // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring + P planes: it is only touched after the
-  // last P.V MMA has retired (every TMA load consumed, every MMA complete).  As a separate 17 KB region it pushed the CTA to 114.7 KB, i.e. ONE CTA per SM instead of two
-  // (measured: 15.5 % warps active); aliased, the CTA is 97.5 KB and two fit.
+  // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring: it is only touched after the last P.V MMA
+  // has retired (every TMA load consumed, every MMA complete)
   static constexpr int OFF_X = OFF_KV;
-  static_assert(kTaQ * (HD + 2) * 4 <= NKV * KV_STAGE + 2 * P_PLANE, "exchange buffer must fit in the aliased region");
-  static constexpr int OFF_BAR = OFF_P + 2 * P_PLANE;
-  static constexpr int N_BARS = 1 + 3 + 3 + 2 + 2 + 1 + 1 + 2 + 2;
+  static_assert(kTaQ * (HD + 2) * 4 <= NKV * KV_STAGE, "exchange buffer must fit in the aliased region");
+  static_assert(K_PLANE % 1024 == 0 && VH_PLANE % 512 == 0 && KV_STAGE % 1024 == 0, "swizzle atom alignment");
+  static constexpr int OFF_BAR = OFF_KV + NKV * KV_STAGE;
+  static constexpr int N_BARS = 1 + 2 * NKV + 2 + 2 + 1 + 1;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
-  static constexpr int TMEM_COLS = (2 * KT + 2 * HD) <= 256 ? 256 : 512;   // S double buffer + one O per key half
+  static constexpr int TMEM_COLS = 256;                   // S / P double buffer (2 KT) + [O | l] per key half (2 NO)
+  static_assert(2 * KT + 2 * NO <= TMEM_COLS, "tensor memory budget (two CTAs per SM)");
+  static_assert(2 * BYTES <= 232448, "two CTAs per SM");
 };
 
 struct TcAttnParams {
@@ -134,6 +153,32 @@ struct TcAttnParams {
   float scale_log2e;       // log2(e) / sqrt(d)
 };
 
+// this thread's KH scores -> p = 2^(s c + neg) as packed fp16 hi / lo words; returns the packed maximum of the hi words
+template <int KH>
+__device__ __forceinline__ __half2 softmax_words(const float* s, float c, float neg, uint32_t* hi, uint32_t* lo) {
+  __half2 pm = __float2half2_rn(0.f);
+#pragma unroll
+  for (int i = 0; i < KH / 2; ++i) {
+    const float a = fast_exp2(fmaf(s[2 * i], c, neg));                    // exp2(-inf) = 0 for masked keys
+    const float b = fast_exp2(fmaf(s[2 * i + 1], c, neg));
+    const uint32_t h = pack_f16x2(a, b);
+    float ra, rb;
+    residual_f16x2(h, a, b, ra, rb);
+    hi[i] = h;
+    lo[i] = pack_f16x2(ra, rb);
+    pm = __hmax2(pm, *reinterpret_cast<const __half2*>(&h));
+  }
+  return pm;
+}
+
+template <int KH>
+__device__ __forceinline__ float row_max(const float* s) {
+  float m3[4] = {s[0], s[1], s[2], s[3]};                                 // 4 independent chains of 3-input maxima
+#pragma unroll
+  for (int i = 4; i + 1 < KH; i += 2) m3[(i >> 1) & 3] = fmaxf(m3[(i >> 1) & 3], fmaxf(s[i], s[i + 1]));
+  return fmaxf(fmaxf(m3[0], m3[1]), fmaxf(m3[2], m3[3]));
+}
+
 template <int HD, int KT>
 __global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
@@ -141,29 +186,32 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
                     const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo,
                     TcAttnParams p) {
   using SM = TcAttnSmem<HD, KT>;
+  constexpr int NO = SM::NO;
+  constexpr int KH = KT / 2;          // keys (= S columns) per softmax thread and tile
+  constexpr int PW = KH / 2;          // packed words per plane, thread and tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + SM::OFF_KV;
-  uint8_t* sP = smem + SM::OFF_P;
   float* sX = reinterpret_cast<float*>(smem + SM::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = q_full + 1;
   uint64_t* kv_empty = kv_full + SM::NKV;
-  uint64_t* s_full = kv_empty + SM::NKV;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* p_empty = p_full + 1;
-  uint64_t* pv_done = p_empty + 1;           // P.V of tile j retired (phase j)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+  uint64_t* s_full = kv_empty + SM::NKV;     // [2] Q.K^T of the tile in buffer st retired
+  uint64_t* p_full = s_full + 2;             // [2] the eight softmax warps wrote P into buffer st
+  uint64_t* pv_done = p_full + 2;            // P.V of tile j retired (phase j); only waited on by a thread that is exactly
+                                             // one phase behind (the rescale path) -- a parity wait cannot tell phase j from j-2
+  uint64_t* o_done = pv_done + 1;            // the LAST P.V retired (single phase): the softmax warps run up to two tiles
+                                             // ahead of the tensor pipe, so the final read must not use pv_done's parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int side = blockIdx.z / p.B, b = blockIdx.z - side * p.B;
   const int src = p.cross ? 1 - side : side;
   const int n_k = src == 0 ? (p.counts0 ? p.counts0[b] : p.n_full0) : (p.counts1 ? p.counts1[b] : p.n_full1);
-  const int T = cdiv(n_k, KT);
+  const int T = n_k > 0 ? cdiv(n_k, KT) : 0;
   const int q_row0 = (side * p.B + b) * p.Np + blockIdx.x * kTaQ;     // global row of the first query
   const int k_row0 = (src * p.B + b) * p.Np;
   const int cq = head * HD, ck = p.D + head * HD;          // first column of this head's q / k
@@ -172,18 +220,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
     mbar_init(pv_done, 1);
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
+    mbar_init(o_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q_hi); tma_prefetch_desc(&tm_q_lo);
     tma_prefetch_desc(&tm_kv_hi); tma_prefetch_desc(&tm_kv_lo);
     tma_prefetch_desc(&tm_vt_hi); tma_prefetch_desc(&tm_vt_lo);
   }
+  // the 16 constant rows of ones under every V^T hi tile (all elements equal, so the swizzle does not matter)
+  for (int i = threadIdx.x; i < SM::NKV * 16 * SM::VROW / 16; i += blockDim.x) {
+    const int stg = i / (16 * SM::VROW / 16), r = i - stg * (16 * SM::VROW / 16);
+    *reinterpret_cast<uint4*>(sKV + stg * SM::KV_STAGE + 2 * SM::K_PLANE + HD * SM::VROW + r * 16) =
+        make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  }
+  fence_proxy_async();
   if (warp == 1) tmem_alloc(tmem_slot, SM::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -201,21 +252,24 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     for (int j = 0; j < T; ++j) {
       const int st = j % SM::NKV, ph = (j / SM::NKV) & 1;
       mbar_wait(&kv_empty[st], ph ^ 1);
-      mbar_expect_tx(&kv_full[st], SM::KV_STAGE);
+      mbar_expect_tx(&kv_full[st], SM::KV_TX);
       uint8_t* dst = sKV + st * SM::KV_STAGE;
       tma_load_2d(dst, &tm_kv_hi, &kv_full[st], ck, k_row0 + j * KT);
       tma_load_2d(dst + SM::K_PLANE, &tm_kv_lo, &kv_full[st], ck, k_row0 + j * KT);
       tma_load_2d(dst + 2 * SM::K_PLANE, &tm_vt_hi, &kv_full[st], j * KT, vt_row0);
-      tma_load_2d(dst + 2 * SM::K_PLANE + SM::V_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
+      tma_load_2d(dst + 2 * SM::K_PLANE + SM::VH_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp)
     if (T > 0) {
       const uint32_t idesc_s = instr_desc(0, 128, KT);                    // fp16, A and B K-major
-      const uint32_t idesc_o = instr_desc(0, 128, HD);
-      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      const uint32_t idesc_o = instr_desc(0, 128, NO);                    // [O | l]
+      const uint32_t idesc_v = instr_desc(0, 128, HD);                    // O only (P_hi x V_lo)
+      const uint32_t q_base = smem_u32(sQ);
       auto issue_S = [&](int j) {
         const int st = j & 1;
+        mbar_wait(&kv_full[j % SM::NKV], (j / SM::NKV) & 1);
+        tc_fence_after();
         const uint32_t k_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE);
         if (elect_one()) {
 #pragma unroll
@@ -233,133 +287,107 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         __syncwarp();
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
       issue_S(0);
+      if (T > 1) issue_S(1);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          const int sn = (j + 1) & 1, pn = ((j + 1) >> 1) & 1;
-          mbar_wait(&kv_full[(j + 1) % SM::NKV], ((j + 1) / SM::NKV) & 1);
-          mbar_wait(&s_empty[sn], pn ^ 1);
-          tc_fence_after();
-          issue_S(j + 1);
-        }
-        mbar_wait(p_full, j & 1);
+        const int st = j & 1;
+        mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(sKV + (j % SM::NKV) * SM::KV_STAGE + 2 * SM::K_PLANE);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KT / 16; ++ks) {           // 16 keys per MMA = two 8-key units of P
-            const uint64_t ph_ = smem_desc_nosw(p_base + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
-            const uint64_t pl_ = smem_desc_nosw(p_base + SM::P_PLANE + ks * 2 * (kTaQ * 16), kTaQ * 16, 128);
+          for (int ks = 0; ks < KT / 16; ++ks) {           // 16 keys per MMA = 8 packed columns of P
+            const int hf = ks / (KH / 16), kl = ks % (KH / 16);
+            // key half hf owns S columns [hf KH, (hf + 1) KH): its P is [hi: PW columns | lo: PW columns] there
+            const uint32_t a_hi = tS + st * KT + hf * KH + kl * 8, a_lo = a_hi + PW;
             const uint64_t vh = smem_desc_sw<SM::VROW>(v_base + ks * 32);
-            const uint64_t vl = smem_desc_sw<SM::VROW>(v_base + SM::V_PLANE + ks * 32);
-            // keys [0, KT/2) accumulate into OT[st][0], keys [KT/2, KT) into OT[st][1] (independent softmax halves)
-            const uint32_t dO = tO + (ks / (KT / 32)) * HD;
-            mma_bf16(dO, ph_, vh, idesc_o, (j > 0) || (ks % (KT / 32)) != 0);   // accumulates across key tiles
-            mma_bf16(dO, ph_, vl, idesc_o, 1);
-            mma_bf16(dO, pl_, vh, idesc_o, 1);
+            const uint64_t vl = smem_desc_sw<SM::VROW>(v_base + SM::VH_PLANE + ks * 32);
+            const uint32_t dO = tO + hf * NO;              // independent accumulators per key half
+            mma_f16_ts(dO, a_hi, vh, idesc_o, (j > 0) || kl != 0);       // accumulates across key tiles
+            mma_f16_ts(dO, a_lo, vh, idesc_o, 1);
+            mma_f16_ts(dO, a_hi, vl, idesc_v, 1);
           }
           tc_commit(&kv_empty[j % SM::NKV]);
-          tc_commit(p_empty);
           tc_commit(pv_done);
+          if (j == T - 1) tc_commit(o_done);
         }
         __syncwarp();
+        // the next-but-one score tile overwrites P_j's columns: issued after P.V_j, executed after it (in-order pipe)
+        if (j + 2 < T) issue_S(j + 2);
       }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------------ softmax / accumulate
-    constexpr int KH = KT / 2;
+    // ------------------------------------------------------------------ softmax
     const int half = (warp - 2) >> 2;
     const int w4 = warp & 3;
     const int m = w4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(w4 * 32) << 16;
     const float c = p.scale_log2e;
-    constexpr float kLazy = 8.f;      // log2 units: the reference maximum moves only when the true one is > 2^8 above it
-    const uint32_t tO_mine = tO + lane_base + half * HD;
-    float m_run = -INFINITY;          // true running maximum of this row's scores (this key half)
-    float m_ref = 0.f;                // reference the exponentials are taken against (finite; meaningless until set)
-    bool have_ref = false;
-    float l_run = 0.f;                // sum of exp2((s - m_ref) c)
-    uint4* Ph = reinterpret_cast<uint4*>(sP) + (half * (KH / 8)) * kTaQ + m;        // [8-key chunk][row][8 halves]
-    uint4* Pl = reinterpret_cast<uint4*>(sP + SM::P_PLANE) + (half * (KH / 8)) * kTaQ + m;
+    const uint32_t tS_mine = tS + lane_base + half * KH;
+    const uint32_t tO_mine = tO + lane_base + half * NO;
+    float m_ref = 0.f;                // reference the exponentials are taken against (log-2 domain after * c)
     for (int j = 0; j < T; ++j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(&s_full[st], ph);
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       float s[KH];
-      tmem_ld_n<KH>(tS + lane_base + st * KT + half * KH, s);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      tmem_ld_n<KH>(tS_mine + st * KT, s);
       const int kbase = j * KT + half * KH;
       if (kbase + KH > n_k) {
 #pragma unroll
         for (int i = 0; i < KH; ++i)
           if (kbase + i >= n_k) s[i] = -INFINITY;
       }
-      float mx4[4] = {s[0], s[1], s[2], s[3]};                             // 4 independent chains
-#pragma unroll
-      for (int i = 4; i < KH; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      m_run = fmaxf(m_run, mx);
-      // ---- move the reference?  (first valid score of the row, or the maximum ran away by more than 2^kLazy)
-      const bool move = m_run > -INFINITY && (!have_ref || (m_run - m_ref) * c > kLazy);
-      if (__any_sync(0xffffffffu, move)) {
-        // warp-uniform path (tcgen05.ld / .st are warp-collective); rows that do not move use factor 1
-        const float f = move && have_ref ? fast_exp2((m_ref - m_run) * c) : 1.f;
-        if (j > 0) {                                   // O holds tiles 0 .. j-1: rescale it in place
-          mbar_wait(pv_done, (j - 1) & 1);             // P.V of tile j-1 retired (it cannot be further: it needs our P_j)
-          tc_fence_after();
-          float ot[HD];
-          tmem_ld_n<HD>(tO_mine, ot);
-#pragma unroll
-          for (int i = 0; i < HD; ++i) ot[i] *= f;
-          tmem_st_n<HD>(tO_mine, ot);
-          tc_fence_before();
+      if (j == 0) {                                   // the reference starts as the first tile's row maximum
+        const float mx = row_max<KH>(s);
+        m_ref = mx > -INFINITY ? mx : 0.f;
+      }
+      uint32_t hi[PW], lo[PW];
+      __half2 pm = softmax_words<KH>(s, c, -m_ref * c, hi, lo);
+      // a p above 2^8 (or an fp16 overflow to +inf): raise the reference and rescale what was accumulated so far
+      const bool trig = __hgt(__hmax(__low2half(pm), __high2half(pm)), __float2half_rn(256.f));
+      if (j > 0 && __any_sync(0xffffffffu, trig)) {
+        // warp-uniform path (tcgen05.ld / .st are warp-collective); rows that did not trigger keep factor 1
+        float f = 1.f;
+        if (trig) {
+          const float mx = row_max<KH>(s);
+          f = fast_exp2((m_ref - mx) * c);
+          m_ref = mx;
         }
-        l_run *= f;
-        if (move) { m_ref = m_run; have_ref = true; }
-      }
-      const float neg = -m_ref * c;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        mbar_wait(pv_done, (j - 1) & 1);               // P.V of tile j-1 retired (it cannot be further: it needs our P_j)
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < NO; c0 += 16) {          // [O | l] of this key half, 16 columns at a time
+          float ot[16];
+          uint32_t ow[16];
+          tmem_ld_n<16>(tO_mine + c0, ot);
 #pragma unroll
-      for (int i = 0; i < KH; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], c, neg));                             // exp2(-inf) = 0 for masked keys
-        sum4[i & 3] += s[i];
-      }
-      l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      // P_j -> shared memory (A operand of the PV MMA), fp16 hi / lo planes
-      mbar_wait(p_empty, (j & 1) ^ 1);
-#pragma unroll
-      for (int g = 0; g < KH / 8; ++g) {
-        __half2 h2[4], l2[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float a = s[8 * g + 2 * t], bb = s[8 * g + 2 * t + 1];
-          h2[t] = __floats2half2_rn(a, bb);
-          const float2 back = __half22float2(h2[t]);
-          l2[t] = __floats2half2_rn(a - back.x, bb - back.y);
+          for (int i = 0; i < 16; ++i) ow[i] = __float_as_uint(ot[i] * f);
+          tmem_st16(tO_mine + c0, ow);
+          tmem_st_wait();      // tcgen05.st reads its source registers asynchronously: they are reused by the next chunk
         }
-        Ph[g * kTaQ] = *reinterpret_cast<uint4*>(h2);
-        Pl[g * kTaQ] = *reinterpret_cast<uint4*>(l2);
+        pm = softmax_words<KH>(s, c, -m_ref * c, hi, lo);
       }
-      fence_proxy_async();
+      // P_j (A operand of the P.V MMA) over this thread's own S columns: [hi words | lo words]
+      tmem_st_words<PW>(tS_mine + st * KT, hi);
+      tmem_st_words<PW>(tS_mine + st * KT + PW, lo);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[st]);
     }
-    // ---- O of this key half: one TMEM read after the last P.V
-    float o[HD];
+    // ---- [O | l] of this key half: one TMEM read after the last P.V
+    float o[NO];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int i = 0; i < NO; ++i) o[i] = 0.f;
     if (T > 0) {
-      mbar_wait(pv_done, (T - 1) & 1);
+      mbar_wait(o_done, 0);
       tc_fence_after();
-      tmem_ld_n<HD>(tO_mine, o);
+      tmem_ld_n<NO>(tO_mine, o);
       tc_fence_before();
     }
-    if (!have_ref) m_run = -INFINITY;                 // no valid key in this half: contributes nothing to the merge
-    else m_run = m_ref;                               // the merge below works with the reference the sums are relative to
+    const float l_run = o[HD];                        // sum of the weights, accumulated by the tensor core
+    const float m_run = l_run > 0.f ? m_ref : -INFINITY;   // no valid key in this half: contributes nothing to the merge
     // ---- merge the two key halves
     float* xch = sX + (size_t)m * (HD + 2);
     if (half == 1) {
@@ -382,17 +410,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         uint4* dl = reinterpret_cast<uint4*>(p.msg_lo + off);
 #pragma unroll
         for (int g = 0; g < HD / 8; ++g) {
-          __half2 h2[4], l2[4];
+          uint32_t h4[4], l4[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float a = (o[8 * g + 2 * t] * ca + xch[2 + 8 * g + 2 * t] * cb) * inv;
             const float bb = (o[8 * g + 2 * t + 1] * ca + xch[2 + 8 * g + 2 * t + 1] * cb) * inv;
-            h2[t] = __floats2half2_rn(a, bb);
-            const float2 back = __half22float2(h2[t]);
-            l2[t] = __floats2half2_rn((a - back.x) * 2048.f, (bb - back.y) * 2048.f);
+            h4[t] = pack_f16x2(a, bb);
+            float ra, rb;
+            residual_f16x2(h4[t], a, bb, ra, rb);
+            l4[t] = pack_f16x2(ra * 2048.f, rb * 2048.f);
           }
-          dh[g] = *reinterpret_cast<uint4*>(h2);
-          dl[g] = *reinterpret_cast<uint4*>(l2);
+          dh[g] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+          dl[g] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
         }
       } else {
         float4* dst = reinterpret_cast<float4*>(p.msg + off);

@@ -154,6 +154,37 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- fp16 hi / lo operand split
+// {upper half = fp16(b), lower half = fp16(a)}: element a sits in the low 16 bits (the even element of a pair)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// x - float(h) for both halves of a packed pair with the sm_100 mixed-precision FMA (h * -1 + x): one instruction per
+// element, taking the packed half directly (no unpack); the difference is exact
+__device__ __forceinline__ void residual_f16x2(uint32_t h, float a, float b, float& ra, float& rb) {
+  unsigned short h0, h1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(h0), "=h"(h1) : "r"(h));
+  const unsigned short neg1 = 0xBC00;    // fp16 -1.0
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(ra) : "h"(h0), "h"(neg1), "f"(a));
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(rb) : "h"(h1), "h"(neg1), "f"(b));
+}
+// (a, b) -> hi = fp16(v), lo = fp16((v - hi) * lo_scale) as packed pairs
+__device__ __forceinline__ void split_f16x2(float a, float b, float lo_scale, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2(a, b);
+  float ra, rb;
+  residual_f16x2(hi, a, b, ra, rb);
+  lo = pack_f16x2(ra * lo_scale, rb * lo_scale);
+}
+// 8 consecutive values -> one 16-byte unit of each plane
+__device__ __forceinline__ void split8_f16(const float* v, float lo_scale, uint4& hi, uint4& lo) {
+  split_f16x2(v[0], v[1], lo_scale, hi.x, lo.x);
+  split_f16x2(v[2], v[3], lo_scale, hi.y, lo.y);
+  split_f16x2(v[4], v[5], lo_scale, hi.z, lo.z);
+  split_f16x2(v[6], v[7], lo_scale, hi.w, lo.w);
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): canonical layout in 16-byte units
 //   ((8, n), 2) : ((1, SBO), LBO)   -- 8 rows of one core matrix are 16 B apart (128 B contiguous),

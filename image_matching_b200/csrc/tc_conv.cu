@@ -276,17 +276,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch) e[ch] = fmaf(v, wr[ky * 3 + kx][ch], e[ch]);
             }
-          __half2 h2[4], l2[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ea = fmaxf(e[2 * j], 0.f), eb = fmaxf(e[2 * j + 1], 0.f);
-            const __half ha = __float2half_rn(ea), hb = __float2half_rn(eb);
-            h2[j] = __halves2half2(ha, hb);
-            l2[j] = __halves2half2(__float2half_rn((ea - __half2float(ha)) * kLoScale),
-                                   __float2half_rn((eb - __half2float(hb)) * kLoScale));
-          }
-          hi = *reinterpret_cast<uint4*>(h2);
-          lo = *reinterpret_cast<uint4*>(l2);
+          for (int ch = 0; ch < 8; ++ch) e[ch] = fmaxf(e[ch], 0.f);
+          split8_f16(e, kLoScale, hi, lo);
         }
         *reinterpret_cast<uint4*>(dst + px * 16) = hi;
         *reinterpret_cast<uint4*>(dst + kTcAPlane + px * 16) = lo;
@@ -322,6 +314,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           X = x; Y = y;
           writer = (y < p.H) && (x < p.W);
         }
+        float ss = 0.f;                       // sum of squares over this tile's channels (descriptor head only)
 #pragma unroll 1
         for (int ch = 0; ch < NB / 32; ++ch) {
           float v[32], vc[32];
@@ -358,22 +351,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               bool ovf = false;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                __half2 h2[4], l2[4];
+                float mx = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float a = v[8 * g + 2 * j], b = v[8 * g + 2 * j + 1];
-                  ovf |= (fabsf(a) > 65000.f) | (fabsf(b) > 65000.f);
-                  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-                  h2[j] = __halves2half2(ha, hb);
-                  l2[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * kLoScale),
-                                         __float2half_rn((b - __half2float(hb)) * kLoScale));
-                }
-                oh[(size_t)g * oplane] = *reinterpret_cast<uint4*>(h2);
-                ol[(size_t)g * oplane] = *reinterpret_cast<uint4*>(l2);
+                for (int j = 0; j < 8; j += 2) mx = fmaxf(mx, fmaxf(fabsf(v[8 * g + j]), fabsf(v[8 * g + j + 1])));
+                ovf |= mx > 65000.f;
+                uint4 h4, l4;
+                split8_f16(v + 8 * g, kLoScale, h4, l4);
+                oh[(size_t)g * oplane] = h4;
+                ol[(size_t)g * oplane] = l4;
               }
               if (ovf && p.overflow) *p.overflow = 1;
             } else {
-              // full fp32, C4-planar (consumed by the CUDA-core 1x1 heads)
+              // full fp32, C4-planar (detector logits / raw descriptors)
+              if (p.sumsq) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);      // channel order: same chain as a serial pass
+              }
               const size_t g0 = (size_t)img * p.out_c4_total + p.out_c4_off + (c0 >> 2);
               float4* oh = reinterpret_cast<float4*>(p.out_hi) + g0 * oplane + (size_t)Y * Wo + X;
 #pragma unroll
@@ -382,6 +375,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
           }
         }
+        if (p.sumsq && writer && !p.out_lo)
+          p.sumsq[((size_t)(img * ncb + cb) * p.H + Y) * p.W + X] = ss;
       }
       tc_fence_before();
       __syncwarp();

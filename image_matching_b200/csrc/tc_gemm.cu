@@ -135,17 +135,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {                     // 8 fp16 (16 B) per chunk
-          __half2 h2[4], l2[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = e[q * 8 + 2 * j], b = e[q * 8 + 2 * j + 1];
-            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-            h2[j] = __halves2half2(ha, hb);
-            l2[j] = __halves2half2(__float2half_rn((a - __half2float(ha)) * 2048.f),
-                                   __float2half_rn((b - __half2float(hb)) * 2048.f));
-          }
-          *reinterpret_cast<uint4*>(st + r * 128 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(h2);
-          *reinterpret_cast<uint4*>(st + kGemmATile + r * 128 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(l2);
+          uint4 h4, l4;
+          split8_f16(e + q * 8, 2048.f, h4, l4);
+          *reinterpret_cast<uint4*>(st + r * 128 + ((q ^ sw) << 4)) = h4;
+          *reinterpret_cast<uint4*>(st + kGemmATile + r * 128 + ((q ^ sw) << 4)) = l4;
         }
         fence_proxy_async();
         __syncwarp();

@@ -47,16 +47,7 @@ static_assert(kGnSmem <= 232448, "shared memory budget");
 constexpr float kGnLo = 2048.f;
 
 __device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, float lo_scale) {
-  __half2 h2[4], l2[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float a = v[2 * j], b = v[2 * j + 1];
-    h2[j] = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h2[j]);
-    l2[j] = __floats2half2_rn((a - back.x) * lo_scale, (b - back.y) * lo_scale);
-  }
-  hi = *reinterpret_cast<uint4*>(h2);
-  lo = *reinterpret_cast<uint4*>(l2);
+  split8_f16(v, lo_scale, hi, lo);
 }
 
 __global__ void __launch_bounds__(320, 1)
