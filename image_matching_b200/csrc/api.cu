@@ -100,6 +100,20 @@ struct b200m_handle {
   bool use_fused_gnn = true;     // fused merge/mlp/residual/q|k|v layer kernel (B200M_GNN_IMPL=unfused: four GEMM launches)
   int num_sms = 148;
   int sp_micro_batch = 0;        // > 0: B200M_SP_MICROBATCH override of the images per SuperPoint micro-batch
+  // CUDA-graph replay of whole forward calls (see with_graph below)
+  struct GraphEntry {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    unsigned long long last_use = 0;
+    bool dead = false;           // capture failed once: always run eagerly
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;        // B200M_GRAPHS=0 disables
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+  unsigned long long graph_clock = 0;
+  long long graph_replays = 0;
 };
 
 namespace {
@@ -132,6 +146,95 @@ int finish(b200m_handle* h, LaunchCtx& ctx) {
                 cudaGetErrorString(ctx.err));
   return B200M_OK;
 }
+
+// ------------------------------------------------------------------ CUDA-graph replay of a forward call
+// A forward call is ~60-120 kernel launches whose arguments are a pure function of the entry point's arguments (shapes,
+// device pointers, workspace) and of the handle's packed weights.  The second time an entry point sees the SAME
+// arguments, its launch sequence is captured into a CUDA graph (on a handle-owned stream: torch's default stream is the
+// legacy stream, which cannot be captured) and from then on replayed with one cudaGraphLaunch: no per-launch CPU work
+// (tensor-map encoding, argument marshalling) and back-to-back kernel scheduling on the device.  The reference's caller
+// is a batch_size = 1 loop (superpoint_glue_test.py:65-78), where the ~100 launches of one pair are launch-bound.
+// Semantics of include/b200m.h are unchanged: work is ordered after everything already enqueued on the caller's stream
+// and before everything enqueued later (event hand-over), outputs land in the caller's buffers.  Eager fallback: first
+// sight of a key, per-launch profiling, a caller stream that is itself being captured, B200M_GRAPHS=0, capture failure.
+void drop_graphs(b200m_handle* h) {
+  for (auto& e : h->graphs)
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
+}
+
+template <typename Body>
+int with_graph(b200m_handle* h, void* user_stream, std::vector<uint64_t> key, Body body) {
+  cudaStream_t us = (cudaStream_t)user_stream;
+  if (!h->use_graphs || h->prof.enabled) return body(user_stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(us, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body(user_stream);
+  }
+  b200m_handle::GraphEntry* e = nullptr;
+  for (auto& g : h->graphs)
+    if (g.key == key) { e = &g; break; }
+  if (!e) {                                 // first sight: remember the key, run eagerly
+    if (h->graphs.size() >= 8) {            // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+      if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+      h->graphs.erase(h->graphs.begin() + lru);
+    }
+    b200m_handle::GraphEntry ne;
+    ne.key = std::move(key);
+    ne.last_use = ++h->graph_clock;
+    h->graphs.push_back(std::move(ne));
+    return body(user_stream);
+  }
+  e->last_use = ++h->graph_clock;
+  if (e->dead) return body(user_stream);
+  if (!h->gstream) {
+    if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      h->use_graphs = false;
+      return body(user_stream);
+    }
+  }
+  if (!e->exec) {                           // second sight: capture
+    const long long l0 = h->launches;
+    if (cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      e->dead = true;
+      return body(user_stream);
+    }
+    const int rc = body((void*)h->gstream);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(h->gstream, &g);
+    if (rc != B200M_OK || ee != cudaSuccess || !g || cudaGraphInstantiate(&e->exec, g, 0) != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      e->exec = nullptr;
+      e->dead = true;
+      h->launches = l0;
+      return rc != B200M_OK ? rc : body(user_stream);
+    }
+    cudaGraphDestroy(g);
+    e->launches = h->launches - l0;
+    h->launches = l0;
+  }
+  cudaError_t err = cudaEventRecord(h->g_in, us);
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(h->gstream, h->g_in, 0);
+  if (err == cudaSuccess) err = cudaGraphLaunch(e->exec, h->gstream);
+  if (err == cudaSuccess) err = cudaEventRecord(h->g_out, h->gstream);
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(us, h->g_out, 0);
+  if (err != cudaSuccess) return fail(B200M_ERR_CUDA, "CUDA graph replay failed: %s", cudaGetErrorString(err));
+  h->launches += e->launches;
+  ++h->graph_replays;
+  return B200M_OK;
+}
+
+inline uint64_t kp(const void* p) { return (uint64_t)reinterpret_cast<uintptr_t>(p); }
+inline uint64_t ki(long long a, long long b = 0) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; }
 
 // ------------------------------------------------------------------ packing helpers
 struct Packer {
@@ -374,6 +477,7 @@ int do_pack(b200m_handle* h, cudaStream_t stream) {
   if (want_sp) { int rc = pack_superpoint(h, P); if (rc) return rc; }
   if (want_sg) { int rc = pack_superglue(h, P); if (rc) return rc; }
 
+  drop_graphs(h);                 // captured launches carry pointers into the old weight arena
   if (h->d_w) { cudaFree(h->d_w); h->d_w = nullptr; }
   if (cudaMalloc(&h->d_w, P.host.size() * sizeof(float)) != cudaSuccess)
     return fail(B200M_ERR_CUDA, "cudaMalloc of %zu weight bytes failed", P.host.size() * sizeof(float));
@@ -826,6 +930,8 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_fused_stem = !(impl && strcmp(impl, "unfused") == 0);
   impl = getenv("B200M_GNN_IMPL");
   h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
+  impl = getenv("B200M_GRAPHS");
+  h->use_graphs = !(impl && strcmp(impl, "0") == 0);
   impl = getenv("B200M_SP_MICROBATCH");
   if (impl && atoi(impl) > 0) h->sp_micro_batch = std::min(atoi(impl), 256);
   *out = h;
@@ -835,6 +941,10 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
 void b200m_destroy(b200m_handle* h) {
   if (!h) return;
   DeviceGuard dev_guard__(h->device);
+  drop_graphs(h);
+  if (h->g_in) cudaEventDestroy(h->g_in);
+  if (h->g_out) cudaEventDestroy(h->g_out);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->d_w) cudaFree(h->d_w);
   delete h;
 }
@@ -916,6 +1026,7 @@ int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, 
 }
 
 long long b200m_launch_count(const b200m_handle* h) { return h ? h->launches : 0; }
+long long b200m_graph_replay_count(const b200m_handle* h) { return h ? h->graph_replays : 0; }
 
 int b200m_profile_begin(b200m_handle* h, int max_records) {
   if (!h || max_records <= 0) return fail(B200M_ERR_INVALID, "bad argument");
@@ -977,8 +1088,13 @@ int b200m_superpoint_forward(b200m_handle* h, const float* images, int n_images,
                              void* stream) {
   if (!h || !images || !keypoints || !scores || !counts) return fail(B200M_ERR_INVALID, "null argument");
   if (cap < b200m_keypoint_capacity(h, H, W)) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
-  return sp_forward_impl(h, stream, images, false, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
-                         nullptr, nullptr, 0, 0, ws, ws_bytes);
+  DeviceGuard dev_guard__(h->device);
+  return with_graph(h, stream, {1, kp(images), ki(n_images, cap), ki(H, W), kp(keypoints), kp(scores), kp(descriptors),
+                                kp(counts), kp(ws), (uint64_t)ws_bytes},
+                    [&](void* st) {
+                      return sp_forward_impl(h, st, images, false, n_images, H, W, keypoints, scores, descriptors, counts,
+                                             cap, nullptr, nullptr, nullptr, 0, 0, ws, ws_bytes);
+                    });
 }
 
 int b200m_superpoint_forward_u8(b200m_handle* h, const uint8_t* images, int n_images, int H, int W, float* keypoints,
@@ -986,8 +1102,13 @@ int b200m_superpoint_forward_u8(b200m_handle* h, const uint8_t* images, int n_im
                                 void* stream) {
   if (!h || !images || !keypoints || !scores || !counts) return fail(B200M_ERR_INVALID, "null argument");
   if (cap < b200m_keypoint_capacity(h, H, W)) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
-  return sp_forward_impl(h, stream, images, true, n_images, H, W, keypoints, scores, descriptors, counts, cap, nullptr,
-                         nullptr, nullptr, 0, 0, ws, ws_bytes);
+  DeviceGuard dev_guard__(h->device);
+  return with_graph(h, stream, {2, kp(images), ki(n_images, cap), ki(H, W), kp(keypoints), kp(scores), kp(descriptors),
+                                kp(counts), kp(ws), (uint64_t)ws_bytes},
+                    [&](void* st) {
+                      return sp_forward_impl(h, st, images, true, n_images, H, W, keypoints, scores, descriptors, counts,
+                                             cap, nullptr, nullptr, nullptr, 0, 0, ws, ws_bytes);
+                    });
 }
 
 int b200m_superpoint_dense(b200m_handle* h, const float* images, int n_images, int H, int W, float* semi,
@@ -1103,6 +1224,10 @@ int b200m_superglue_forward(b200m_handle* h, const float* kpts0, const float* sc
   if (!h->packed_sg) return fail(B200M_ERR_WEIGHTS, "SuperGlue weights are not packed (b200m_set_tensor + b200m_pack)");
   if (B <= 0) return B200M_OK;
   DeviceGuard dev_guard__(h->device);
+  return with_graph(h, stream, {3, kp(kpts0), kp(scores0), kp(desc0), kp(counts0), kp(kpts1), kp(scores1), kp(desc1),
+                                kp(counts1), ki(B, N), ki(M, H0), ki(W0, H1), ki(W1), kp(matches0), kp(matches1),
+                                kp(mscores0), kp(mscores1), kp(ws), (uint64_t)ws_bytes},
+                    [&](void* stream) -> int {
   LaunchCtx ctx = make_ctx(h, stream);
   if (N == 0 || M == 0) {   // superglue_test.py:235-242
     launch_match_select(ctx, nullptr, nullptr, nullptr, 0, nullptr, nullptr, B, N, M, 0.f, (long long*)matches0,
@@ -1119,6 +1244,7 @@ int b200m_superglue_forward(b200m_handle* h, const float* kpts0, const float* sc
   sg_core(h, ctx, w, kpts0, scores0, counts0, kpts1, scores1, counts1, B, N, M, H0, W0, H1, W1, matches0,
           matches1, mscores0, mscores1);
   return finish(h, ctx);
+                    });
 }
 
 int b200m_keypoint_encode(b200m_handle* h, const float* kpts, const float* scores, const float* desc, int B, int N,
@@ -1248,6 +1374,11 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   if (B <= 0) return B200M_OK;
   if (cap < b200m_keypoint_capacity(h, H, W) || cap <= 0) return fail(B200M_ERR_INVALID, "keypoint capacity %d too small", cap);
   DeviceGuard dev_guard0__(h->device);
+  return with_graph(h, stream, {images_u8 ? 5u : 4u, kp(image0), kp(image1), ki(B, cap), ki(H, W), kp(keypoints0),
+                                kp(scores0), kp(descriptors0), kp(counts0), kp(keypoints1), kp(scores1), kp(descriptors1),
+                                kp(counts1), kp(matches0), kp(matches1), kp(mscores0), kp(mscores1), kp(ws),
+                                (uint64_t)ws_bytes},
+                    [&](void* stream) -> int {
   const int D = h->cfg.descriptor_dim;
   const size_t sp_bytes = align_up(sp_ws_bytes(h, B, H, W), 256);
   if (ws_bytes < sp_bytes) return fail(B200M_ERR_WORKSPACE, "matching workspace too small");
@@ -1271,6 +1402,7 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   sg_core(h, ctx, w, keypoints0, scores0, counts0, keypoints1, scores1, counts1, B, cap, cap, H, W, H, W, matches0,
           matches1, mscores0, mscores1);
   return finish(h, ctx);
+                    });
 }
 
 int b200m_matching_forward(b200m_handle* h, const float* image0, const float* image1, int B, int H, int W,

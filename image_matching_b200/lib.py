@@ -68,6 +68,7 @@ SIGNATURES = {
     "b200m_debug_conv_layer": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
     "b200m_debug_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200m_launch_count": (C.c_longlong, [_P]),
+    "b200m_graph_replay_count": (C.c_longlong, [_P]),
     "b200m_profile_begin": (_I, [_P, _I]),
     "b200m_profile_end": (_I, [_P, C.c_char_p, _Z]),
 }

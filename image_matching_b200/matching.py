@@ -84,6 +84,7 @@ class _Engine:
         self.dirty = True
         self.ws = None
         self.packed = {}        # module id -> _weights_version this engine last packed
+        self._staging = {}
 
     def close(self):
         if self.handle is not None:
@@ -160,6 +161,19 @@ class _Engine:
 
     def launch_count(self) -> int:
         return int(_lib.load().b200m_launch_count(self.handle)) if self.handle is not None else 0
+
+    def graph_replays(self) -> int:
+        return int(_lib.load().b200m_graph_replay_count(self.handle)) if self.handle is not None else 0
+
+    def staging(self, key, nbytes: int, device):
+        """Persistent (per shape key) flat device buffer: stable pointers let the library replay its captured CUDA graph."""
+        buf = self._staging.get(key)
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            if len(self._staging) > 8:
+                self._staging.clear()
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self._staging[key] = buf
+        return buf
 
 
 def _stream(device):
@@ -406,6 +420,36 @@ class SuperGlue(_B200Module):
         return {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1}
 
 
+_OUT_LAYOUT = (("keypoints0", "f", lambda B, c, D: (B, c, 2)), ("scores0", "f", lambda B, c, D: (B, c)),
+               ("descriptors0", "f", lambda B, c, D: (B, D, c)), ("keypoints1", "f", lambda B, c, D: (B, c, 2)),
+               ("scores1", "f", lambda B, c, D: (B, c)), ("descriptors1", "f", lambda B, c, D: (B, D, c)),
+               ("counts", "i", lambda B, c, D: (2, B)), ("matches0", "l", lambda B, c, D: (B, c)),
+               ("matches1", "l", lambda B, c, D: (B, c)), ("matching_scores0", "f", lambda B, c, D: (B, c)),
+               ("matching_scores1", "f", lambda B, c, D: (B, c)))
+_OUT_DTYPES = {"f": (torch.float32, 4), "i": (torch.int32, 4), "l": (torch.int64, 8)}
+
+
+def _out_bytes(B, cap, D):
+    n = 0
+    for _, t, shp in _OUT_LAYOUT:
+        n = (n + 255) // 256 * 256 + int(np.prod(shp(B, cap, D))) * _OUT_DTYPES[t][1]
+    return n + 256
+
+
+def _out_views(flat: torch.Tensor, B, cap, D):
+    """The forward_device result dict as views into one flat uint8 buffer (256-byte aligned sub-tensors)."""
+    out, off = {}, 0
+    assert flat.data_ptr() % 256 == 0           # torch's CUDA allocations are 512-byte aligned
+    for name, t, shp in _OUT_LAYOUT:
+        dt, sz = _OUT_DTYPES[t]
+        shape = shp(B, cap, D)
+        off = (off + 255) // 256 * 256
+        nb = int(np.prod(shape)) * sz
+        out[name] = flat[off: off + nb].view(dt).view(shape)
+        off += nb
+    return out
+
+
 class Matching(nn.Module):
     """Image Matching Frontend (SuperPoint + SuperGlue); reference: superglue/models/matching_test.py:47-82."""
 
@@ -422,9 +466,11 @@ class Matching(nn.Module):
         return self._engine.ensure(device, self.superpoint, self.superglue)
 
     # ---- fused fast path: one C call for SuperPoint x2 + SuperGlue, no host sync inside
-    def forward_device(self, image0: torch.Tensor, image1: torch.Tensor):
+    def forward_device(self, image0: torch.Tensor, image1: torch.Tensor, out: dict | None = None):
         """Device-resident results without any host synchronisation: dict of padded tensors plus
-        per-pair `counts0/1` (number of valid leading keypoints)."""
+        per-pair `counts0/1` (number of valid leading keypoints).  `out`: a dict returned by an earlier call with the
+        same shapes, to be overwritten in place -- with unchanged input, output and workspace pointers the library
+        replays the CUDA graph it captured for this call instead of re-launching ~100 kernels one by one."""
         image0, image1 = _image(image0), _image(image1)
         if image0.dtype != image1.dtype:
             image0, image1 = image0.float() / (255.0 if image0.dtype == torch.uint8 else 1.0), \
@@ -439,20 +485,8 @@ class Matching(nn.Module):
         if self.superpoint.config["max_keypoints"] < 0:
             return self._forward_device_unbounded(L, image0, image1)
         cap = int(L.b200m_keypoint_capacity(e.handle, H, W))
-        f32, i64 = torch.float32, torch.int64
-        out = {
-            "keypoints0": torch.empty((B, cap, 2), dtype=f32, device=dev),
-            "scores0": torch.empty((B, cap), dtype=f32, device=dev),
-            "descriptors0": torch.empty((B, D, cap), dtype=f32, device=dev),
-            "keypoints1": torch.empty((B, cap, 2), dtype=f32, device=dev),
-            "scores1": torch.empty((B, cap), dtype=f32, device=dev),
-            "descriptors1": torch.empty((B, D, cap), dtype=f32, device=dev),
-            "counts": torch.empty((2, B), dtype=torch.int32, device=dev),
-            "matches0": torch.empty((B, cap), dtype=i64, device=dev),
-            "matches1": torch.empty((B, cap), dtype=i64, device=dev),
-            "matching_scores0": torch.empty((B, cap), dtype=f32, device=dev),
-            "matching_scores1": torch.empty((B, cap), dtype=f32, device=dev),
-        }
+        if out is None or out["keypoints0"].shape != (B, cap, 2) or out["keypoints0"].device != dev:
+            out = _out_views(torch.empty(_out_bytes(B, cap, D), dtype=torch.uint8, device=dev), B, cap, D)
         nbytes = L.b200m_matching_workspace_bytes(e.handle, B, H, W)
         ws = e.workspace(nbytes, dev)
         c0, c1 = out["counts"][0], out["counts"][1]
@@ -464,6 +498,33 @@ class Matching(nn.Module):
             _ptr(out["matches0"]), _ptr(out["matches1"]), _ptr(out["matching_scores0"]),
             _ptr(out["matching_scores1"]), _ptr(ws), ws.numel(), _stream(dev)), "b200m_matching_forward")
         return out
+
+    def _forward_replayable(self, image0, image1):
+        """forward_device for the reference-facing ``forward``: the caller hands in fresh tensors on every call and must
+        get fresh tensors back, but a CUDA graph replays only with unchanged pointers.  So (for batches up to 256 MB of
+        pixels) the images are copied into a persistent staging buffer, the library writes into a persistent result
+        buffer, and ONE device copy of that buffer becomes the caller's result -- three small copies buy the replay of
+        ~100 launches, which is what bounds the reference's own batch_size = 1 loop (superpoint_glue_test.py:65-78)."""
+        image0, image1 = _image(image0), _image(image1)
+        nbytes = image0.numel() * image0.element_size()
+        if (self.superpoint.config["max_keypoints"] < 0 or image0.dtype != image1.dtype or image0.shape != image1.shape
+                or nbytes > (128 << 20)):
+            return self.forward_device(image0, image1)
+        L = self._ensure(image0.device)
+        e = self._engine
+        B, _, H, W = image0.shape
+        D = self.superpoint.config["descriptor_dim"]
+        cap = int(L.b200m_keypoint_capacity(e.handle, H, W))
+        key = (B, H, W, cap, D, image0.dtype)
+        nb_al = (nbytes + 255) // 256 * 256
+        stage = e.staging(("in",) + key, 2 * nb_al, image0.device)
+        s0 = stage[:nbytes].view(image0.dtype).view(image0.shape)
+        s1 = stage[nb_al:nb_al + nbytes].view(image0.dtype).view(image0.shape)
+        s0.copy_(image0)
+        s1.copy_(image1)
+        flat = e.staging(("out",) + key, _out_bytes(B, cap, D), image0.device)
+        self.forward_device(s0, s1, out=_out_views(flat, B, cap, D))
+        return _out_views(flat.clone(), B, cap, D)
 
     def _forward_device_unbounded(self, L, image0, image1):
         """``max_keypoints = -1`` (the default of SuperPoint.default_config and of superpoint_glue_test.py:29): the
@@ -501,7 +562,7 @@ class Matching(nn.Module):
         pred = {}
         need0, need1 = "keypoints0" not in data, "keypoints1" not in data
         if need0 and need1 and data["image0"].shape == data["image1"].shape:
-            out = self.forward_device(data["image0"], data["image1"])
+            out = self._forward_replayable(data["image0"], data["image1"])
             cnt = out["counts"].cpu()          # the only host sync: list lengths are data dependent
             c0, c1 = cnt[0].tolist(), cnt[1].tolist()
             k0, s0, d0 = SuperPoint._to_lists(out["keypoints0"], out["scores0"], out["descriptors0"], c0)

@@ -215,8 +215,14 @@ int b200m_debug_conv_layer(b200m_handle* h, int layer, int use_tc, const float* 
 int b200m_debug_attention(b200m_handle* h, const float* qkv, float* msg, int B, int Np, int n0, int n1, int cross,
                           int use_tc, void* stream);
 
-/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches); kernels executed through a
+ * replayed CUDA graph are counted like directly launched ones. */
 long long b200m_launch_count(const b200m_handle* h);
+/* The forward entry points (b200m_matching_forward[_u8], b200m_superpoint_forward[_u8], b200m_superglue_forward) capture
+ * their launch sequence into a CUDA graph the second time they are called with identical arguments (same shapes,
+ * pointers and workspace) and replay it afterwards; semantics are unchanged (stream-ordered, caller-owned buffers).
+ * B200M_GRAPHS=0 in the environment disables it.  This returns how many calls were served by a replay. */
+long long b200m_graph_replay_count(const b200m_handle* h);
 
 /* Per-launch CUDA-event timing on the launching stream (bench.py's roofline leg; off by default).
  * b200m_profile_end synchronises the device and writes {"kernel": {"ms": total, "launches": n}, ...}. */
