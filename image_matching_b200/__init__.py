@@ -5,8 +5,8 @@ classes it owns).  See DESIGN.md / INTEGRATION.md at the repo root.
 """
 from .matching import (Matching, MatchingOfficial, SuperPoint, SuperPointOfficial, SuperGlue,  # noqa: F401
                        knn_ratio_match)
-from .registration import estimate_affine_partial_2d, warp_affine, register_pairs  # noqa: F401
+from .registration import estimate_affine_partial_2d, warp_affine, register_pairs, resize_u8  # noqa: F401
 from . import synth, lib  # noqa: F401
 
 __all__ = ["Matching", "MatchingOfficial", "SuperPoint", "SuperPointOfficial", "SuperGlue", "knn_ratio_match", "estimate_affine_partial_2d", "warp_affine",
-           "register_pairs", "synth", "lib"]
+           "register_pairs", "resize_u8", "synth", "lib"]

@@ -575,7 +575,15 @@ void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const floa
 }
 
 // encoder + heads for `n` images (n <= micro-batch): fills w.semi (C4, 32 groups) and w.draw (C4, dpad/4 groups)
-void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, const float* images, int n) {
+// images: fp32 pixels, or (images_u8 != null) the raw 8-bit pixels -- normalised inside the fused stem's patch load; only
+// the unfused / CUDA-core paths still need the fp32 copy (w.imgf)
+void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, const float* images, int n,
+              const uint8_t* images_u8 = nullptr) {
+  auto fp32_images = [&]() -> const float* {
+    if (!images_u8) return images;
+    launch_u8_to_unit_f32(ctx, images_u8, w.imgf, (size_t)n * d.H * d.W);
+    return w.imgf;
+  };
   // the C4 buffers are addressed per image with each layer's own channel-group count, so the ping-pong
   // buffers are simply re-interpreted per layer
   if (h->use_tc) {
@@ -589,13 +597,15 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
       p.in_hi = nullptr; p.in_lo = nullptr; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
       p.out_hi = w.p1; p.out_lo = w.p1_lo; p.out_c4_total = 8; p.out_c4_off = 0; p.overflow = ovf;
       p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = d.H; p.W = d.W; p.relu = 1; p.pool = 1; p.ks = 3;
-      p.img = images;
+      p.img = images_u8 ? nullptr : images;
+      p.img_u8 = images_u8;
       memcpy(p.c1, h->stem_host.data(), sizeof(p.c1));
       p.bias_in_params = 1;
       memcpy(p.bias_c, L.bias_host.data(), sizeof(float) * L.cout_pad);
       stem = launch_tc_conv(ctx, p, h->num_sms);
     }
     if (!stem) {
+      images = fp32_images();
       launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, w.p0_lo, n, d.H, d.W);
       run_conv_tc(h, ctx, h->c1b, w.p0, w.p0_lo, w.p1, w.p1_lo, 8, n, d.H, d.W, true, ovf);      // -> 64 x H2 x W2
     }
@@ -613,6 +623,7 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
                 w.sumsq);
     return;
   } else {
+    images = fp32_images();
     launch_conv1_direct(ctx, images, h->d_w + h->conv1_w, h->d_w + h->conv1_b, w.p0, nullptr, n, d.H, d.W);
     run_conv(h, ctx, h->c1b, w.p0, 16, 0, w.p1, 16, n, d.H, d.W, true, true);       // -> 64 x H2 x W2
     run_conv(h, ctx, h->c2a, w.p1, 16, 0, w.p0, 16, n, d.H2, d.W2, true, false);
@@ -646,14 +657,9 @@ int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool 
   cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), ctx.stream);
   for (int i0 = 0; i0 < n_images; i0 += mb) {
     const int n = std::min(mb, n_images - i0);
-    const float* images_mb;
-    if (images_u8) {   // SSHIDataset.py:26-29 normalisation (pixel / 255, rounded to fp32) done on the device
-      launch_u8_to_unit_f32(ctx, static_cast<const uint8_t*>(images_any) + (size_t)i0 * H * W, w.imgf, (size_t)n * H * W);
-      images_mb = w.imgf;
-    } else {
-      images_mb = static_cast<const float*>(images_any) + (size_t)i0 * H * W;
-    }
-    sp_dense(h, ctx, d, w, images_mb, n);
+    // 8-bit input: SSHIDataset.py:26-29's normalisation (pixel / 255, rounded to fp32) happens in the stem's patch load
+    if (images_u8) sp_dense(h, ctx, d, w, nullptr, n, static_cast<const uint8_t*>(images_any) + (size_t)i0 * H * W);
+    else sp_dense(h, ctx, d, w, static_cast<const float*>(images_any) + (size_t)i0 * H * W, n);
     if (semi_out)
       launch_c4_to_nchw(ctx, w.semi, 32, 0, 65, semi_out + (size_t)i0 * 65 * d.hc * d.wc, n, d.hc, d.wc, false);
     if (desc_out)
@@ -1334,6 +1340,16 @@ int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M, int
   launch_dense_argmax(ctx, Z, B, N, M, idx0, max0, idx1, ld);
   launch_match_select(ctx, idx0, max0, idx1, ld, nullptr, nullptr, B, N, M, h->cfg.match_threshold,
                       (long long*)matches0, (long long*)matches1, mscores0, mscores1);
+  return finish(h, ctx);
+}
+
+int b200m_resize_linear_u8(b200m_handle* h, const uint8_t* src, int B, int src_h, int src_w, uint8_t* dst, int dst_h,
+                           int dst_w, void* stream) {
+  if (!h || !src || !dst) return fail(B200M_ERR_INVALID, "null argument");
+  if (B < 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return fail(B200M_ERR_INVALID, "bad image size");
+  DeviceGuard dev_guard__(h->device);
+  LaunchCtx ctx = make_ctx(h, stream);
+  launch_resize_linear_u8(ctx, src, B, src_h, src_w, dst, dst_h, dst_w);
   return finish(h, ctx);
 }
 

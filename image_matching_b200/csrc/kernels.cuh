@@ -57,6 +57,8 @@ struct TcConvParams {
   // fused first layer: img != null -> the input activations are computed from the grayscale images (n, H, W) with the
   // stem weights c1 = [9 taps][64] | bias [64] (carried in the kernel parameters) instead of being read from in_hi / in_lo
   const float* img = nullptr;
+  const unsigned char* img_u8 = nullptr;    // alternative to img: raw 8-bit pixels, divided by 255 in the patch load
+                                            // (datasets/SSHIDataset.py:26-28 + the caller's .float(), correctly rounded)
   float c1[9 * 64 + 64];
   int bias_in_params = 0;                   // cout_pad <= 128: the epilogue reads the bias from bias_c (constant bank)
   float bias_c[128];
@@ -199,6 +201,9 @@ void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, con
                          const int* counts0, const int* counts1, int B, int N, int M, float thr,
                          long long* matches0, long long* matches1, float* ms0, float* ms1);
 
+// cv2.resize(src, (dw, dh)), uint8 single channel, INTER_LINEAR -- the data loader's resize (datasets/SSHIDataset.py:20-22)
+void launch_resize_linear_u8(LaunchCtx& ctx, const unsigned char* src, int B, int sh, int sw, unsigned char* dst, int dh,
+                             int dw);
 // multi-GPU gather wire format (one int32 buffer per rank: [pair][index row | score-bits row][N])
 void launch_pack_match_wire(LaunchCtx& ctx, const long long* matches, const float* scores, int B_valid, int B_wire,
                             int N, int ld, int* wire);

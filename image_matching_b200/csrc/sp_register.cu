@@ -361,4 +361,61 @@ bool launch_warp_affine(LaunchCtx& ctx, const void* src, int dtype, int B, int s
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cv2.resize(src, (dw, dh)) of the reference's data loader (datasets/SSHIDataset.py:20-22; uint8, INTER_LINEAR), restated
+// from OpenCV 4.13 imgproc/src/resize.cpp: destination coordinate in double cast to float, 11-bit fixed-point weights
+// (round half to even), horizontal taps clamped with their weight reset, vertical rows clipped with the weights kept,
+// and OpenCV's substitution of its 2x2 box filter for an exact 2x decimation.  One thread per destination pixel; a warp
+// writes 32 consecutive bytes and reads two source rows.  HBM-bound: (source bytes touched + destination bytes) / time.
+struct ResizeCoef { int i0, i1, w0, w1; };
+__device__ __forceinline__ ResizeCoef resize_coef(int d, int sn, double scale, bool vertical) {
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);      // no FMA contraction: OpenCV rounds twice
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (!vertical) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  }
+  ResizeCoef c;
+  c.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  c.w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  c.i0 = min(max(s, 0), sn - 1);
+  c.i1 = min(max(s + 1, 0), sn - 1);
+  return c;
+}
+__global__ void __launch_bounds__(256) resize_linear_u8_kernel(const unsigned char* __restrict__ src, int sh, int sw,
+                                                               unsigned char* __restrict__ dst, int dh, int dw,
+                                                               double scale_x, double scale_y, int area2) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dw || y >= dh) return;
+  const unsigned char* s = src + (size_t)blockIdx.z * sh * sw;
+  int v;
+  if (area2) {
+    const unsigned char* r0 = s + (size_t)(2 * y) * sw + 2 * x;
+    v = (r0[0] + r0[1] + r0[sw] + r0[sw + 1] + 2) >> 2;
+  } else {
+    const ResizeCoef cx = resize_coef(x, sw, scale_x, false), cy = resize_coef(y, sh, scale_y, true);
+    const unsigned char* r0 = s + (size_t)cy.i0 * sw;
+    const unsigned char* r1 = s + (size_t)cy.i1 * sw;
+    const int h0 = r0[cx.i0] * cx.w0 + r0[cx.i1] * cx.w1;
+    const int h1 = r1[cx.i0] * cx.w0 + r1[cx.i1] * cx.w1;
+    v = (((cy.w0 * (h0 >> 4)) >> 16) + ((cy.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+  }
+  dst[((size_t)blockIdx.z * dh + y) * dw + x] = (unsigned char)v;
+}
+
+void launch_resize_linear_u8(LaunchCtx& ctx, const unsigned char* src, int B, int sh, int sw, unsigned char* dst, int dh,
+                             int dw) {
+  if (B <= 0 || dh <= 0 || dw <= 0) return;
+  ProfScope prof__(ctx, "resize_u8");
+  const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+  const int area2 = (int)scale_x == 2 && (int)scale_y == 2 && fabs(inv_x - 0.5) < 2.220446049250313e-16 &&
+                    fabs(inv_y - 0.5) < 2.220446049250313e-16;
+  dim3 grid(cdiv(dw, 32), cdiv(dh, 8), B);
+  resize_linear_u8_kernel<<<grid, 256, 0, ctx.stream>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, area2);
+  B200M_LAUNCH_CHECK(ctx, "resize_u8");
+}
+
 }  // namespace b200m

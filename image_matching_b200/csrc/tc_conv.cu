@@ -248,11 +248,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       int cb, x0, y0, img;
       decode(tile, cb, x0, y0, img);
       asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");          // everyone is done with the previous patch
-      const float* im = p.img + (size_t)img * p.H * p.W;
+      const size_t img_off = (size_t)img * p.H * p.W;
       for (int i = t; i < 400; i += kStemT) {
         const int r = i / 20, c = i - r * 20;
         const int gy = y0 - 2 + r, gx = x0 - 2 + c;
-        patch[i] = (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? __ldg(im + (size_t)gy * p.W + gx) : 0.f;
+        float v = 0.f;
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+          const size_t o = img_off + (size_t)gy * p.W + gx;
+          // 8-bit input: the loader's `pixel / 255.` (float64) followed by .float() == one correctly rounded fp32 division
+          v = p.img_u8 ? __fdiv_rn((float)__ldg(p.img_u8 + o), 255.f) : __ldg(p.img + o);
+        }
+        patch[i] = v;
       }
       asm volatile("bar.sync 3, %0;" ::"n"(kStemT) : "memory");
       const int cst = 2 * it + kbw;                                      // running A-stage index (two per tile)
@@ -434,7 +440,7 @@ bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
     if (p.pool) return false;
     return p.nb == 64 ? launch_tc_t<64, false, 1>(ctx, p, num_sms) : launch_tc_t<128, false, 1>(ctx, p, num_sms);
   }
-  if (p.img) {   // fused first layer (image -> 64 channels) in front of a 64 -> 64 pooled layer
+  if (p.img || p.img_u8) {   // fused first layer (image -> 64 channels) in front of a 64 -> 64 pooled layer
     if (p.nb != 64 || p.cin != 64 || p.cout_pad != 64 || !p.pool) return false;
     // (weights resident, 2 A stages = one tile: the two stages are filled concurrently by stem warps 0-3 / 4-7;
     // measured 7.6 ms vs 8.7 ms with streamed weights + 3 stages)

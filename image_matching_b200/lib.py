@@ -63,6 +63,7 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _Z, _P]),
     "b200m_matching_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,
                                        _P, _P, _P, _P, _P, _Z, _P]),
+    "b200m_resize_linear_u8": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     "b200m_pack_match_wire": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "b200m_unpack_match_wire": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "b200m_debug_conv_layer": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),

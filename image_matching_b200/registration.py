@@ -118,3 +118,31 @@ def register_pairs(owner, pred: dict, ransac_reproj_threshold: float = 7.0, resi
 
 
 __all__ = ["estimate_affine_partial_2d", "warp_affine", "register_pairs"]
+
+
+def resize_u8(owner, images: torch.Tensor, resize_scale: float | None = None, dsize: tuple[int, int] | None = None):
+    """The data loader's resize on the device (datasets/SSHIDataset.py:20-22):
+    ``cv2.resize(img, (int(resize_scale * W), int(resize_scale * H)))`` for uint8 grayscale images (H,W), (B,H,W) or
+    (B,1,H,W) -- bit-identical to OpenCV 4.13's INTER_LINEAR.  ``dsize`` = (width, height) overrides the scale.  The
+    uint8 result can be passed straight to ``Matching`` / ``SuperPoint`` (their first kernel divides by 255 while loading
+    the pixels, as SSHIDataset.py:26-28 + the caller's ``.float()`` do).  CUDA only -- no CPU fallback."""
+    if images.device.type != "cuda":
+        raise RuntimeError("image_matching_b200 runs on CUDA (sm_100a) only -- there is no CPU fallback")
+    if images.dtype != torch.uint8:
+        raise ValueError(f"resize_u8 takes uint8 images (the loader resizes before normalising), got {images.dtype}")
+    shape = images.shape
+    if images.dim() == 4 and shape[1] != 1:
+        raise ValueError("expected single-channel images")
+    x = images.reshape(-1, shape[-2], shape[-1]).contiguous()
+    B, H, W = x.shape
+    if dsize is None:
+        if resize_scale is None:
+            return images
+        dsize = (int(resize_scale * W), int(resize_scale * H))
+    dw, dh = int(dsize[0]), int(dsize[1])
+    if dw <= 0 or dh <= 0:
+        raise ValueError("empty destination size")
+    L, h = _handle(owner, x.device)
+    dst = torch.empty((B, dh, dw), dtype=torch.uint8, device=x.device)
+    _lib.check(L.b200m_resize_linear_u8(h, _ptr(x), B, H, W, _ptr(dst), dh, dw, _stream(x.device)), "b200m_resize_linear_u8")
+    return dst.reshape(tuple(shape[:-2]) + (dh, dw))

@@ -194,6 +194,14 @@ int b200m_matching_forward_u8(b200m_handle* h, const uint8_t* image0, const uint
                            int cap, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* The data loader's resize: cv2.resize(img, (dst_w, dst_h)) of datasets/SSHIDataset.py:20-22 -- 8-bit
+ * grayscale, default INTER_LINEAR -- for B images (B,src_h,src_w) uint8 on the device, bit-identical to OpenCV 4.13
+ * (11-bit fixed-point bilinear; its 2x2 box filter for an exact 2x decimation).  The caller passes
+ * dst_w = int(resize_scale * src_w), dst_h = int(resize_scale * src_h) like the reference does.  The result feeds
+ * b200m_matching_forward_u8 / b200m_superpoint_forward_u8, whose first kernel divides by 255 while it loads the pixels. */
+int b200m_resize_linear_u8(b200m_handle* h, const uint8_t* src, int B, int src_h, int src_w, uint8_t* dst, int dst_h,
+                           int dst_w, void* stream);
+
 /* Multi-GPU gather of the results (pairs are sharded over ranks, the only collective is the final gather
  * of match indices): ONE int32 wire buffer per rank, (B_wire, 2, N) = per pair a row of match indices (int64 -> int32)
  * and a row of matching-score bits, so a single all-gather moves both.  `pack` reads this rank's (B_valid, N) results

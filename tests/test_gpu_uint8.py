@@ -39,3 +39,40 @@ def test_uint8_images_match_float_images_bit_for_bit():
     s8 = m.superpoint(torch.from_numpy(a8).cuda())
     sf = m.superpoint(af.cuda())
     assert all(torch.equal(x, y) for x, y in zip(s8["keypoints"], sf["keypoints"]))
+
+
+def test_resize_matches_cv2_golden_and_oracle():
+    """b200m_resize_linear_u8 (datasets/SSHIDataset.py:20-22 on the device): bit-identical to the cv2-generated golden
+    (tests/golden/resize.npz) and to the oracle at the loader's real sizes, batched, incl. the exact-2x box path."""
+    from conftest import load_golden
+    from image_matching_b200 import SuperPoint, resize_u8
+    from oracle import input_oracle as IO
+    sp = SuperPoint({"weights": None, "descriptor_dim": 128}).eval().to("cuda:0")
+    g = load_golden("resize")
+    for i, (h, w, sc) in enumerate(g["cases"]):
+        got = resize_u8(sp, torch.from_numpy(g[f"src_{i}"]).cuda(), float(sc)).cpu().numpy()
+        assert np.array_equal(got, g[f"dst_{i}"]), (i, h, w, sc)
+    rng = np.random.default_rng(9)
+    for H, W, sc in [(1944, 2592, 0.125), (960, 1280, 0.5), (1000, 1504, 0.32)]:
+        src = rng.integers(0, 256, (3, 1, H, W), dtype=np.uint8)
+        got = resize_u8(sp, torch.from_numpy(src).cuda(), sc).cpu().numpy()
+        dw, dh = int(sc * W), int(sc * H)
+        assert got.shape == (3, 1, dh, dw)
+        for b in range(3):
+            assert np.array_equal(got[b, 0], IO.resize_linear_u8(src[b, 0], dw, dh)), (H, W, sc, b)
+
+
+def test_loader_pipeline_on_device_equals_reference_loader():
+    """resize + /255 on the device (uint8 in) == the reference's loader on the host (oracle restatement) through SuperPoint."""
+    from image_matching_b200 import SuperPoint, resize_u8, synth
+    from oracle import input_oracle as IO
+    sp = SuperPoint({"weights": None, "descriptor_dim": 128, "max_keypoints": 200}).eval()
+    sp.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in real_superpoint_weights().items()})
+    sp = sp.to("cuda:0")
+    big = np.round(synth.make_image(3, 960, 1280) * 255).astype(np.uint8)
+    host = IO.load_like_sshi(big, 0.25)                                   # (1, 240, 320) float32, the reference's loader
+    dev8 = resize_u8(sp, torch.from_numpy(big).cuda()[None, None], 0.25)  # (1, 1, 240, 320) uint8 on the device
+    a = sp(torch.from_numpy(host)[None].cuda())
+    b = sp(dev8)
+    assert torch.equal(a["keypoints"][0], b["keypoints"][0]) and torch.equal(a["descriptors"][0], b["descriptors"][0])
+    assert a["keypoints"][0].shape[0] == 200
