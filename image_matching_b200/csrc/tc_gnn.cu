@@ -26,6 +26,8 @@
 // 0,1 (free once GEMM3 retired) in the TMA box layout and written with cp.async.bulk.tensor stores; the next tile's x
 // is fetched into the same blocks after the last store has read them.
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogues / x splitter (thread = (token row, column half)).
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -39,7 +41,7 @@ constexpr int kGnTile = 2 * kGnPlane;           // hi + lo
 constexpr int kGnRing = 3;
 constexpr int kGnOffRing = 4 * kGnTile;
 constexpr int kGnOffBar = kGnOffRing + kGnRing * kGnTile;
-constexpr int kGnBars = 2 * kGnRing + 6 + 4;
+constexpr int kGnBars = 2 * kGnRing + 6 + 4 + 2;
 constexpr int kGnOffBias = kGnOffBar + kGnBars * 8 + 16;
 constexpr int kGnBiasFloats = 256 + 128 + 256;  // mlp1 (merge bias folded in) | mlp2 | next q,k  (the V bias is per TMEM lane)
 constexpr size_t kGnSmem = kGnOffBias + kGnBiasFloats * 4;   // 232080 of the 232448 bytes a CTA may have: no alignment slack
@@ -50,6 +52,15 @@ __device__ __forceinline__ void gn_split8(const float* v, uint4& hi, uint4& lo, 
   split8_f16(v, lo_scale, hi, lo);
 }
 
+// Developer aid (make EXTRA=-DB200M_GNN_TRACE, run with B200M_GNN_TRACE=1): clock64 stamps of one CTA's third tile for
+// the producer / MMA / first epilogue warp, dumped to stderr by the launcher.  This is how the two stalls fixed in round 2
+// were found (the residual's strided loads clogging the memory-instruction queue; the exposed x load at the tile start).
+#ifdef B200M_GNN_TRACE
+__device__ long long* g_gnn_trace = nullptr;
+#define GT(slot) do { if (traced && lane == 0) tr[(slot)] = clock64(); } while (0)
+#else
+#define GT(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(320, 1)
 tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_constant__ CUtensorMap tm_att_lo,
                     const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qkv_hi,
@@ -69,10 +80,20 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   uint64_t* xnew_ready = hid_ready + 1;     // x_new planes written (XM blocks 2,3)
   uint64_t* acc_full = xnew_ready + 1;      // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* xm01_free = acc_empty + 2;      // GEMM3's first two K blocks retired: XM blocks 0,1 may take the x reload
+  uint64_t* x2_full = xm01_free + 1;        // the tile's fp32 x landed in XM blocks 0,1 a second time (residual add)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x2_full + 1);
 
   float* sBias = reinterpret_cast<float*>(smem + kGnOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200M_GNN_TRACE
+  long long* const tr = g_gnn_trace;
+  const bool traced_cta = tr != nullptr && blockIdx.x == 5;
+  bool traced = false;
+#define GT_ARM(cond) traced = traced_cta && (cond)
+#else
+#define GT_ARM(cond) do { } while (0)
+#endif
   if (smem_u32(smem) & 1023) __trap();
   for (int i = threadIdx.x; i < kGnBiasFloats; i += blockDim.x) sBias[i] = p.bias[i];
   const int ntiles = cdiv(p.rows, 128);
@@ -87,6 +108,8 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     mbar_init(hid_ready, 8);
     mbar_init(xnew_ready, 8);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    mbar_init(xm01_free, 1);
+    mbar_init(x2_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_att_hi); tma_prefetch_desc(&tm_att_lo); tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_qkv_hi); tma_prefetch_desc(&tm_qkv_lo); tma_prefetch_desc(&tm_vt_hi); tma_prefetch_desc(&tm_vt_lo);
@@ -100,17 +123,19 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int s = 0, ph = 0;
-    auto load_x = [&](int tile) {
-      mbar_expect_tx(x_full, 2 * kGnTile);
+    auto load_x = [&](int tile, uint64_t* bar) {
+      mbar_expect_tx(bar, 2 * kGnTile);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        tma_load_2d(sXM + kb * kGnTile, &tm_x, x_full, kb * 64, tile * 128);
-        tma_load_2d(sXM + kb * kGnTile + kGnPlane, &tm_x, x_full, kb * 64 + 32, tile * 128);
+        tma_load_2d(sXM + kb * kGnTile, &tm_x, bar, kb * 64, tile * 128);
+        tma_load_2d(sXM + kb * kGnTile + kGnPlane, &tm_x, bar, kb * 64 + 32, tile * 128);
       }
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      if (it == 0) load_x(tile);
+      GT_ARM(it == 2);
+      GT(0);
+      if (it == 0) load_x(tile, x_full);
       const uint8_t* w = p.wts;
       for (int kb = 0; kb < 2; ++kb) {          // GEMM1: attention planes + W_merge tile per K block
         mbar_wait(&empty[s], ph ^ 1);
@@ -125,15 +150,30 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         if (++s == kGnRing) { s = 0; ph ^= 1; }
       }
       if (it > 0) {                             // this tile's x: XM blocks 0,1 are free once the previous tile's last
+        GT(1);
         mbar_wait(x_free, (it - 1) & 1);        // staged store has read them (GEMM1 above does not need x)
-        load_x(tile);
+        GT(2);
+        load_x(tile, x_full);
       }
       for (int i = 0; i < n_wtiles; ++i) {      // GEMM2 (8), GEMM3 (4), GEMM4 (2 per column tile)
+        GT(10 + 2 * i);
         mbar_wait(&empty[s], ph ^ 1);
+        GT(11 + 2 * i);
         mbar_expect_tx(&full[s], kGnTile);
         bulk_load(sRing + s * kGnTile, w, kGnTile, &full[s]);
         w += kGnTile;
         if (++s == kGnRing) { s = 0; ph ^= 1; }
+        if (i == 11) {
+          // the residual needs the old x once more.  Fetching it with per-thread loads (one 1 KB-strided row per thread:
+          // 4 k sector requests per tile) clogged the SM's memory-instruction queue exactly when the MMA warp issues
+          // GEMM3 -- clock64 stamps showed its mbarrier / tcgen05.mma instructions taking 6 k cycles there.  TMA brings the
+          // same 64 KB back into XM blocks 0,1 (free once GEMM3's K blocks 0,1 retired; the next weight tile waits for
+          // the same event), in the box layout epilogue 3 updates in place.
+          GT(3);
+          mbar_wait(xm01_free, it & 1);
+          GT(4);
+          load_x(tile, x2_full);
+        }
       }
     }
   } else if (warp == 1) {
@@ -187,8 +227,11 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      GT_ARM(it == 2);
+      GT(100);
       // ---- GEMM1 (merge) -> buffer 1
       acquire(1);
+      GT(101);
       for (int kb = 0; kb < 2; ++kb) {
         const int sa = s, pa = ph;
         if (++s == kGnRing) { s = 0; ph ^= 1; }
@@ -204,35 +247,52 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         if (++s == kGnRing) { s = 0; ph ^= 1; }
       }
       publish(1);
+      GT(102);
       // ---- GEMM2 (mlp layer 1), column tile 0 -> buffer 0: x part first, msg part once the merge epilogue is done
       mbar_wait(x_ready, it & 1);
       acquire(0);
+      GT(103);
       step_xm(0, 0, true);
       step_xm(0, 1, false);
+      GT(104);
       mbar_wait(msg_ready, it & 1);
       tc_fence_after();
+      GT(105);
       step_xm(0, 2, false);
       step_xm(0, 3, false);
       publish(0);
+      GT(106);
       // ---- GEMM2 column tile 1 -> buffer 1
       acquire(1);
+      GT(107);
       for (int kb = 0; kb < 4; ++kb) step_xm(1, kb, kb == 0);
       publish(1);
+      GT(108);
       // ---- GEMM3 (mlp layer 2) -> buffer 0
       mbar_wait(hid_ready, it & 1);
       acquire(0);
-      for (int kb = 0; kb < 4; ++kb) step_xm(0, kb, kb == 0);
+      GT(109);
+      for (int kb = 0; kb < 4; ++kb) {
+        step_xm(0, kb, kb == 0);
+        if (kb == 1) {
+          if (elect_one()) tc_commit(xm01_free);
+          __syncwarp();
+        }
+      }
       publish(0);
+      GT(110);
       // ---- GEMM4 (next layer's q|k|v), column tiles alternate buffers 0,1,0
       if (p.nt4 > 0) {
         mbar_wait(xnew_ready, it & 1);
         tc_fence_after();
+        GT(111);
         for (int nt = 0; nt < p.nt4; ++nt) {
           const int b = nt & 1;
           acquire(b);
           step_xm(b, 2, true, nt == 2);
           step_xm(b, 3, false, nt == 2);
           publish(b);
+          GT(112 + nt);
         }
       }
     }
@@ -306,10 +366,11 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
     const float* b_qk = sBias + 384;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int r = tile * 128 + row;
-      const bool rok = r < p.rows;
+      GT_ARM(it == 2 && warp == 2);
+      GT(200);
       // ---- x: raw fp32 (two 32-column boxes per K block) -> hi / lo planes, in place; this thread: K block `half`
       mbar_wait(x_full, it & 1);
+      GT(201);
       {
         uint8_t* kb = sXM + half * kGnTile;
         float e[64];
@@ -326,8 +387,11 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         store_planes(kb, 32, e + 32, kGnLo);
       }
       signal(x_ready);
+      GT(202);
       // ---- epilogue 1: msg = acc (b_merge lives in b_1') -> XM blocks 2,3 (this thread: columns half*64 .. +63)
       wait_acc(1);
+      if (it > 0 && p.nt4 > 0) stage_begin();     // the previous tile's V^T stores were staged in blocks 2,3: reads done?
+      GT(203);
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
@@ -336,10 +400,12 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       }
       release_acc(1);
       signal(msg_ready);
+      GT(204);
       // ---- epilogue 2: hid = relu(acc + b_1); this thread: column tile `half` (buffer `half`), 128 columns.
       // hid overwrites [x | msg], so every GEMM2 MMA must have retired: wait for both buffers.
       wait_acc(0);
       wait_acc(1);
+      GT(205);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         float v[32];
@@ -352,15 +418,15 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       release_acc(0);
       release_acc(1);
       signal(hid_ready);
+      GT(206);
       // ---- epilogue 3: x_new = x + acc + b_2 -> operand planes in XM blocks 2,3 and, as fp32 in the TMA box layout of
       // the x load, into XM blocks 0,1 (free: GEMM3 has retired), from where one bulk tensor store writes the tile.
-      // (the old x is fetched before the accumulator wait: the L2 round trip hides behind GEMM3)
-      const float* xrow = p.X + (size_t)r * p.ldx + half * 64;
-      float4 xold[16];
-#pragma unroll
-      for (int g = 0; g < 16; ++g)
-        xold[g] = rok ? __ldcg(reinterpret_cast<const float4*>(xrow) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // The old x arrives by TMA in exactly that box layout (second load of the tile, issued behind GEMM3) and is
+      // updated in place.
       wait_acc(0);
+      GT(207);
+      mbar_wait(x2_full, it & 1);
+      GT(216);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         float v[32];
@@ -369,14 +435,16 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         uint8_t* box = sXM + half * kGnTile + ch * kGnPlane + row * 128;     // fp32 box: columns half*64 + ch*32 .. +31
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 old = xold[ch * 8 + g];
+          float4* cell = reinterpret_cast<float4*>(box + ((g ^ sw) << 4));
+          const float4 old = *cell;
           v[4 * g] += old.x; v[4 * g + 1] += old.y; v[4 * g + 2] += old.z; v[4 * g + 3] += old.w;
-          *reinterpret_cast<float4*>(box + ((g ^ sw) << 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          *cell = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
         store_planes(sXM + (2 + half) * kGnTile, ch * 32, v, kGnLo);
       }
       release_acc(0);
       signal(xnew_ready);
+      GT(208);
       stage_end();
       if (storer) {
 #pragma unroll
@@ -388,11 +456,15 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       }
       __syncwarp();
       // ---- epilogue 4: next layer's q | k -> fp16 hi / lo planes [rows][384]; V arrives transposed (TMEM lane =
-      // channel, column = token) -> V^T planes [block][128][Np].  Each 128-column tile is staged in XM blocks 0,1
-      // (block = 64 columns: hi plane | lo plane, the layout of a SWIZZLE_128B box) and stored by TMA.
+      // channel, column = token) -> V^T planes [block][128][Np].  Each 128-column tile is staged (block = 64 columns: hi
+      // plane | lo plane, the layout of a SWIZZLE_128B box) and stored by TMA: q and k in XM blocks 0,1, the V^T tile in
+      // blocks 2,3 (the x_new planes there are dead once GEMM4 retired) -- so blocks 0,1 are released for the NEXT tile's
+      // x one column tile earlier and its DRAM latency hides behind the V epilogue (it was 4.6 k exposed cycles per tile).
       for (int nt = 0; nt < p.nt4; ++nt) {
         const int b = nt & 1;
+        GT(209 + 2 * nt);
         wait_acc(b);
+        GT(210 + 2 * nt);
         const float bv = nt == 2 ? __ldg(p.bias + kGnBiasFloats + row) : 0.f;   // V: this thread's channel = `row`
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
@@ -404,8 +476,11 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bv;
           }
-          if (ch == 0) stage_begin();
-          store_planes(sXM + half * kGnTile, ch * 32, v, 1.f);      // attention planes carry the unscaled residual
+          if (ch == 0) {
+            stage_begin();                                        // every earlier staged store has read its buffer
+            if (nt == 2 && storer) mbar_arrive(x_free);           // ... so blocks 0,1 may take the next tile's x now
+          }
+          store_planes(sXM + ((nt == 2 ? 2 : 0) + half) * kGnTile, ch * 32, v, 1.f);   // attention planes: unscaled residual
         }
         release_acc(b);
         stage_end();
@@ -422,8 +497,8 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
               const int t0 = tile * 128 + hf * 64;
               if (t0 < p.rows) {
                 const int blk = t0 / p.vt_np, rr0 = t0 - blk * p.vt_np;
-                tma_store_2d(&tm_vt_hi, sXM + hf * kGnTile, rr0, blk * 128);
-                tma_store_2d(&tm_vt_lo, sXM + hf * kGnTile + kGnPlane, rr0, blk * 128);
+                tma_store_2d(&tm_vt_hi, sXM + (2 + hf) * kGnTile, rr0, blk * 128);
+                tma_store_2d(&tm_vt_lo, sXM + (2 + hf) * kGnTile + kGnPlane, rr0, blk * 128);
               }
             }
           }
@@ -431,8 +506,9 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         }
         __syncwarp();
       }
-      // ---- the staging blocks may take the next tile's x once the last store has read them
-      if (storer) {
+      GT(215);
+      // ---- last layer (no q|k|v epilogue): blocks 0,1 may take the next tile's x once the x store has read them
+      if (p.nt4 == 0 && storer) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(x_free);
       }
@@ -491,8 +567,31 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
   if (!opt.ensure(tc_gnn_layer_kernel, (int)kGnSmem)) return false;
   const int ntiles = cdiv(p.rows, 128);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
+#ifdef B200M_GNN_TRACE
+  static long long* tbuf = nullptr;
+  if (getenv("B200M_GNN_TRACE") && !tbuf) {
+    cudaMalloc(&tbuf, 512 * 8);
+    cudaMemset(tbuf, 0, 512 * 8);
+    cudaMemcpyToSymbol(g_gnn_trace, &tbuf, sizeof(tbuf));
+  }
+#endif
   tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gnn_layer");
+#ifdef B200M_GNN_TRACE
+  if (tbuf) {
+    static int n = 0;
+    if (++n == 40) {
+      long long hb[512];
+      cudaMemcpy(hb, tbuf, sizeof(hb), cudaMemcpyDeviceToHost);
+      const long long t0 = hb[200];
+      fprintf(stderr, "GT producer: tile start %lld, x_free wait %lld -> %lld, x reload wait %lld -> %lld\n", hb[0] - t0,
+              hb[1] - t0, hb[2] - t0, hb[3] - t0, hb[4] - t0);
+      for (int i = 0; i < 18; ++i) fprintf(stderr, "GT producer wtile %2d: wait %6lld got %6lld\n", i, hb[10 + 2 * i] - t0, hb[11 + 2 * i] - t0);
+      for (int i = 100; i <= 114; ++i) fprintf(stderr, "GT mma %d: %6lld\n", i, hb[i] - t0);
+      for (int i = 200; i <= 216; ++i) fprintf(stderr, "GT epi %d: %6lld\n", i, hb[i] - t0);
+    }
+  }
+#endif
   return true;
 }
 
