@@ -11,15 +11,24 @@
 //     takes its A operand from tensor memory.  No st.shared, no fence.proxy.async per tile, no p_empty / s_empty
 //     barriers (the tensor pipe executes in issue order: Q.K^T of tile j+2 into the same columns is issued after P.V of
 //     tile j), and the CTA shrinks by the 32 KB of P planes.
-//   * the row sum comes from the tensor core: the V^T tile carries 16 extra rows of ones, so P.V (N = d + 16) also
+//   * d = 32: the row sum comes from the tensor core: the V^T tile carries 16 extra rows of ones, so P.V (N = d + 16) also
 //     accumulates sum_j (p_hi + p_lo)_j -- exactly the weights that multiply V -- next to O.  No FADD per element.
+//     d = 64: the threads keep the sums (the MUFU, not the FMA pipe, paces them there: two MMAs' worth of tensor work per
+//     exponential) so that O needs only d columns and 64-key tiles fit tensor memory (-11 % against 32-key tiles).
 //   * no running maximum: exponentials are taken against a reference that is the row maximum of the FIRST key tile and
 //     only moves when a later p exceeds 2^8 (detected on the packed fp16 words with one HMNMX2 per two elements; rare).
 //     Only then the scores are re-read, the reference is raised and O (with its sum columns) is rescaled in TMEM.
 //   * the hi / lo split uses the sm_100 mixed-precision FMA (fma.rn.f32.f16: x - float(h) in ONE instruction taking the
 //     packed half directly), 2 instructions per element instead of 3.
 //
-// One CTA per (side, pair, head, 128-query tile), two CTAs per SM; key tiles of KT keys stream through a 4-stage TMA ring.
+// One CTA per (side, pair, head, 128-query tile), two CTAs per SM; key tiles of KT = 64 keys stream through a TMA ring
+// (4 stages at d = 32, 2 at d = 64).  Where the time goes at 1024 keys (clock64 stamps of all 4096 CTAs, B200M_ATTN_TRACE):
+// a CTA lives ~27 k cycles -- 1.5 k set-up, 2.0 k until the first score tile, 20.8 k in the 16-tile loop, 2.2 k output, 0.8 k
+// exit sync -- and its slot is re-filled 2.3 k cycles later.  The loop runs at the MUFU rate (two co-resident CTAs: 4 softmax
+// warps per scheduler x 256 MUFU cycles per tile ~ 80 % of the ~1.3 k-cycle tile period); the fixed costs overlap the
+// other CTA's loop, which alone is bound by its single MMA-issuing thread (a warp issues one tcgen05.mma per ~45 cycles
+// whatever its size: 18 per tile).  Tried and measured worse: a persistent two-CTA-per-SM variant (the resident CTAs run
+// in lock step and queue on the tensor pipe: +12 %), P_hi x [V_hi ; V_lo] as one N = 2d MMA with thread-side sums (+4 %).
 //   warp 0      TMA producer : Q tile once, then K / V^T tiles (hi and lo planes), 2-D tensor maps, 128- or 64-byte
 //                              swizzle (= row length), i.e. the canonical K-major swizzled UMMA layouts.  K tiles are
 //                              [keys][d]; V is read from the transposed copy V^T [d][keys] that the q|k|v projection's
@@ -30,6 +39,10 @@
 //   warps 2..9  softmax      : thread = (query row, key half): tcgen05.ld 32 scores, p = ex2.approx((s - ref) c), split,
 //                              tcgen05.st.  The two key halves keep independent references / accumulators (2-way
 //                              split-KV) and are merged once at the end.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -120,14 +133,20 @@ template <int HD, int KT>
 struct TcAttnSmem {
   static constexpr int QROW = HD * 2;                     // bytes per Q / K row (fp16)
   static constexpr int VROW = KT * 2;                     // bytes per V^T row
-  static constexpr int NO = HD + 16;                      // P.V accumulator columns: O (d) | 16 copies of the row sum
+  // P.V accumulator columns per key half.  d = 32: O (d) | 16 copies of the row sum -- the V^T hi tile carries 16 extra
+  // rows of ones, so the tensor core also accumulates sum_j (p_hi + p_lo)_j, exactly the weights that multiply V, and the
+  // softmax threads spend no FADD per element (measured: summing in the threads instead costs 4 % at 1024 keys).
+  // d = 64: O only, the threads keep the row sums; that leaves tensor-memory room for 64-key tiles (2 x 64 S columns +
+  // 2 x 64 O columns), half as many tiles and barrier round trips as the 32-key tiles the ones rows would force.
+  static constexpr bool ONES = HD == 32;
+  static constexpr int NO = ONES ? HD + 16 : HD;
   static constexpr int Q_PLANE = kTaQ * QROW;
   static constexpr int K_PLANE = KT * QROW;
-  static constexpr int VH_PLANE = NO * VROW;              // V^T hi rows followed by 16 rows of ones
+  static constexpr int VH_PLANE = NO * VROW;              // V^T hi rows (followed by the 16 rows of ones)
   static constexpr int VL_PLANE = HD * VROW;
   static constexpr int KV_STAGE = 2 * K_PLANE + VH_PLANE + VL_PLANE;
   static constexpr int KV_TX = 2 * K_PLANE + 2 * VL_PLANE;   // bytes one stage receives by TMA (the ones rows are constant)
-  static constexpr int NKV = 4;                           // K/V ring depth
+  static constexpr int NKV = HD == 32 ? 4 : 2;            // K/V ring depth
   static constexpr int OFF_KV = 2 * Q_PLANE;
   // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring: it is only touched after the last P.V MMA
   // has retired (every TMA load consumed, every MMA complete)
@@ -137,7 +156,7 @@ struct TcAttnSmem {
   static constexpr int OFF_BAR = OFF_KV + NKV * KV_STAGE;
   static constexpr int N_BARS = 1 + 2 * NKV + 2 + 2 + 1 + 1;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
-  static constexpr int TMEM_COLS = 256;                   // S / P double buffer (2 KT) + [O | l] per key half (2 NO)
+  static constexpr int TMEM_COLS = 256;                   // S / P double buffer (2 KT) + O per key half (2 NO)
   static_assert(2 * KT + 2 * NO <= TMEM_COLS, "tensor memory budget (two CTAs per SM)");
   static_assert(2 * BYTES <= 232448, "two CTAs per SM");
 };
@@ -154,21 +173,25 @@ struct TcAttnParams {
 };
 
 // this thread's KH scores -> p = 2^(s c + neg) as packed fp16 hi / lo words; returns the packed maximum of the hi words
-template <int KH>
-__device__ __forceinline__ __half2 softmax_words(const float* s, float c, float neg, uint32_t* hi, uint32_t* lo) {
+// SUM: also returns the sum of the p (otherwise the packed maximum of the hi words, as a float)
+template <int KH, bool SUM>
+__device__ __forceinline__ float softmax_words(const float* s, float c, float neg, uint32_t* hi, uint32_t* lo) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                                    // four chains: the adds hide behind the MUFU
   __half2 pm = __float2half2_rn(0.f);
 #pragma unroll
   for (int i = 0; i < KH / 2; ++i) {
     const float a = fast_exp2(fmaf(s[2 * i], c, neg));                    // exp2(-inf) = 0 for masked keys
     const float b = fast_exp2(fmaf(s[2 * i + 1], c, neg));
+    if constexpr (SUM) acc[i & 3] += a + b;
     const uint32_t h = pack_f16x2(a, b);
     float ra, rb;
     residual_f16x2(h, a, b, ra, rb);
     hi[i] = h;
     lo[i] = pack_f16x2(ra, rb);
-    pm = __hmax2(pm, *reinterpret_cast<const __half2*>(&h));
+    if constexpr (!SUM) pm = __hmax2(pm, *reinterpret_cast<const __half2*>(&h));
   }
-  return pm;
+  if constexpr (SUM) return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  else return __half2float(__hmax(__low2half(pm), __high2half(pm)));
 }
 
 template <int KH>
@@ -179,6 +202,9 @@ __device__ __forceinline__ float row_max(const float* s) {
   return fmaxf(fmaxf(m3[0], m3[1]), fmaxf(m3[2], m3[3]));
 }
 
+#ifdef B200M_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#endif
 template <int HD, int KT>
 __global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
@@ -207,6 +233,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200M_ATTN_TRACE
+  long long* const tr = g_attn_trace ? g_attn_trace + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (tr && threadIdx.x == 64) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tr[0] = sm; tr[1] = clock64(); }
+#endif
   const int head = blockIdx.y;
   const int side = blockIdx.z / p.B, b = blockIdx.z - side * p.B;
   const int src = p.cross ? 1 - side : side;
@@ -217,6 +247,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   const int cq = head * HD, ck = p.D + head * HD;          // first column of this head's q / k
   const int vt_row0 = (src * p.B + b) * p.D + head * HD;   // first row of this head in V^T [block][D][Np]
 
+  // K / V^T tile j -> ring stage j % NKV (one elected thread)
+  auto load_kv = [&](int j) {
+    const int st = j % SM::NKV;
+    mbar_expect_tx(&kv_full[st], SM::KV_TX);
+    uint8_t* dst = sKV + st * SM::KV_STAGE;
+    tma_load_2d(dst, &tm_kv_hi, &kv_full[st], ck, k_row0 + j * KT);
+    tma_load_2d(dst + SM::K_PLANE, &tm_kv_lo, &kv_full[st], ck, k_row0 + j * KT);
+    tma_load_2d(dst + 2 * SM::K_PLANE, &tm_vt_hi, &kv_full[st], j * KT, vt_row0);
+    tma_load_2d(dst + 2 * SM::K_PLANE + SM::VH_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
+  };
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
@@ -227,37 +267,33 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     tma_prefetch_desc(&tm_q_hi); tma_prefetch_desc(&tm_q_lo);
     tma_prefetch_desc(&tm_kv_hi); tma_prefetch_desc(&tm_kv_lo);
     tma_prefetch_desc(&tm_vt_hi); tma_prefetch_desc(&tm_vt_lo);
+    // the first loads go out BEFORE the tensor-memory allocation and the CTA-wide sync below: their L2 / DRAM latency
+    // (~2.6 k cycles to the first score tile) overlaps the ~1.9 k cycles of set-up instead of following it
+    // (Q and tile 0 do not wait for the key count either -- a pair without keys just lets them land, see below)
+    mbar_expect_tx(q_full, 2 * SM::Q_PLANE);
+    tma_load_2d(sQ, &tm_q_hi, q_full, cq, q_row0);
+    tma_load_2d(sQ + SM::Q_PLANE, &tm_q_lo, q_full, cq, q_row0);
+    load_kv(0);
   }
-  // the 16 constant rows of ones under every V^T hi tile (all elements equal, so the swizzle does not matter)
-  for (int i = threadIdx.x; i < SM::NKV * 16 * SM::VROW / 16; i += blockDim.x) {
-    const int stg = i / (16 * SM::VROW / 16), r = i - stg * (16 * SM::VROW / 16);
-    *reinterpret_cast<uint4*>(sKV + stg * SM::KV_STAGE + 2 * SM::K_PLANE + HD * SM::VROW + r * 16) =
-        make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-  }
-  fence_proxy_async();
   if (warp == 1) tmem_alloc(tmem_slot, SM::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 2 * KT;
+#ifdef B200M_ATTN_TRACE
+  if (tr && threadIdx.x == 64) tr[2] = clock64();
+#endif
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (T > 0) {
-      mbar_expect_tx(q_full, 2 * SM::Q_PLANE);
-      tma_load_2d(sQ, &tm_q_hi, q_full, cq, q_row0);
-      tma_load_2d(sQ + SM::Q_PLANE, &tm_q_lo, q_full, cq, q_row0);
+    // ------------------------------------------------------------------ TMA producer (Q and tile 0 are on their way)
+    for (int j = 1; j < T; ++j) {
+      if (j >= SM::NKV) mbar_wait(&kv_empty[j % SM::NKV], ((j / SM::NKV) & 1) ^ 1);
+      load_kv(j);
     }
-    for (int j = 0; j < T; ++j) {
-      const int st = j % SM::NKV, ph = (j / SM::NKV) & 1;
-      mbar_wait(&kv_empty[st], ph ^ 1);
-      mbar_expect_tx(&kv_full[st], SM::KV_TX);
-      uint8_t* dst = sKV + st * SM::KV_STAGE;
-      tma_load_2d(dst, &tm_kv_hi, &kv_full[st], ck, k_row0 + j * KT);
-      tma_load_2d(dst + SM::K_PLANE, &tm_kv_lo, &kv_full[st], ck, k_row0 + j * KT);
-      tma_load_2d(dst + 2 * SM::K_PLANE, &tm_vt_hi, &kv_full[st], j * KT, vt_row0);
-      tma_load_2d(dst + 2 * SM::K_PLANE + SM::VH_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
+    if (T == 0) {                      // nothing consumes the early loads: they must have landed before the CTA exits
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp)
@@ -303,7 +339,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             const uint64_t vh = smem_desc_sw<SM::VROW>(v_base + ks * 32);
             const uint64_t vl = smem_desc_sw<SM::VROW>(v_base + SM::VH_PLANE + ks * 32);
             const uint32_t dO = tO + hf * NO;              // independent accumulators per key half
-            mma_f16_ts(dO, a_hi, vh, idesc_o, (j > 0) || kl != 0);       // accumulates across key tiles
+            const uint32_t acc = (j > 0) || kl != 0;       // accumulates across key tiles
+            mma_f16_ts(dO, a_hi, vh, idesc_o, acc);
             mma_f16_ts(dO, a_lo, vh, idesc_o, 1);
             mma_f16_ts(dO, a_hi, vl, idesc_v, 1);
           }
@@ -325,7 +362,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     const float c = p.scale_log2e;
     const uint32_t tS_mine = tS + lane_base + half * KH;
     const uint32_t tO_mine = tO + lane_base + half * NO;
+    if constexpr (SM::ONES) {
+      // the 16 constant rows of ones under every V^T hi tile (all elements equal, so the swizzle does not matter).  Written
+      // here, while the first score tile is still on its way, instead of before the CTA-wide sync; the first P.V that
+      // reads them is issued after this thread's p_full arrival.
+      for (int i = threadIdx.x - 64; i < SM::NKV * 16 * SM::VROW / 16; i += 256) {
+        const int stg = i / (16 * SM::VROW / 16), r = i - stg * (16 * SM::VROW / 16);
+        *reinterpret_cast<uint4*>(sKV + stg * SM::KV_STAGE + 2 * SM::K_PLANE + HD * SM::VROW + r * 16) =
+            make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+      }
+      fence_proxy_async();
+    }
     float m_ref = 0.f;                // reference the exponentials are taken against (log-2 domain after * c)
+    float l_run = 0.f;                // sum of this key half's weights (every p is hi + lo to 2^-22: the sum the P.V MMAs apply)
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
@@ -338,14 +387,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         for (int i = 0; i < KH; ++i)
           if (kbase + i >= n_k) s[i] = -INFINITY;
       }
+#ifdef B200M_ATTN_TRACE
+      if (tr && threadIdx.x == 64 && j == 0) tr[3] = clock64();
+#endif
       if (j == 0) {                                   // the reference starts as the first tile's row maximum
         const float mx = row_max<KH>(s);
         m_ref = mx > -INFINITY ? mx : 0.f;
       }
       uint32_t hi[PW], lo[PW];
-      __half2 pm = softmax_words<KH>(s, c, -m_ref * c, hi, lo);
-      // a p above 2^8 (or an fp16 overflow to +inf): raise the reference and rescale what was accumulated so far
-      const bool trig = __hgt(__hmax(__low2half(pm), __high2half(pm)), __float2half_rn(256.f));
+      // l_tile: the tile's row sum (d = 64) or its largest fp16 weight (d = 32, where the tensor core keeps the sums)
+      float l_tile = softmax_words<KH, !SM::ONES>(s, c, -m_ref * c, hi, lo);
+      // a weight above 2^8 (d = 64: a tile sum above 2^10, so no weight exceeds that; +inf if an exponential overflowed):
+      // raise the reference and rescale what was accumulated so far
+      const bool trig = l_tile > (SM::ONES ? 256.f : 1024.f);
       if (j > 0 && __any_sync(0xffffffffu, trig)) {
         // warp-uniform path (tcgen05.ld / .st are warp-collective); rows that did not trigger keep factor 1
         float f = 1.f;
@@ -356,8 +410,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         }
         mbar_wait(pv_done, (j - 1) & 1);               // P.V of tile j-1 retired (it cannot be further: it needs our P_j)
         tc_fence_after();
+        l_run *= f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < NO; c0 += 16) {          // [O | l] of this key half, 16 columns at a time
+        for (int c0 = 0; c0 < NO; c0 += 16) {          // O of this key half, 16 columns at a time
           float ot[16];
           uint32_t ow[16];
           tmem_ld_n<16>(tO_mine + c0, ot);
@@ -366,8 +421,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
           tmem_st16(tO_mine + c0, ow);
           tmem_st_wait();      // tcgen05.st reads its source registers asynchronously: they are reused by the next chunk
         }
-        pm = softmax_words<KH>(s, c, -m_ref * c, hi, lo);
+        l_tile = softmax_words<KH, !SM::ONES>(s, c, -m_ref * c, hi, lo);
       }
+      if constexpr (!SM::ONES) l_run += l_tile;
       // P_j (A operand of the P.V MMA) over this thread's own S columns: [hi words | lo words]
       tmem_st_words<PW>(tS_mine + st * KT, hi);
       tmem_st_words<PW>(tS_mine + st * KT + PW, lo);
@@ -376,7 +432,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
     }
-    // ---- [O | l] of this key half: one TMEM read after the last P.V
+#ifdef B200M_ATTN_TRACE
+    if (tr && threadIdx.x == 64) tr[4] = clock64();
+#endif
+    // ---- O of this key half: one TMEM read after the last P.V
     float o[NO];
 #pragma unroll
     for (int i = 0; i < NO; ++i) o[i] = 0.f;
@@ -386,7 +445,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       tmem_ld_n<NO>(tO_mine, o);
       tc_fence_before();
     }
-    const float l_run = o[HD];                        // sum of the weights, accumulated by the tensor core
+    if constexpr (SM::ONES) l_run = o[HD];            // sum of the weights, accumulated by the tensor core
     const float m_run = l_run > 0.f ? m_ref : -INFINITY;   // no valid key in this half: contributes nothing to the merge
     // ---- merge the two key halves
     float* xch = sX + (size_t)m * (HD + 2);
@@ -435,12 +494,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       }
     }
   }
+#ifdef B200M_ATTN_TRACE
+  if (tr && threadIdx.x == 64) tr[5] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, SM::TMEM_COLS);
   }
+#ifdef B200M_ATTN_TRACE
+  if (tr && threadIdx.x == 64) tr[6] = clock64();
+#endif
 }
 
 // 2-D view of a [rows][ld] fp16 plane; box = box_cols x box_rows with the swizzle that matches the row length
@@ -479,8 +544,47 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
   p.cross = cross ? 1 : 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   dim3 grid(cdiv(Np, kTaQ), heads, 2 * B);
+#ifdef B200M_ATTN_TRACE
+  static long long* tbuf = nullptr;
+  const int ncta = grid.x * grid.y * grid.z;
+  static int n = 0;
+  ++n;
+  if (getenv("B200M_ATTN_TRACE") && n == 40) {
+    cudaMalloc(&tbuf, (size_t)ncta * 64);
+    cudaMemset(tbuf, 0, (size_t)ncta * 64);
+    cudaMemcpyToSymbol(g_attn_trace, &tbuf, sizeof(tbuf));
+  }
+#endif
   kern<<<grid, 320, SM::BYTES, ctx.stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_attention");
+#ifdef B200M_ATTN_TRACE
+  if (tbuf && n == 40) {
+    std::vector<long long> hb((size_t)ncta * 8);
+    cudaMemcpy(hb.data(), tbuf, hb.size() * 8, cudaMemcpyDeviceToHost);
+    long long* nul = nullptr;
+    cudaMemcpyToSymbol(g_attn_trace, &nul, sizeof(nul));
+    // per SM: CTAs sorted by start; report mean phases and the idle gap between a CTA's end and the next start on the SM
+    std::vector<std::vector<std::pair<long long, int>>> per_sm(256);
+    for (int i = 0; i < ncta; ++i) per_sm[hb[8 * i] & 255].push_back({hb[8 * i + 1], i});
+    double setup = 0, first = 0, loop = 0, epi = 0, exitc = 0, life = 0, span = 0; long long cnt = 0; int nsm = 0;
+    for (auto& v : per_sm) {
+      if (v.empty()) continue;
+      ++nsm;
+      std::sort(v.begin(), v.end());
+      long long t_first = v.front().first, t_last = 0;
+      for (auto& e : v) {
+        const long long* r = &hb[8 * e.second];
+        setup += r[2] - r[1]; first += r[3] - r[2]; loop += r[4] - r[3]; epi += r[5] - r[4]; exitc += r[6] - r[5]; life += r[6] - r[1];
+        t_last = std::max(t_last, r[6]); ++cnt;
+      }
+      span += t_last - t_first;
+    }
+    fprintf(stderr, "ATTN trace: %d CTAs on %d SMs; per CTA mean cycles: setup %.0f, to first S %.0f, tile loop %.0f, output %.0f, exit sync %.0f, life %.0f; per SM span %.0f => %.0f per CTA slot (2 slots)\n",
+            ncta, nsm, setup / cnt, first / cnt, loop / cnt, epi / cnt, exitc / cnt, life / cnt, span / nsm, span / nsm / (cnt / (double)nsm) * 2);
+    // one SM in detail
+    for (auto& v : per_sm) if (!v.empty()) { for (size_t i = 0; i < v.size() && i < 12; ++i) { const long long* r = &hb[8 * v[i].second]; fprintf(stderr, "  cta %5d start %8lld end %8lld\n", v[i].second, r[1] - v[0].first, r[6] - v[0].first); } break; }
+  }
+#endif
   return true;
 }
 
@@ -493,7 +597,7 @@ bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo,
   if (Np % 8) return false;   // V^T rows must be 16-byte multiples for TMA
   // hd = 16 (D = 64) rows would be 32 B; the fp32 CUDA-core kernel handles that model
   if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
-  if (hd == 64) return launch_tc_attn_t<64, 32>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
+  if (hd == 64) return launch_tc_attn_t<64, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
   return false;
 }
 

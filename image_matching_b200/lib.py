@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200match.so")
+# B200M_LIB: developer override (A/B timing of two builds); the in-tree library is the product
+LIB_PATH = os.environ.get("B200M_LIB") or os.path.join(_HERE, "libb200match.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_KENC = 8
