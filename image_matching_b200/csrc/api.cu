@@ -98,6 +98,9 @@ struct b200m_handle {
   bool use_tc_gemm = true;       // tcgen05 linear layers (B200M_GEMM_IMPL=simt selects the fp32 CUDA-core GEMM)
   bool use_fused_stem = true;    // first conv computed inside the second conv's kernel (B200M_STEM_IMPL=unfused: two kernels)
   bool use_fused_gnn = true;     // fused merge/mlp/residual/q|k|v layer kernel (B200M_GNN_IMPL=unfused: four GEMM launches)
+  // precision experiment, never set in the product: B200M_SINGLE=desc,gemm,gnn,attn (any subset) drops the lo planes'
+  // products in the descriptor head / SuperGlue GEMMs / fused layer / attention (profiles/r02_single_product_experiment.md)
+  bool single_desc = false, single_gemm = false, single_gnn = false, single_attn = false;
   int num_sms = 148;
   int sp_micro_batch = 0;        // > 0: B200M_SP_MICROBATCH override of the images per SuperPoint micro-batch
   // CUDA-graph replay of whole forward calls (see with_graph below)
@@ -557,9 +560,11 @@ void run_conv(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* 
 // surfaced through finish(): the output buffer would otherwise be consumed unwritten.
 void run_conv_tc(b200m_handle* h, LaunchCtx& ctx, const ConvLayer& L, const float* in_hi, const float* in_lo,
                  float* out_hi, float* out_lo, int out_c4_total, int n, int H, int W, bool pool, int* overflow,
-                 bool relu = true, int in_c8_total = 0, int in_c8_off = 0, float* sumsq = nullptr) {
+                 bool relu = true, int in_c8_total = 0, int in_c8_off = 0, float* sumsq = nullptr,
+                 int single_from_cb = 1 << 30) {
   TcConvParams p;
   p.sumsq = sumsq;
+  p.single_from_cb = single_from_cb;
   p.in_hi = in_hi; p.in_lo = in_lo; p.wpk = h->d_w + L.tc_w_off; p.bias = h->d_w + L.b_off;
   p.out_hi = out_hi; p.out_lo = out_lo; p.out_c4_total = out_c4_total; p.out_c4_off = 0; p.overflow = overflow;
   p.cin = L.cin; p.cout_pad = L.cout_pad; p.nb = L.nb; p.n = n; p.H = H; p.W = W; p.relu = relu ? 1 : 0;
@@ -615,12 +620,14 @@ void sp_dense(b200m_handle* h, LaunchCtx& ctx, const SpDims& d, const SpWs& w, c
     run_conv_tc(h, ctx, h->c3b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.H3, d.W3, true, ovf);     // -> 128 x hc x wc
     run_conv_tc(h, ctx, h->c4a, w.p1, w.p1_lo, w.p0, w.p0_lo, 16, n, d.hc, d.wc, false, ovf);
     run_conv_tc(h, ctx, h->c4b, w.p0, w.p0_lo, w.p1, w.p1_lo, 16, n, d.hc, d.wc, false, ovf);    // x4
-    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, w.p0_lo, 64, n, d.hc, d.wc, false, ovf);  // cPa | cDa (512 ch)
+    // cPa | cDa (512 ch = four 128-channel column blocks; the experiment's single-product part is cDa = blocks 2, 3)
+    run_conv_tc(h, ctx, h->heads, w.p1, w.p1_lo, w.p0, w.p0_lo, 64, n, d.hc, d.wc, false, ovf, true, 0, 0, nullptr,
+                h->single_desc ? 2 : 1 << 30);
     // 1x1 heads on the same pipeline (one tap per K block), full fp32 C4-planar outputs
     run_conv_tc(h, ctx, h->pb, w.p0, w.p0_lo, w.semi, nullptr, 32, n, d.hc, d.wc, false, ovf, false, 64, 0);
     // descriptor head: raw descriptors + per-pixel sums of squares (the L2 normalisation is applied by the sampler)
     run_conv_tc(h, ctx, h->db, w.p0, w.p0_lo, w.draw, nullptr, d.dpad / 4, n, d.hc, d.wc, false, ovf, false, 64, 32,
-                w.sumsq);
+                w.sumsq, h->single_desc ? 0 : 1 << 30);
     return;
   } else {
     images = fp32_images();
@@ -741,6 +748,7 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.alpha = 1.f; p.relu = relu ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
   p.C_lo = C_lo; p.out_f16 = C_lo ? 1 : 0;
   p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np; p.lo_scale = lo_scale;
+  p.single = h->single_gemm ? 1 : 0;
   if (h->use_tc_gemm && launch_tc_gemm(ctx, p, h->d_w + L.w_hi_off, h->d_w + L.w_lo_off, h->num_sms)) return;
   launch_gemm(ctx, p);
 }
@@ -789,7 +797,7 @@ void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0
       const b200m_handle::Gnn& G = h->gnn[l];
       const bool cross = h->cfg.gnn_cross[l] != 0;
       bool ok = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, nullptr, B, w.Np, D, kHeads, c0, c1, N, M,
-                                    cross, att_hi, att_lo);
+                                    cross, att_hi, att_lo, h->single_attn);
       GnnFusedParams p;
       p.wts = reinterpret_cast<const uint8_t*>(h->d_w + G.fused_w_off);
       p.bias = h->d_w + G.fused_b_off;
@@ -799,6 +807,7 @@ void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0
       p.rows = (int)w.rows;
       p.nt4 = (l + 1 < l_end && G.fused_has_qkv) ? 3 : 0;
       p.overflow = nullptr;
+      p.single = h->single_gnn ? 1 : 0;
       ok = ok && launch_tc_gnn_layer(ctx, p, att_hi, att_lo, h->num_sms);
       if (!ok && ctx.err == cudaSuccess) {
         ctx.err = cudaErrorLaunchFailure;
@@ -813,7 +822,8 @@ void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0
     bool done = false;
     if (h->use_tc_attn) {
       run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false, w.QKV_lo, w.VT, w.VT_lo, 2 * D, w.Np);
-      done = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, cross);
+      done = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, w.MSG, B, w.Np, D, kHeads, c0, c1, N, M, cross,
+                                 nullptr, nullptr, h->single_attn);
     }
     if (!done) {
       run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false);
@@ -841,6 +851,7 @@ void sg_scores(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, int N, int
     run_linear(h, ctx, h->final_proj, w.X + side * 2 * D, 2 * D, w.QKV, D, side, false, false, w.QKV_lo, nullptr, nullptr,
                0, 1, 2048.f);
     p.batch_rows_a = w.Np; p.batch_rows_b = w.Np;
+    p.single = h->single_gemm ? 1 : 0;
     if (launch_tc_gemm(ctx, p, w.QKV, w.QKV_lo, h->num_sms)) return;
   }
   launch_gemm(ctx, p);
@@ -936,6 +947,13 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_fused_stem = !(impl && strcmp(impl, "unfused") == 0);
   impl = getenv("B200M_GNN_IMPL");
   h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
+  impl = getenv("B200M_SINGLE");
+  if (impl) {
+    h->single_desc = strstr(impl, "desc") != nullptr;
+    h->single_gemm = strstr(impl, "gemm") != nullptr;
+    h->single_gnn = strstr(impl, "gnn") != nullptr;
+    h->single_attn = strstr(impl, "attn") != nullptr;
+  }
   impl = getenv("B200M_GRAPHS");
   h->use_graphs = !(impl && strcmp(impl, "0") == 0);
   impl = getenv("B200M_SP_MICROBATCH");

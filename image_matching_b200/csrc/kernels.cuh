@@ -66,6 +66,9 @@ struct TcConvParams {
   // epilogue also writes sum_c out[c]^2 over the tile's nb channels per pixel to sumsq[image][cout block][H][W]; the
   // descriptor sampler divides by the norm, so the normalised dense map never exists in HBM
   float* sumsq = nullptr;
+  // precision experiment (B200M_SINGLE=desc, profiles/r02_single_product_experiment.md): column blocks >= single_from_cb
+  // are computed from the hi planes only (one fp16 product instead of three)
+  int single_from_cb = 1 << 30;
 };
 bool launch_tc_conv(LaunchCtx& ctx, const TcConvParams& p, int num_sms);
 size_t tc_conv_weight_floats(int cin, int cout_pad, int nb, int ks);
@@ -131,6 +134,7 @@ struct GemmParams {
   float lo_scale = 1.f;        // out_f16: C_lo = fp16((v - C) * lo_scale)  (2048 for planes consumed as the weight operand)
   // tensor-core GEMM, batch > 1: rows of A / W of problem b start at b * batch_rows_a / b * batch_rows_b of the same arrays
   int batch_rows_a = 0, batch_rows_b = 0;
+  int single = 0;              // precision experiment (B200M_SINGLE=gemm): hi planes only
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
 // tcgen05 fp16x3 version for weight GEMMs (w_hi / w_lo: [N][K] fp16 planes, lo scaled by 2048); false if declined
@@ -155,7 +159,7 @@ void launch_attention(LaunchCtx& ctx, const float* qkv, float* msg, int B, int N
 bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                          const void* vt_lo, float* msg, int B, int Np, int D,
                          int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross,
-                         void* msg_hi = nullptr, void* msg_lo = nullptr);
+                         void* msg_hi = nullptr, void* msg_lo = nullptr, bool single = false);
 
 // ------------------------------------------------------------------ fused GNN layer tail (tc_gnn.cu), D = 128
 // merge -> mlp -> residual -> next layer's q|k|v in one kernel; activations never leave the SM between the GEMMs
@@ -168,6 +172,7 @@ struct GnnFusedParams {
   int rows;
   int nt4;                   // 3: also produce the next layer's q|k|v; 0: last layer
   int* overflow;             // sticky flag: a state left the fp16 range (or null)
+  int single = 0;            // precision experiment (B200M_SINGLE=gnn): hi planes only
 };
 bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* att_hi, const void* att_lo, int num_sms);
 size_t gnn_fused_weight_floats(bool with_qkv);

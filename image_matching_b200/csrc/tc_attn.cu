@@ -170,6 +170,7 @@ struct TcAttnParams {
   int n_full0, n_full1;
   int cross;
   float scale_log2e;       // log2(e) / sqrt(d)
+  int single;              // precision experiment (B200M_SINGLE=attn): hi planes only
 };
 
 // this thread's KH scores -> p = 2^(s c + neg) as packed fp16 hi / lo words; returns the packed maximum of the hi words
@@ -315,8 +316,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             const uint64_t kh = smem_desc_sw<SM::QROW>(k_base + ks * 32);
             const uint64_t kl = smem_desc_sw<SM::QROW>(k_base + SM::K_PLANE + ks * 32);
             mma_bf16(tS + st * KT, qh, kh, idesc_s, ks != 0);
-            mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
-            mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
+            if (!p.single) {
+              mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
+              mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
+            }
           }
           tc_commit(&s_full[st]);
         }
@@ -341,8 +344,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             const uint32_t dO = tO + hf * NO;              // independent accumulators per key half
             const uint32_t acc = (j > 0) || kl != 0;       // accumulates across key tiles
             mma_f16_ts(dO, a_hi, vh, idesc_o, acc);
-            mma_f16_ts(dO, a_lo, vh, idesc_o, 1);
-            mma_f16_ts(dO, a_hi, vl, idesc_v, 1);
+            if (!p.single) {
+              mma_f16_ts(dO, a_lo, vh, idesc_o, 1);
+              mma_f16_ts(dO, a_hi, vl, idesc_v, 1);
+            }
           }
           tc_commit(&kv_empty[j % SM::NKV]);
           tc_commit(pv_done);
@@ -527,7 +532,7 @@ template <int HD, int KT>
 static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                              const void* vt_lo, float* msg, int B, int Np,
                              int D, int heads, const int* c0, const int* c1, int nf0, int nf1, bool cross,
-                             void* msg_hi, void* msg_lo) {
+                             void* msg_hi, void* msg_lo, bool single) {
   ProfScope prof__(ctx, "tc_attention");
   const size_t rows = (size_t)2 * B * Np;
   CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
@@ -542,6 +547,7 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
   TcAttnParams p;
   p.msg = msg; p.msg_hi = reinterpret_cast<__half*>(msg_hi); p.msg_lo = reinterpret_cast<__half*>(msg_lo); p.B = B; p.Np = Np; p.D = D; p.counts0 = c0; p.counts1 = c1; p.n_full0 = nf0; p.n_full1 = nf1;
   p.cross = cross ? 1 : 0;
+  p.single = single ? 1 : 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   dim3 grid(cdiv(Np, kTaQ), heads, 2 * B);
 #ifdef B200M_ATTN_TRACE
@@ -592,12 +598,12 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
 bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
                          const void* vt_lo, float* msg, int B, int Np, int D,
                          int heads, const int* counts0, const int* counts1, int n_full0, int n_full1, bool cross,
-                         void* msg_hi, void* msg_lo) {
+                         void* msg_hi, void* msg_lo, bool single) {
   const int hd = D / heads;
   if (Np % 8) return false;   // V^T rows must be 16-byte multiples for TMA
   // hd = 16 (D = 64) rows would be 32 B; the fp32 CUDA-core kernel handles that model
-  if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
-  if (hd == 64) return launch_tc_attn_t<64, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo);
+  if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo, single);
+  if (hd == 64) return launch_tc_attn_t<64, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo, single);
   return false;
 }
 

@@ -188,6 +188,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       mbar_wait(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + buf * (4 * NB);
+      const bool single = (tile % ncb) >= p.single_from_cb;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
@@ -211,8 +212,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const uint64_t al = a_hi32 | (uint64_t)(a_lo16 | (((a_off + kTcAPlane) >> 4) & 0x3FFF));
               const uint32_t d = d0 + sub * (2 * NB);      // main accumulator; cross accumulator at d + NB
               const uint32_t acc = (kb | tap | ks) != 0;
-              mma_bf16(d, ah, bw, idesc2, acc);         // kind::f16: [A_hi W_hi^T | A_hi W_lo^T]
-              mma_bf16(d + NB, al, bw, idesc1, 1);      // + A_lo W_hi^T (first NB rows of the chunk)
+              if (single) {
+                mma_bf16(d, ah, bw, idesc1, acc);       // experiment: A_hi W_hi^T only
+              } else {
+                mma_bf16(d, ah, bw, idesc2, acc);       // kind::f16: [A_hi W_hi^T | A_hi W_lo^T]
+                mma_bf16(d + NB, al, bw, idesc1, 1);    // + A_lo W_hi^T (first NB rows of the chunk)
+              }
             }
           }
           if (!RESIDENT) tc_commit(&b_empty[sb]);
@@ -308,6 +313,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       const int aph = SM::ACC_BUFS == 2 ? ((lt >> 1) & 1) : (lt & 1);
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
+      const float cross_scale = cb >= p.single_from_cb ? 0.f : 1.f / kLoScale;   // experiment: no cross accumulator
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const int x = x0 + sub * 8 + xs, y = y0 + ys;
@@ -340,7 +346,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = fmaf(vc[j], 1.f / kLoScale, v[j]) + bj[j];
+            float t = (cross_scale != 0.f ? fmaf(vc[j], cross_scale, v[j]) : v[j]) + bj[j];
             if (p.relu) t = fmaxf(t, 0.f);
             if (POOL) {
               t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));

@@ -105,8 +105,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint64_t ah = smem_desc_sw128(a_hi + ks * 32), al = smem_desc_sw128(a_lo + ks * 32);
           const uint64_t wh = smem_desc_sw128(w_hi + ks * 32), wl = smem_desc_sw128(w_lo + ks * 32);
           mma_bf16(d, ah, wh, idesc, (kb | ks) != 0);             // kind::f16, fp16 operands (idesc)
-          mma_bf16(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
-          mma_bf16(d + kGemmNT, al, wh, idesc, 1);
+          if (!p.single) {
+            mma_bf16(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
+            mma_bf16(d + kGemmNT, al, wh, idesc, 1);
+          }
         }
         tc_commit(&empty[s]);
         if (kb == nkb - 1) tc_commit(&acc_full[buf]);
@@ -171,7 +173,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (c0 >= p.N) continue;           // uniform per warp
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = p.alpha * fmaf(vc[j], 1.f / 2048.f, v[j]) + (p.bias ? __ldg(p.bias + min(c0 + j, p.N - 1)) : 0.f);
+          float t = p.alpha * (p.single ? v[j] : fmaf(vc[j], 1.f / 2048.f, v[j])) + (p.bias ? __ldg(p.bias + min(c0 + j, p.N - 1)) : 0.f);
           if (p.relu) t = fmaxf(t, 0.f);
           v[j] = t;
         }
