@@ -205,14 +205,57 @@ class CpuArm:
         """Bounded sample: up to n_pairs pairs, stopping early once budget_s of CPU work is spent."""
         self.run(self.inputs(seeds_from - 1))                 # warm-up (thread pool, page faults)
         inps = [self.inputs(seeds_from + i) for i in range(n_pairs)]
+        self.results = []                                     # (inputs, prediction) of every timed pair: parity_vs_cpu()
         done, t0 = 0, time.perf_counter()
         for inp in inps:
-            self.run(inp)
+            self.results.append((inp, self.run(inp)))
             done += 1
             if time.perf_counter() - t0 > budget_s:
                 break
         dt = time.perf_counter() - t0
         return done / dt, dt, done
+
+
+def parity_vs_cpu(arm, m, dev):
+    """The pairs the CPU arm just timed, once more through the CUDA path (one pair per call, like the reference's
+    caller): keypoint-set and match-pair differences against the CPU arm's own results.  A checker riding on the
+    cpu_baseline leg -- it runs after every timed region."""
+    import torch
+
+    def arr(x):
+        return np.asarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x)
+
+    def kp_set(k):
+        return set(map(tuple, arr(k).astype(np.int64).tolist()))
+
+    def pairs(k0, k1, m0):
+        k0, k1 = arr(k0).astype(np.int64), arr(k1).astype(np.int64)
+        return {(tuple(k0[i]), tuple(k1[j])) for i, j in enumerate(arr(m0).tolist()) if j >= 0}
+
+    nk = kf = nm = mf = 0
+    for inp, ref in arm.results:
+        if arm.c["kind"] == "matching":
+            a, b = inp
+            got = m({"image0": torch.from_numpy(a[None, None]).to(dev), "image1": torch.from_numpy(b[None, None]).to(dev)})
+            gk0, gk1 = got["keypoints0"][0], got["keypoints1"][0]
+            rk0, rk1 = ref["keypoints0"], ref["keypoints1"]
+            if arm.kind == "reference":               # lists of per-image tensors; the port returns the single pair's arrays
+                rk0, rk1 = rk0[0], rk1[0]
+            for r, g in ((rk0, gk0), (rk1, gk1)):
+                nk += len(kp_set(r))
+                kf += len(kp_set(r) ^ kp_set(g))
+        else:
+            keys = ["keypoints0", "scores0", "descriptors0", "keypoints1", "scores1", "descriptors1"]
+            z = torch.zeros(1, 1, arm.c["H"], arm.c["W"], device=dev)
+            got = m(dict(zip(keys, [torch.from_numpy(x).to(dev) for x in inp]), image0=z, image1=z))
+            rk0 = gk0 = inp[0][0]
+            rk1 = gk1 = inp[3][0]
+        rm0 = arr(ref[0] if isinstance(ref, tuple) else ref["matches0"])
+        rp, gp = pairs(rk0, rk1, rm0[0] if rm0.ndim == 2 else rm0), pairs(gk0, gk1, arr(got["matches0"])[0])
+        nm += len(rp)
+        mf += len(rp ^ gp)
+    return {"pairs": len(arm.results), "keypoints": nk, "keypoint_flips": kf, "matches": nm, "match_flips": mf,
+            "against": arm.what}
 
 
 def c5_features(seed, B, c):
@@ -577,6 +620,7 @@ def run_b200(args, cname, c):
             v, dt, done = arm.pairs_per_s(args.cpu_pairs, args.cpu_budget)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind,
                                     "sample": f"{done} pairs of the {cname} workload through {arm.what} ({dt:.1f} s)"}
+            line["parity_vs_cpu_arm"] = parity_vs_cpu(arm, m, dev)
         _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
