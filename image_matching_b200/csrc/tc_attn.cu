@@ -3,6 +3,7 @@
 // (x = hi + lo, hi = fp16(x), lo = fp16(x - hi); every product is hi*hi + hi*lo + lo*hi, exact in the fp32
 // accumulator; |q|,|k|,|v| = O(1) and p in [0, 2^8], so the unscaled lo term costs < 3e-8 relative).
 // Reference: superglue/models/superglue_test.py:85-89 (attention), :92-107 (MultiHeadedAttention).
+// Instantiated for head_dim 16 / 32 / 64 (descriptor_dim 64 / 128 / 256: the widths of the reference's SuperPoint checkpoints).
 //
 // Round-2 rewrite.  The round-1 kernel spent ~12 instructions per score element in the softmax warps (issue-bound:
 // 5.9 ms per 64-pair step against a 2.3 ms MUFU floor); this version needs ~4.5:
@@ -113,17 +114,17 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// K-major swizzled descriptor for rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); 8-row groups are
-// 8*ROWB bytes apart
+// K-major swizzled descriptor for rows of ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B, 32 -> SWIZZLE_32B); 8-row
+// groups are 8*ROWB bytes apart
 template <int ROWB>
 __device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr) {
-  static_assert(ROWB == 128 || ROWB == 64, "row length must be 64 or 128 bytes");
+  static_assert(ROWB == 128 || ROWB == 64 || ROWB == 32, "row length must be 32, 64 or 128 bytes");
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)((8 * ROWB) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
+  d |= (uint64_t)(ROWB == 128 ? 2 : ROWB == 64 ? 4 : 6) << 61;
   return d;
 }
 
@@ -138,7 +139,7 @@ struct TcAttnSmem {
   // softmax threads spend no FADD per element (measured: summing in the threads instead costs 4 % at 1024 keys).
   // d = 64: O only, the threads keep the row sums; that leaves tensor-memory room for 64-key tiles (2 x 64 S columns +
   // 2 x 64 O columns), half as many tiles and barrier round trips as the 32-key tiles the ones rows would force.
-  static constexpr bool ONES = HD == 32;
+  static constexpr bool ONES = HD <= 32;
   static constexpr int NO = ONES ? HD + 16 : HD;
   static constexpr int Q_PLANE = kTaQ * QROW;
   static constexpr int K_PLANE = KT * QROW;
@@ -146,13 +147,14 @@ struct TcAttnSmem {
   static constexpr int VL_PLANE = HD * VROW;
   static constexpr int KV_STAGE = 2 * K_PLANE + VH_PLANE + VL_PLANE;
   static constexpr int KV_TX = 2 * K_PLANE + 2 * VL_PLANE;   // bytes one stage receives by TMA (the ones rows are constant)
-  static constexpr int NKV = HD == 32 ? 4 : 2;            // K/V ring depth
+  static constexpr int NKV = HD <= 32 ? 4 : 2;            // K/V ring depth
   static constexpr int OFF_KV = 2 * Q_PLANE;
   // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring: it is only touched after the last P.V MMA
   // has retired (every TMA load consumed, every MMA complete)
   static constexpr int OFF_X = OFF_KV;
   static_assert(kTaQ * (HD + 2) * 4 <= NKV * KV_STAGE, "exchange buffer must fit in the aliased region");
-  static_assert(K_PLANE % 1024 == 0 && VH_PLANE % 512 == 0 && KV_STAGE % 1024 == 0, "swizzle atom alignment");
+  static_assert(K_PLANE % (8 * QROW) == 0 && Q_PLANE % 1024 == 0 && VH_PLANE % 512 == 0 && KV_STAGE % 1024 == 0,
+                "swizzle atom alignment");
   static constexpr int OFF_BAR = OFF_KV + NKV * KV_STAGE;
   static constexpr int N_BARS = 1 + 2 * NKV + 2 + 2 + 1 + 1;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
@@ -521,7 +523,8 @@ static bool make_f16_map(CUtensorMap* m, const void* base, size_t rows, size_t c
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -601,7 +604,7 @@ bool launch_tc_attention(LaunchCtx& ctx, const void* qkv_hi, const void* qkv_lo,
                          void* msg_hi, void* msg_lo, bool single) {
   const int hd = D / heads;
   if (Np % 8) return false;   // V^T rows must be 16-byte multiples for TMA
-  // hd = 16 (D = 64) rows would be 32 B; the fp32 CUDA-core kernel handles that model
+  if (hd == 16) return launch_tc_attn_t<16, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo, single);
   if (hd == 32) return launch_tc_attn_t<32, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo, single);
   if (hd == 64) return launch_tc_attn_t<64, 64>(ctx, qkv_hi, qkv_lo, vt_hi, vt_lo, msg, B, Np, D, heads, counts0, counts1, n_full0, n_full1, cross, msg_hi, msg_lo, single);
   return false;

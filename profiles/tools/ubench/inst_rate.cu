@@ -24,6 +24,9 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, int ite
       if (OP == 5) asm volatile("{.reg .b32 t; max.f16x2 t, %0, %1; max.f16x2 %0, t, %2;}" : "+r"(h[i]) : "r"(h[(i + 1) & 7]), "r"(h[(i + 2) & 7]));
       if (OP == 6) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(1.5f));
       if (OP == 7) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(h[i]) : "r"(h[(i + 1) & 7]), "r"(0x12345u));
+      if (OP == 10) { unsigned long long v = ((unsigned long long)__float_as_uint(a[(i + 1) & 7]) << 32) | __float_as_uint(a[i]);
+                      asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(0x3f8003473f800347ull), "l"(0x3f0000003f000000ull));
+                      a[i] = __uint_as_float((uint32_t)v); if (i == 7) a[0] += __uint_as_float((uint32_t)(v >> 32)) * 1e-30f; }
       if (OP == 8) { asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] = __uint_as_float(h[i] | 0x3f000000u); }
     }
   }
@@ -45,6 +48,6 @@ template <int OP> void run(const char* name) {
 }
 int main() {
   run<0>("MUFU.EX2"); run<9>("LOP (baseline for F2FP test)"); run<1>("F2FP.F16.F32.PACK_AB (per instr)"); run<8>("F2FP.BF16 (per instr)"); run<2>("FHFMA"); run<3>("FFMA"); run<4>("FMNMX3");
-  run<5>("HMNMX2 x2 / VHMNMX"); run<6>("FADD"); run<7>("LOP3");
+  run<10>("FFMA2 (fma.rn.f32x2, per instr)"); run<5>("HMNMX2 x2 / VHMNMX"); run<6>("FADD"); run<7>("LOP3");
   return 0;
 }

@@ -263,24 +263,26 @@ def test_end_to_end_vs_reference(name):
         assert np.all(np.diff(lin) > 0)
 
 
-def test_against_oracle_fresh_seed():
-    """Same seeded inputs through the numpy oracle and the CUDA path (seed not in the goldens)."""
+@pytest.mark.parametrize("D,kenc", [(128, (32, 64, 128)), (64, (32, 64))])
+def test_against_oracle_fresh_seed(D, kenc):
+    """Same seeded inputs through the numpy oracle and the CUDA path (seed not in the goldens).  D = 64 is the
+    reference's third shipped SuperPoint width (superPointNet_allss_descriptor_64): head_dim 16 attention on tcgen05."""
     from image_matching_b200 import synth
     from oracle import matching_oracle as O
-    cfg = golden_cfg(max_kp=128, iters=25)
-    sp, sg = synth.superpoint_weights(7, 128), synth.superglue_weights(7, 128)
+    cfg = golden_cfg(D=D, kenc=kenc, max_kp=128, iters=25)
+    sp, sg = synth.superpoint_weights(7, D), synth.superglue_weights(7, D, kenc)
     a, b = synth.make_pair(11, 96, 136)
     r = O.matching_forward(a, b, sp, sg, cfg)
     m = _matching(cfg, sp, sg)
     pred = m({"image0": _t(a[None, None]), "image1": _t(b[None, None])})
     for side in "01":
         ref, got = kp_set(r["keypoints" + side]), kp_set(pred["keypoints" + side][0].cpu().numpy())
-        print(f"FLIPS fresh_seed side{side}: {len(ref)} oracle keypoints, {len(ref ^ got)} differ")
+        print(f"FLIPS fresh_seed D={D} side{side}: {len(ref)} oracle keypoints, {len(ref ^ got)} differ")
         assert ref == got
     rp = match_pairs(r["keypoints0"], r["keypoints1"], r["matches0"])
     gp = match_pairs(pred["keypoints0"][0].cpu().numpy(), pred["keypoints1"][0].cpu().numpy(),
                      pred["matches0"][0].cpu().numpy())
-    print(f"FLIPS fresh_seed: {len(rp)} oracle matches, {len(rp ^ gp)} differ")
+    print(f"FLIPS fresh_seed D={D}: {len(rp)} oracle matches, {len(rp ^ gp)} differ")
     assert rp == gp
 
 

@@ -60,11 +60,6 @@ def test_tc_attention(D, kenc, case):
         qkv[:, :D] = qkv[:, :D].abs()
     ref = _ref(qkv, B, Np, D, n0, n1, cross)
     simt = stages.debug_attention(m, qkv, B, Np, n0, n1, cross, False)
-    if D == 64:      # head_dim 16: the tensor-core kernel declines, the library uses the CUDA-core kernel
-        with pytest.raises(RuntimeError):
-            stages.debug_attention(m, qkv, B, Np, n0, n1, cross, True)
-        assert float((simt.double() - ref).abs().max()) < 2e-5
-        return
     tc = stages.debug_attention(m, qkv, B, Np, n0, n1, cross, True)
     e_s = float((simt.double() - ref).abs().max())
     e_t = float((tc.double() - ref).abs().max())
