@@ -88,6 +88,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     const uint32_t idesc = instr_desc(0 /*f16*/, 128, kGemmNT);
+    // [W_hi ; W_lo] of a stage are contiguous (2 x NT rows of 128 B): A_hi x [W_hi ; W_lo]^T is ONE N = 2 NT MMA that lands
+    // as [main | cross] in the adjacent accumulator columns -- 20 KB of shared-memory operand reads per K step instead of
+    // 24 KB.  The kernel is shared-memory-bandwidth bound (ncu at D = 256: 44 % of its LSU wavefronts are bank
+    // conflicts, L1/shared 68 % busy at 35 % tensor-pipe): three N = 128 MMAs alone ask for the full 128 B/clk, next to
+    // the splitter's 64 KB in + out per stage and the TMA fill.
+    const uint32_t idesc_wide = instr_desc(0 /*f16*/, 128, 2 * kGemmNT);
     int s = 0, ph = 0, lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int buf = lt & 1, aph = (lt >> 1) & 1;
@@ -104,10 +110,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ah = smem_desc_sw128(a_hi + ks * 32), al = smem_desc_sw128(a_lo + ks * 32);
           const uint64_t wh = smem_desc_sw128(w_hi + ks * 32), wl = smem_desc_sw128(w_lo + ks * 32);
-          mma_bf16(d, ah, wh, idesc, (kb | ks) != 0);             // kind::f16, fp16 operands (idesc)
           if (!p.single) {
-            mma_bf16(d + kGemmNT, ah, wl, idesc, (kb | ks) != 0);
+            mma_bf16(d, ah, wh, idesc_wide, (kb | ks) != 0);      // kind::f16: [A_hi W_hi^T | A_hi W_lo^T]
             mma_bf16(d + kGemmNT, al, wh, idesc, 1);
+          } else {
+            mma_bf16(d, ah, wh, idesc, (kb | ks) != 0);
           }
         }
         tc_commit(&empty[s]);
