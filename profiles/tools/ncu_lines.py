@@ -72,8 +72,12 @@ def main():
             print(f"  stall {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {float(vals[i]):.2f}")
     src = ncu_csv(rep, "source")
     h = src[1]
-    data = src[2:]
     iS, iN, iW = h.index("Source"), h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
+    data = []
+    for r in src[2:]:                     # a report with several launches repeats the table: keep the first launch
+        if len(r) <= max(iS, iN, iW) or not re.fullmatch(r"(0x)?[0-9a-fA-F]+", r[0]):
+            break
+        data.append(r)
     tot_n = sum(int(r[iN]) for r in data)
     tot_w = sum(int(r[iW]) for r in data)
     ops, opw = collections.Counter(), collections.Counter()
