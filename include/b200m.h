@@ -25,7 +25,11 @@
  * Conventions
  *   - plain C: pointers + sizes only, no torch types.  All tensor pointers are DEVICE pointers
  *     in the reference's own layouts (NCHW / (B,C,N) fp32, int64 match indices) unless the
- *     name ends in _host.  The library borrows them; it never allocates user-visible memory.
+ *     name ends in _host.  The library borrows them; it never allocates user-visible memory, and the product entry
+ *     points (forward / stage calls listed above) never allocate at all: their scratch is the caller's workspace.  Only
+ *     three test hooks -- b200m_debug_conv_layer, b200m_debug_attention and the reference-layout convenience
+ *     b200m_sample_descriptors -- take a stream-ordered temporary (cudaMallocAsync / cudaFreeAsync on the call's
+ *     stream) for their layout conversion.
  *   - every call takes the CUDA stream to launch on (cudaStream_t passed as void*); no hidden
  *     synchronisation, except where documented (b200m_pack, *_host helpers).
  *   - scratch memory is a caller-owned workspace sized by the matching *_workspace_bytes call.
