@@ -148,7 +148,13 @@ struct TcAttnSmem {
   static constexpr int KV_STAGE = 2 * K_PLANE + VH_PLANE + VL_PLANE;
   static constexpr int KV_TX = 2 * K_PLANE + 2 * VL_PLANE;   // bytes one stage receives by TMA (the ones rows are constant)
   static constexpr int NKV = HD <= 32 ? 4 : 2;            // K/V ring depth
-  static constexpr int OFF_KV = 2 * Q_PLANE;
+  // d <= 32: Q lives in TENSOR memory (the softmax threads copy their row there once; Q.K^T then takes its A operand from
+  // TMEM like P.V does): an SS-mode M128 x N64 x K16 MMA is bound by its 6 KB of shared-memory operand reads (48 cycles
+  // at 128 B/clk against 32 of tensor time, profiles/r02_ubench_mma_issue_rate.txt), and with two CTAs per SM the tensor
+  // pipe -- not only the MUFU -- paces the tile loop.  d = 64 has no TMEM columns left for it and keeps Q in shared memory.
+  static constexpr bool QTMEM = HD <= 32;
+  static constexpr int Q_COLS = QTMEM ? HD : 0;            // hi words (HD / 2) | lo words (HD / 2)
+  static constexpr int OFF_KV = QTMEM ? 0 : 2 * Q_PLANE;
   // half-merge exchange (128 rows x (HD + 2) floats) ALIASES the K/V ring: it is only touched after the last P.V MMA
   // has retired (every TMA load consumed, every MMA complete)
   static constexpr int OFF_X = OFF_KV;
@@ -159,7 +165,7 @@ struct TcAttnSmem {
   static constexpr int N_BARS = 1 + 2 * NKV + 2 + 2 + 1 + 1;
   static constexpr size_t BYTES = 1024 + OFF_BAR + N_BARS * 8 + 16;
   static constexpr int TMEM_COLS = 256;                   // S / P double buffer (2 KT) + O per key half (2 NO)
-  static_assert(2 * KT + 2 * NO <= TMEM_COLS, "tensor memory budget (two CTAs per SM)");
+  static_assert(2 * KT + 2 * NO + Q_COLS <= TMEM_COLS, "tensor memory budget (two CTAs per SM)");
   static_assert(2 * BYTES <= 232448, "two CTAs per SM");
 };
 
@@ -173,6 +179,8 @@ struct TcAttnParams {
   int cross;
   float scale_log2e;       // log2(e) / sqrt(d)
   int single;              // precision experiment (B200M_SINGLE=attn): hi planes only
+  const __half* q_hi; const __half* q_lo;   // the q|k|v planes [rows][ldq] (Q read directly when it goes to tensor memory)
+  int ldq; long long rows;
 };
 
 // this thread's KH scores -> p = 2^(s c + neg) as packed fp16 hi / lo words; returns the packed maximum of the hi words
@@ -261,7 +269,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     tma_load_2d(dst + 2 * SM::K_PLANE + SM::VH_PLANE, &tm_vt_lo, &kv_full[st], j * KT, vt_row0);
   };
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(q_full, SM::QTMEM ? 8 : 1);       // Q landed: one TMA transaction, or the eight softmax warps' TMEM stores
     for (int i = 0; i < SM::NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
     mbar_init(pv_done, 1);
@@ -273,9 +281,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     // the first loads go out BEFORE the tensor-memory allocation and the CTA-wide sync below: their L2 / DRAM latency
     // (~2.6 k cycles to the first score tile) overlaps the ~1.9 k cycles of set-up instead of following it
     // (Q and tile 0 do not wait for the key count either -- a pair without keys just lets them land, see below)
-    mbar_expect_tx(q_full, 2 * SM::Q_PLANE);
-    tma_load_2d(sQ, &tm_q_hi, q_full, cq, q_row0);
-    tma_load_2d(sQ + SM::Q_PLANE, &tm_q_lo, q_full, cq, q_row0);
+    if constexpr (!SM::QTMEM) {
+      mbar_expect_tx(q_full, 2 * SM::Q_PLANE);
+      tma_load_2d(sQ, &tm_q_hi, q_full, cq, q_row0);
+      tma_load_2d(sQ + SM::Q_PLANE, &tm_q_lo, q_full, cq, q_row0);
+    }
     load_kv(0);
   }
   if (warp == 1) tmem_alloc(tmem_slot, SM::TMEM_COLS);
@@ -283,7 +293,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 2 * KT;
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * KT, tQ = tO + 2 * NO;
 #ifdef B200M_ATTN_TRACE
   if (tr && threadIdx.x == 64) tr[2] = clock64();
 #endif
@@ -295,7 +305,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       load_kv(j);
     }
     if (T == 0) {                      // nothing consumes the early loads: they must have landed before the CTA exits
-      mbar_wait(q_full, 0);
+      if constexpr (!SM::QTMEM) mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
     }
   } else if (warp == 1) {
@@ -313,14 +323,23 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks) {          // 16 channels = 32 B inside the swizzled row
-            const uint64_t qh = smem_desc_sw<SM::QROW>(q_base + ks * 32);
-            const uint64_t ql = smem_desc_sw<SM::QROW>(q_base + SM::Q_PLANE + ks * 32);
             const uint64_t kh = smem_desc_sw<SM::QROW>(k_base + ks * 32);
             const uint64_t kl = smem_desc_sw<SM::QROW>(k_base + SM::K_PLANE + ks * 32);
-            mma_bf16(tS + st * KT, qh, kh, idesc_s, ks != 0);
-            if (!p.single) {
-              mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
-              mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
+            if constexpr (SM::QTMEM) {                  // 16 channels = 8 packed columns of the Q row in tensor memory
+              const uint32_t qh = tQ + ks * 8, ql = tQ + HD / 2 + ks * 8;
+              mma_f16_ts(tS + st * KT, qh, kh, idesc_s, ks != 0);
+              if (!p.single) {
+                mma_f16_ts(tS + st * KT, qh, kl, idesc_s, 1);
+                mma_f16_ts(tS + st * KT, ql, kh, idesc_s, 1);
+              }
+            } else {
+              const uint64_t qh = smem_desc_sw<SM::QROW>(q_base + ks * 32);
+              const uint64_t ql = smem_desc_sw<SM::QROW>(q_base + SM::Q_PLANE + ks * 32);
+              mma_bf16(tS + st * KT, qh, kh, idesc_s, ks != 0);
+              if (!p.single) {
+                mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
+                mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
+              }
             }
           }
           tc_commit(&s_full[st]);
@@ -328,6 +347,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         __syncwarp();
       };
       mbar_wait(q_full, 0);
+      tc_fence_after();
       issue_S(0);
       if (T > 1) issue_S(1);
       for (int j = 0; j < T; ++j) {
@@ -369,6 +389,31 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
     const float c = p.scale_log2e;
     const uint32_t tS_mine = tS + lane_base + half * KH;
     const uint32_t tO_mine = tO + lane_base + half * NO;
+    if constexpr (SM::QTMEM) {
+      // this thread's query row -> tensor memory: half 0 copies the hi plane's HD / 2 packed words, half 1 the lo plane's
+      // (memory order = the packed K-major A layout: word c of the row holds channels 2c, 2c + 1)
+      if (T > 0) {
+        constexpr int QW = HD / 2;
+        uint32_t qw[QW];
+        const long long qrow = (long long)q_row0 + m;
+        if (qrow < p.rows) {
+          const uint4* src = reinterpret_cast<const uint4*>((half ? p.q_lo : p.q_hi) + qrow * p.ldq + cq);
+#pragma unroll
+          for (int i = 0; i < QW / 4; ++i) {
+            const uint4 v = __ldg(src + i);
+            qw[4 * i] = v.x; qw[4 * i + 1] = v.y; qw[4 * i + 2] = v.z; qw[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < QW; ++i) qw[i] = 0u;
+        }
+        tmem_st_words<QW>(tQ + lane_base + half * QW, qw);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_full);
+      }
+    }
     if constexpr (SM::ONES) {
       // the 16 constant rows of ones under every V^T hi tile (all elements equal, so the swizzle does not matter).  Written
       // here, while the first score tile is still on its way, instead of before the CTA-wide sync; the first P.V that
@@ -551,6 +596,8 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
   p.msg = msg; p.msg_hi = reinterpret_cast<__half*>(msg_hi); p.msg_lo = reinterpret_cast<__half*>(msg_lo); p.B = B; p.Np = Np; p.D = D; p.counts0 = c0; p.counts1 = c1; p.n_full0 = nf0; p.n_full1 = nf1;
   p.cross = cross ? 1 : 0;
   p.single = single ? 1 : 0;
+  p.q_hi = reinterpret_cast<const __half*>(qkv_hi); p.q_lo = reinterpret_cast<const __half*>(qkv_lo);
+  p.ldq = 3 * D; p.rows = (long long)rows;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   dim3 grid(cdiv(Np, kTaQ), heads, 2 * B);
 #ifdef B200M_ATTN_TRACE
