@@ -28,8 +28,10 @@
 // exit sync -- and its slot is re-filled 2.3 k cycles later.  The loop runs at the MUFU rate (two co-resident CTAs: 4 softmax
 // warps per scheduler x 256 MUFU cycles per tile ~ 80 % of the ~1.3 k-cycle tile period); the fixed costs overlap the
 // other CTA's loop, which alone is bound by its single MMA-issuing thread (a warp issues one tcgen05.mma per ~45 cycles
-// whatever its size: 18 per tile).  Tried and measured worse: a persistent two-CTA-per-SM variant (the resident CTAs run
-// in lock step and queue on the tensor pipe: +12 %), P_hi x [V_hi ; V_lo] as one N = 2d MMA with thread-side sums (+4 %).
+// whatever its size: 18 per tile).  Tried and measured worse: a persistent two-CTA-per-SM variant (the resident CTAs
+// queue on the tensor pipe: +12 %, with or without a deliberate half-item offset between them), P_hi x [V_hi ; V_lo] as one
+// N = 2d MMA with thread-side sums (+4 %), two MMA-issuing warps that take the even / odd key tiles (neutral at 1024
+// keys, -1.6 % at 4096: the 80-register cap of 352 threads eats the gain).  Kept: Q in tensor memory (-7 %).
 //   warp 0      TMA producer : Q tile once, then K / V^T tiles (hi and lo planes), 2-D tensor maps, 128- or 64-byte
 //                              swizzle (= row length), i.e. the canonical K-major swizzled UMMA layouts.  K tiles are
 //                              [keys][d]; V is read from the transposed copy V^T [d][keys] that the q|k|v projection's
