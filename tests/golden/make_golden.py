@@ -178,6 +178,41 @@ def main_c3():
           int(pred["keypoints1"][0].shape[0]), "valid matches:", int((pred["matches0"][0] > -1).sum()))
 
 
+def convert_allss64_superpoint_weights():
+    """The reference's D=64 SuperPoint checkpoint (superPointNet_allss_descriptor_64.pth.tar), converted like the others."""
+    ck = torch.load(os.path.join(REF, "superpoint/models/weights/superPointNet_allss_descriptor_64.pth.tar"),
+                    map_location="cpu")
+    sd = {(k[7:] if "module" in k else k): v.numpy() for k, v in ck["model_state_dict"].items()}
+    path = os.path.join(HERE, "superpoint_allss64_weights.npz")
+    np.savez_compressed(path, **sd)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    return sd
+
+
+def main_d64():
+    """The third SuperPoint width the reference ships (D = 64, head_dim 16): one 640x480 pair, the reference's own
+    checkpoint, 1024 keypoints, kenc [32, 64], 18 layers, 30 Sinkhorn iterations; boundary outputs only."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    sp = convert_allss64_superpoint_weights()
+    sg = synth.superglue_weights(2, 64, (32, 64))
+    cfg = make_cfg(D=64, kenc=(32, 64), max_kp=1024, iters=30)
+    m = build_reference(cfg, sp, sg)
+    a, b = synth.make_pair_batch([1], 480, 640)
+    pred = m({"image0": torch.from_numpy(a), "image1": torch.from_numpy(b)})
+    out = {"seeds": np.asarray([1]), "H": 480, "W": 640}
+    for k, v in pred.items():
+        if isinstance(v, (list, tuple)):
+            for i, t in enumerate(v):
+                out[f"{k}_{i}"] = t.numpy()
+        else:
+            out[k] = v.numpy()
+    path = os.path.join(HERE, "d64_real.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", "kpts:", int(pred["keypoints0"][0].shape[0]),
+          int(pred["keypoints1"][0].shape[0]), "valid matches:", int((pred["matches0"][0] > -1).sum()))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -213,6 +248,8 @@ if __name__ == "__main__":
         main_official()      # only the fixture added for SURVEY.md 8(f3); the others are unchanged
     elif len(sys.argv) > 1 and sys.argv[1] == "c3":
         main_c3()            # only the config-3 fixture (round 2); the others are unchanged
+    elif len(sys.argv) > 1 and sys.argv[1] == "d64":
+        main_d64()           # only the D = 64 fixture (round 2); the others are unchanged
     else:
         main()
         main_official()

@@ -55,6 +55,10 @@ def _case(name):
         return dict(g=load_golden(name), cfg=golden_cfg(D=256, kenc=(32, 64, 128, 256), max_kp=2048, iters=30),
                     sp=dict(np.load(os.path.join(GOLDEN, "superpoint_coco256_weights.npz"))),
                     sg=synth.superglue_weights(1, 256, (32, 64, 128, 256)), H=960, W=1280, seeds=[1])
+    if name == "d64_real":
+        return dict(g=load_golden(name), cfg=golden_cfg(D=64, kenc=(32, 64), max_kp=1024, iters=30),
+                    sp=dict(np.load(os.path.join(GOLDEN, "superpoint_allss64_weights.npz"))),
+                    sg=synth.superglue_weights(2, 64, (32, 64)), H=480, W=640, seeds=[1])
     if name == "c1_real":
         return dict(g=load_golden(name), cfg=golden_cfg(max_kp=1024), sp=real_superpoint_weights(),
                     sg=synth.superglue_weights(0, 128), H=480, W=640, seeds=[1])
@@ -219,7 +223,7 @@ def test_superglue_given_reference_features(stage):
     assert np.abs(pred["matching_scores0"].cpu().numpy() - g["matching_scores0"])[both].max() < 1e-3
 
 
-@pytest.mark.parametrize("name", ["ragged_hw", "c1_real", "c1_pair", "small_stages", "d256_small", "c3_real"])
+@pytest.mark.parametrize("name", ["ragged_hw", "c1_real", "c1_pair", "small_stages", "d256_small", "c3_real", "d64_real"])
 def test_end_to_end_vs_reference(name):
     from image_matching_b200 import synth
     c = _case(name)

@@ -159,6 +159,24 @@ def test_torch_cpu_oracle_config3_golden():
     assert np.array_equal(r["matches0"], g["matches0"][0]) and np.array_equal(r["matches1"], g["matches1"][0])
 
 
+def test_torch_cpu_oracle_d64_golden():
+    """The third SuperPoint width the reference ships (D = 64, its own allss_descriptor_64 checkpoint, 640x480, 1024
+    keypoints): the torch-CPU oracle reproduces the reference-generated golden -- identical keypoints and matches."""
+    import os
+    from conftest import GOLDEN
+    from oracle import matching_oracle_torch as OT
+    g = load_golden("d64_real")
+    cfg = golden_cfg(D=64, kenc=(32, 64), max_kp=1024, iters=30)
+    sp = dict(np.load(os.path.join(GOLDEN, "superpoint_allss64_weights.npz")))
+    sg = synth.superglue_weights(2, 64, (32, 64))
+    a, b = synth.make_pair(1, 480, 640)
+    r = OT.matching_forward(a, b, sp, sg, cfg)
+    for side in "01":
+        assert np.array_equal(r["keypoints" + side], g[f"keypoints{side}_0"])
+        assert np.abs(r["descriptors" + side] - g[f"descriptors{side}_0"]).max() < 1e-5
+    assert np.array_equal(r["matches0"], g["matches0"][0]) and np.array_equal(r["matches1"], g["matches1"][0])
+
+
 def test_reference_copy_reproduces_goldens_and_port():
     """oracle/_ref (the reference's own modules, copied by oracle/make_ref.py -- the CPU baseline bench.py times)
     reproduces the committed golden bit for bit, and the torch-CPU port agrees with it on a fresh seed."""
