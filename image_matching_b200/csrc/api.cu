@@ -948,6 +948,10 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   impl = getenv("B200M_GNN_IMPL");
   h->use_fused_gnn = !(impl && strcmp(impl, "unfused") == 0);
   impl = getenv("B200M_SINGLE");
+  if (impl && impl[0] && !kSingleExp) {
+    delete h;
+    return fail(B200M_ERR_INVALID, "B200M_SINGLE needs a library built with EXTRA=-DB200M_SINGLE_EXPERIMENT");
+  }
   if (impl) {
     h->single_desc = strstr(impl, "desc") != nullptr;
     h->single_gemm = strstr(impl, "gemm") != nullptr;

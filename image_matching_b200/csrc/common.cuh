@@ -13,6 +13,15 @@ namespace b200m {
 
 constexpr int kWarp = 32;
 
+// Precision experiment (profiles/r02_single_product_experiment.md): the hi-x-hi-only code paths exist ONLY in a build made
+// with EXTRA=-DB200M_SINGLE_EXPERIMENT.  As run-time branches in the MMA-issue and epilogue loops they had cost the
+// product build 4 % of its throughput (the conv kernels 8.1 -> 8.9 ms per step), so the product build compiles them out.
+#ifdef B200M_SINGLE_EXPERIMENT
+constexpr bool kSingleExp = true;
+#else
+constexpr bool kSingleExp = false;
+#endif
+
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }

@@ -330,7 +330,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             if constexpr (SM::QTMEM) {                  // 16 channels = 8 packed columns of the Q row in tensor memory
               const uint32_t qh = tQ + ks * 8, ql = tQ + HD / 2 + ks * 8;
               mma_f16_ts(tS + st * KT, qh, kh, idesc_s, ks != 0);
-              if (!p.single) {
+              if (!(kSingleExp && p.single)) {
                 mma_f16_ts(tS + st * KT, qh, kl, idesc_s, 1);
                 mma_f16_ts(tS + st * KT, ql, kh, idesc_s, 1);
               }
@@ -338,7 +338,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
               const uint64_t qh = smem_desc_sw<SM::QROW>(q_base + ks * 32);
               const uint64_t ql = smem_desc_sw<SM::QROW>(q_base + SM::Q_PLANE + ks * 32);
               mma_bf16(tS + st * KT, qh, kh, idesc_s, ks != 0);
-              if (!p.single) {
+              if (!(kSingleExp && p.single)) {
                 mma_bf16(tS + st * KT, qh, kl, idesc_s, 1);
                 mma_bf16(tS + st * KT, ql, kh, idesc_s, 1);
               }
@@ -368,7 +368,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
             const uint32_t dO = tO + hf * NO;              // independent accumulators per key half
             const uint32_t acc = (j > 0) || kl != 0;       // accumulates across key tiles
             mma_f16_ts(dO, a_hi, vh, idesc_o, acc);
-            if (!p.single) {
+            if (!(kSingleExp && p.single)) {
               mma_f16_ts(dO, a_lo, vh, idesc_o, 1);
               mma_f16_ts(dO, a_hi, vl, idesc_v, 1);
             }

@@ -188,7 +188,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       mbar_wait(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + buf * (4 * NB);
-      const bool single = (tile % ncb) >= p.single_from_cb;
+      const bool single = kSingleExp && (tile % ncb) >= p.single_from_cb;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
@@ -313,7 +313,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       const int aph = SM::ACC_BUFS == 2 ? ((lt >> 1) & 1) : (lt & 1);
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
-      const float cross_scale = cb >= p.single_from_cb ? 0.f : 1.f / kLoScale;   // experiment: no cross accumulator
+      const bool single = kSingleExp && cb >= p.single_from_cb;                 // experiment: no cross accumulator
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const int x = x0 + sub * 8 + xs, y = y0 + ys;
@@ -346,7 +346,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = (cross_scale != 0.f ? fmaf(vc[j], cross_scale, v[j]) : v[j]) + bj[j];
+            float t = (single ? v[j] : fmaf(vc[j], 1.f / kLoScale, v[j])) + bj[j];
             if (p.relu) t = fmaxf(t, 0.f);
             if (POOL) {
               t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));

@@ -110,7 +110,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ah = smem_desc_sw128(a_hi + ks * 32), al = smem_desc_sw128(a_lo + ks * 32);
           const uint64_t wh = smem_desc_sw128(w_hi + ks * 32), wl = smem_desc_sw128(w_lo + ks * 32);
-          if (!p.single) {
+          if (!(kSingleExp && p.single)) {
             mma_bf16(d, ah, wh, idesc_wide, (kb | ks) != 0);      // kind::f16: [A_hi W_hi^T | A_hi W_lo^T]
             mma_bf16(d + kGemmNT, al, wh, idesc, 1);
           } else {
@@ -193,7 +193,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = p.alpha * (p.single ? v[j] : fmaf(vc[j], 1.f / 2048.f, v[j])) + bj[j];
+          float t = p.alpha * ((kSingleExp && p.single) ? v[j] : fmaf(vc[j], 1.f / 2048.f, v[j])) + bj[j];
           if (p.relu) t = fmaxf(t, 0.f);
           v[j] = t;
         }

@@ -193,7 +193,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
         const uint64_t ah = smem_desc_sw128(a + ks * 32), al = smem_desc_sw128(a + kGnPlane + ks * 32);
         const uint64_t wh = smem_desc_sw128(w + ks * 32), wl = smem_desc_sw128(w + kGnPlane + ks * 32);
         const uint32_t acc = !(first && ks == 0);
-        if (p.single) {                       // experiment: hi planes only
+        if (kSingleExp && p.single) {         // experiment: hi planes only
           mma_bf16(d, ah, wh, idesc, acc);
           continue;
         }
@@ -344,7 +344,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
       tmem_ld32_issue(t, v);
       tmem_ld32_issue(t + 128, vc);
       tmem_ld_wait();
-      if (!p.single) {
+      if (!(kSingleExp && p.single)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], 1.f / kGnLo, v[j]);
       }

@@ -8,6 +8,9 @@ created): B200M_SINGLE = "", desc, gemm, gnn, attn, "gemm,gnn,attn", "desc,gemm,
       which itself has 0 flips on every golden -- a 30x larger sample than the goldens;
   (c) kernel times of one 64-pair step.
 
+The library must be built with  make -C image_matching_b200/csrc clean all EXTRA=-DB200M_SINGLE_EXPERIMENT  (the product
+build compiles the single-product code paths out and rejects B200M_SINGLE).
+
 usage: python profiles/tools/single_product_experiment.py            (driver: runs every setting, prints a table)
        python profiles/tools/single_product_experiment.py --worker   (one setting, JSON on stdout)
 """
