@@ -160,6 +160,22 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- packed fp32 (sm_100: FFMA2)
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// (a.lo * b.lo + c.lo, a.hi * b.hi + c.hi), each an IEEE round-to-nearest fp32 FMA
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // ---------------------------------------------------------------- fp16 hi / lo operand split
 // {upper half = fp16(b), lower half = fp16(a)}: element a sits in the low 16 bits (the even element of a pair)
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
