@@ -400,6 +400,7 @@ def run_b200(args, cname, c):
         return xs, ev
 
     pending = []
+    host_out = {}                 # pinned result buffers of the end-to-end leg
 
     def step_e2e():
         if not pending:
@@ -422,8 +423,17 @@ def run_b200(args, cname, c):
             g0, gs0 = gather_matches(m0, s0, B * world, handle=m._engine.handle, dst=0)
             if rank == 0:
                 m0, s0 = g0, gs0
-        # what the reference's caller reads back per pair (superpoint_glue_test.py:79-82)
-        return [m0.cpu(), s0.cpu()] + [e.cpu() for e in extra]
+        # what the reference's caller reads back per pair (superpoint_glue_test.py:79-82), into pinned host buffers (one
+        # stream sync for all of them instead of one pageable copy + sync per tensor)
+        res = []
+        for i, t in enumerate([m0, s0] + extra):
+            key = (i, tuple(t.shape), t.dtype)
+            if key not in host_out:
+                host_out[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host_out[key].copy_(t, non_blocking=True)
+            res.append(host_out[key])
+        cur.synchronize()
+        return res
 
     for _ in range(max(args.warmup, 3)):
         out = step_device()
