@@ -19,6 +19,8 @@
 //                               MMAs of tile i+1.
 //   warps 6..9  epilogue      : tcgen05.ld -> alpha/bias/ReLU/residual -> stores (row-contiguous float4; the V^T
 //                               copy is written column-wise so a warp stores 128 contiguous bytes).
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -36,6 +38,15 @@ constexpr int kGemmStage = 2 * kGemmATile + 2 * kGemmBTile;   // A box0 -> hi, A
 constexpr int kGemmBarOff = kGemmStages * kGemmStage;
 constexpr size_t kGemmSmem = 1024 + kGemmBarOff + (3 * kGemmStages + 4) * 8 + 16;
 
+// Developer aid (make EXTRA=-DB200M_GEMM_TRACE, run with B200M_GEMM_TRACE=1 B200M_GRAPHS=0): clock64 stamps of one CTA's
+// fourth tile for the MMA warp, the first splitter warp and the first epilogue warp (per 32-column chunk), printed for a
+// few launches with M >= 16384.  This is how the two epilogue costs fixed in round 2 were found (see the epilogue).
+#ifdef B200M_GEMM_TRACE
+__device__ long long* g_gemm_trace = nullptr;
+#define GMT(slot) do { if (traced && lane == 0) tr[(slot)] = clock64(); } while (0)
+#else
+#define GMT(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(320, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w_hi,
                const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
@@ -50,6 +61,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200M_GEMM_TRACE
+  long long* const tr = g_gemm_trace;
+  bool traced = false;
+  int tcount = 0;
+#define GMT_ARM() do { traced = tr != nullptr && blockIdx.x == 5 && tcount == 3; ++tcount; } while (0)
+#else
+#define GMT_ARM() do { } while (0)
+#endif
   // batched mode (score matrix): `batch` independent problems whose A / W rows are stacked with a fixed row pitch in
   // the SAME 2-D arrays (tensor-map row coordinate = bt * pitch + tile row) and whose C blocks are strideC apart
   const int m_tiles = cdiv(p.M, 128), n_tiles = cdiv(p.N, kGemmNT);
@@ -97,11 +116,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     int s = 0, ph = 0, lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int buf = lt & 1, aph = (lt >> 1) & 1;
+      GMT_ARM();
+      GMT(0);
       mbar_wait(&acc_empty[buf], aph ^ 1);
+      GMT(1);
       tc_fence_after();
       const uint32_t d = tmem_base + buf * (2 * kGemmNT);   // main accumulator; cross terms at d + NT
       for (int kb = 0; kb < nkb; ++kb) {
+        GMT(2 + 2 * kb);
         mbar_wait(&split[s], ph);
+        GMT(3 + 2 * kb);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * kGemmStage), a_lo = a_hi + kGemmATile;
         const uint32_t w_hi = a_hi + 2 * kGemmATile, w_lo = w_hi + kGemmBTile;
@@ -129,8 +153,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int t = threadIdx.x - 64;    // 0..127
     int s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      GMT_ARM();
       for (int kb = 0; kb < nkb; ++kb) {
+        if (warp == 2) GMT(32 + 2 * kb);
         mbar_wait(&full[s], ph);
+        if (warp == 2) GMT(33 + 2 * kb);
         uint8_t* st = smem + s * kGemmStage;
         const int r = t, sw = r & 7;                      // this thread's row and its swizzle phase
         float e[64];
@@ -152,6 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split[s]);
+        if (warp == 2 && kb == nkb - 1) GMT(60);
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
       }
     }
@@ -164,7 +192,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int bt = tile / per_batch, tt = tile - bt * per_batch;
       const int m0 = (tt / n_tiles) * 128, n0 = (tt % n_tiles) * kGemmNT;
       const int buf = lt & 1, aph = (lt >> 1) & 1;
+      GMT_ARM();
+      if (warp == 6) GMT(64);
       mbar_wait(&acc_full[buf], aph);
+      if (warp == 6) GMT(65);
       tc_fence_after();
       const int r = m0 + mrow;
       const bool rok = r < p.M;
@@ -174,8 +205,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int ch = 0; ch < kGemmNT / 32; ++ch) {
         float v[32], vc[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(w4 * 32) << 16) + buf * (2 * kGemmNT) + ch * 32;
+        if (warp == 6) GMT(70 + 4 * ch);
         tmem_ld32(taddr, v);
         tmem_ld32(taddr + kGemmNT, vc);
+        if (warp == 6) GMT(71 + 4 * ch);
         const int c0 = n0 + ch * 32;
         if (c0 >= p.N) continue;           // uniform per warp
         // bias of the chunk: eight 16-byte loads when the chunk is whole and aligned (one L1 load per ELEMENT made this
@@ -197,21 +230,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (p.relu) t = fmaxf(t, 0.f);
           v[j] = t;
         }
+        if (warp == 6) GMT(72 + 4 * ch);
+        if (!p.out_f16) {
+          // fp32 output (and the residual read).  A thread owns a row, so a plain 16-byte store per thread touches 32
+          // different rows per warp instruction and HALF of each 32-byte sector; the LSU's cost is per sector (clock64
+          // stamps: ~1.1 k cycles of stores per 32-column chunk, more than the chunk's tensor-memory loads and math).
+          // Lane pairs (2t, 2t+1) therefore swap one float4 of every eight columns, so that each instruction writes the
+          // even lane's row and the next the odd lane's row as FULL 32-byte sectors (16 instead of 32 per instruction).
+          const bool odd = lane & 1;
+          const bool pok = (r ^ 1) < p.M;
+          float* own = crow;
+          float* par = p.C + (size_t)bt * p.strideC + (size_t)(r ^ 1) * p.ldc;
+          auto swap4 = [&](float4 x) {
+            return make_float4(__shfl_xor_sync(0xffffffffu, x.x, 1), __shfl_xor_sync(0xffffffffu, x.y, 1),
+                               __shfl_xor_sync(0xffffffffu, x.z, 1), __shfl_xor_sync(0xffffffffu, x.w, 1));
+          };
+          if (p.accumulate) {
+            // all loads of the chunk first (interleaved with the stores they were issued one dependent ~600-cycle round
+            // trip at a time: 6.3 k cycles per chunk, the MMA warp waited 15 k cycles per tile for an accumulator buffer)
+            float4 l1[4], l2[4];
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2) {
+              const int c = c0 + 8 * g2 + (odd ? 4 : 0);
+              const bool cok = c < p.N;
+              l1[g2] = (cok && (odd ? pok : rok)) ? *reinterpret_cast<const float4*>((odd ? par : own) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+              l2[g2] = (cok && (odd ? rok : pok)) ? *reinterpret_cast<const float4*>((odd ? own : par) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2) {
+              // even lane: l1 = own cols [8g2, +4), l2 = partner's; odd lane: l1 = partner's cols [8g2 + 4, +4), l2 = own
+              const float4 got = swap4(odd ? l1[g2] : l2[g2]);     // partner's data goes home, ours comes back
+              const float4 a = odd ? got : l1[g2];                  // own row, cols 8g2 .. 8g2+3
+              const float4 b = odd ? l2[g2] : got;                  // own row, cols 8g2+4 .. 8g2+7
+              v[8 * g2] += a.x; v[8 * g2 + 1] += a.y; v[8 * g2 + 2] += a.z; v[8 * g2 + 3] += a.w;
+              v[8 * g2 + 4] += b.x; v[8 * g2 + 5] += b.y; v[8 * g2 + 6] += b.z; v[8 * g2 + 7] += b.w;
+            }
+          }
+#pragma unroll
+          for (int g2 = 0; g2 < 4; ++g2) {
+            const float4 a0 = make_float4(v[8 * g2], v[8 * g2 + 1], v[8 * g2 + 2], v[8 * g2 + 3]);
+            const float4 a1 = make_float4(v[8 * g2 + 4], v[8 * g2 + 5], v[8 * g2 + 6], v[8 * g2 + 7]);
+            const float4 recv = swap4(odd ? a0 : a1);
+            const int c = c0 + 8 * g2 + (odd ? 4 : 0);
+            if (c < p.N) {
+              if (odd ? pok : rok) *reinterpret_cast<float4*>((odd ? par : own) + c) = odd ? recv : a0;   // the even lane's row
+              if (odd ? rok : pok) *reinterpret_cast<float4*>((odd ? own : par) + c) = odd ? a1 : recv;   // the odd lane's row
+            }
+          }
+          continue;
+        }
         if (rok) {
           // fp16 planes: a thread's 32 columns are 64 contiguous bytes per plane -> four 16-byte stores instead of sixteen
           // 4-byte ones (the q|k|v projections were bound by the store instructions, not by HBM: 0.87 -> 0.65 ms per step,
           // C3's per-GEMM GNN 8.1 -> 6.2 ms; also transposing the V^T stores inside lane quads measured neutral)
           const bool wide_planes = p.out_f16 && c0 + 32 <= p.N;
           __half2 hrow[16], lrow[16];
+          // the V third of a q|k|v projection is consumed only through V^T: its plane copy is not written
+          const bool v_only = p.out_f16 && p.VT && c0 >= p.vt_col0;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int c = c0 + 4 * g;
             if (c >= p.N) break;
             float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + c);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
             if (p.out_f16) {
               // fp16 hi / lo planes (+ transposed V planes): consumed by the attention kernel
               const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
@@ -221,7 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const __half2 l23 = __floats2half2_rn((o.z - b23.x) * ls, (o.w - b23.y) * ls);
               hrow[2 * g] = h01; hrow[2 * g + 1] = h23;
               lrow[2 * g] = l01; lrow[2 * g + 1] = l23;
-              if (!wide_planes) {
+              if (!wide_planes && !v_only) {
                 __half* ch = reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c;
                 __half* cl = reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c;
                 *reinterpret_cast<__half2*>(ch) = h01; *reinterpret_cast<__half2*>(ch + 2) = h23;
@@ -237,11 +317,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 vl[o0] = __low2half(l01); vl[o0 + np] = __high2half(l01);
                 vl[o0 + 2 * np] = __low2half(l23); vl[o0 + 3 * np] = __high2half(l23);
               }
-            } else {
-              *reinterpret_cast<float4*>(crow + c) = o;
             }
           }
-          if (wide_planes) {
+          if (wide_planes && !v_only) {
             uint4* ch = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c0);
             uint4* cl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c0);
 #pragma unroll
@@ -255,6 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (warp == 6) GMT(66);
     }
   }
   tc_fence_before();
@@ -296,6 +375,7 @@ static bool make_sw128_map2(CUtensorMap* m, const float* base, size_t rows, int 
 bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms) {
   if (p.batch < 1 || p.K % 8 || p.lda % 4 || p.ldc % 4 || (p.N % 4 && p.batch == 1) || p.K < 32 || p.M <= 0) return false;
   if (p.batch > 1 && (p.out_f16 || p.accumulate || p.strideC % 4)) return false;
+  if (p.out_f16 && p.accumulate) return false;       // the plane epilogue has no residual read
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(w_hi)) & 15) return false;
   ProfScope prof__(ctx, "tc_gemm");
   CUtensorMap ma, mh, ml;
@@ -310,8 +390,35 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   if (!opt.ensure(tc_gemm_kernel, (int)kGemmSmem)) return false;
   const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT) * p.batch;
   const int grid = total < num_sms ? total : num_sms;
+#ifdef B200M_GEMM_TRACE
+  static long long* tbuf = nullptr;
+  if (getenv("B200M_GEMM_TRACE") && !tbuf) {
+    cudaMalloc(&tbuf, 128 * 8);
+    cudaMemset(tbuf, 0, 128 * 8);
+  }
+  static int nlaunch = 0;
+  const bool want = tbuf && p.M >= 16384 && (++nlaunch >= 40 && nlaunch < 48);
+  long long* arg = want ? tbuf : nullptr;
+  cudaMemcpyToSymbolAsync(g_gemm_trace, &arg, sizeof(arg), 0, cudaMemcpyHostToDevice, ctx.stream);
+  if (want) cudaMemsetAsync(tbuf, 0, 128 * 8, ctx.stream);
+#endif
   tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
+#ifdef B200M_GEMM_TRACE
+  if (want) {
+    long long hb[128];
+    cudaStreamSynchronize(ctx.stream);
+    cudaMemcpy(hb, tbuf, sizeof(hb), cudaMemcpyDeviceToHost);
+    const long long t0 = hb[0];
+    const int nkb = (p.K + 63) / 64;
+    fprintf(stderr, "GEMM trace M=%d N=%d K=%d acc=%d f16=%d: mma tile start 0, acc acquired %lld;", p.M, p.N, p.K, p.accumulate, p.out_f16, hb[1] - t0);
+    for (int kb = 0; kb < nkb; ++kb) fprintf(stderr, " kb%d wait %lld got %lld;", kb, hb[2 + 2 * kb] - t0, hb[3 + 2 * kb] - t0);
+    fprintf(stderr, "\n   splitter:");
+    for (int kb = 0; kb < nkb; ++kb) fprintf(stderr, " kb%d wait %lld got %lld;", kb, hb[32 + 2 * kb] - t0, hb[33 + 2 * kb] - t0);
+    fprintf(stderr, " last split done %lld\n   epilogue: wait %lld got %lld done %lld\n", hb[60] - t0, hb[64] - t0, hb[65] - t0, hb[66] - t0);
+    for (int ch = 0; ch < 4; ++ch) fprintf(stderr, "     chunk %d: start %lld tmem loaded %lld math done %lld\n", ch, hb[70 + 4 * ch] - t0, hb[71 + 4 * ch] - t0, hb[72 + 4 * ch] - t0);
+  }
+#endif
   return true;
 }
 
