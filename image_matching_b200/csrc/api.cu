@@ -117,6 +117,13 @@ struct b200m_handle {
   cudaEvent_t g_in = nullptr, g_out = nullptr;
   unsigned long long graph_clock = 0;
   long long graph_replays = 0;
+  // small-batch latency (the reference caller's batch of one pair, superpoint_glue_test.py:66):
+  int pdl_max_pairs = 8;         // calls of at most this many pairs / images launch with PDL (B200M_PDL_MAX_PAIRS)
+  bool pdl_now = false;          // this call's setting (make_ctx)
+  int sp_dual_max = 4;           // Matching.forward of at most this many pairs runs the two images' SuperPoint passes
+                                 // concurrently (forked side stream, second workspace; B200M_SP_DUAL_MAX, 0 = never)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 
 namespace {
@@ -140,6 +147,7 @@ LaunchCtx make_ctx(b200m_handle* h, void* stream) {
   c.err_where = &h->err_where;
   c.err = cudaSuccess;
   c.prof = &h->prof;
+  c.pdl = h->pdl_now;
   return c;
 }
 
@@ -660,6 +668,7 @@ int sp_forward_impl(b200m_handle* h, void* stream, const void* images_any, bool 
   SpWs w;
   if (!sp_carve(h, d, mb, A, w)) return fail(B200M_ERR_WORKSPACE, "SuperPoint workspace too small: need %zu bytes", A.off);
   DeviceGuard dev_guard__(h->device);
+  h->pdl_now = n_images <= h->pdl_max_pairs;
   LaunchCtx ctx = make_ctx(h, stream);
   cudaMemsetAsync(w.overflow, 0, 2 * sizeof(int), ctx.stream);
   for (int i0 = 0; i0 < n_images; i0 += mb) {
@@ -962,6 +971,10 @@ int b200m_create(const b200m_config* cfg, int device, b200m_handle** out) {
   h->use_graphs = !(impl && strcmp(impl, "0") == 0);
   impl = getenv("B200M_SP_MICROBATCH");
   if (impl && atoi(impl) > 0) h->sp_micro_batch = std::min(atoi(impl), 256);
+  impl = getenv("B200M_PDL_MAX_PAIRS");
+  if (impl) h->pdl_max_pairs = atoi(impl);
+  impl = getenv("B200M_SP_DUAL_MAX");
+  if (impl) h->sp_dual_max = atoi(impl);
   *out = h;
   return B200M_OK;
 }
@@ -973,6 +986,9 @@ void b200m_destroy(b200m_handle* h) {
   if (h->g_in) cudaEventDestroy(h->g_in);
   if (h->g_out) cudaEventDestroy(h->g_out);
   if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->d_w) cudaFree(h->d_w);
   delete h;
 }
@@ -1256,6 +1272,7 @@ int b200m_superglue_forward(b200m_handle* h, const float* kpts0, const float* sc
                                 kp(counts1), ki(B, N), ki(M, H0), ki(W0, H1), ki(W1), kp(matches0), kp(matches1),
                                 kp(mscores0), kp(mscores1), kp(ws), (uint64_t)ws_bytes},
                     [&](void* stream) -> int {
+  h->pdl_now = B <= h->pdl_max_pairs;
   LaunchCtx ctx = make_ctx(h, stream);
   if (N == 0 || M == 0) {   // superglue_test.py:235-242
     launch_match_select(ctx, nullptr, nullptr, nullptr, 0, nullptr, nullptr, B, N, M, 0.f, (long long*)matches0,
@@ -1399,7 +1416,9 @@ int b200m_unpack_match_wire(b200m_handle* h, const int32_t* wire, int world, int
 size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W) {
   if (!h) return 0;
   int cap = b200m_keypoint_capacity(h, H, W);
-  return align_up(sp_ws_bytes(h, B, H, W), 256) + b200m_superglue_workspace_bytes(h, B, cap, cap) + 256;
+  // (small batches: one SuperPoint workspace per image side, the two passes run concurrently)
+  return align_up(sp_ws_bytes(h, B, H, W), 256) * (B <= h->sp_dual_max ? 2 : 1) +
+         b200m_superglue_workspace_bytes(h, B, cap, cap) + 256;
 }
 
 static int matching_forward_impl(b200m_handle* h, const void* image0, const void* image1, bool images_u8, int B, int H,
@@ -1419,8 +1438,22 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
                     [&](void* stream) -> int {
   const int D = h->cfg.descriptor_dim;
   const size_t sp_bytes = align_up(sp_ws_bytes(h, B, H, W), 256);
-  if (ws_bytes < sp_bytes) return fail(B200M_ERR_WORKSPACE, "matching workspace too small");
-  Arena A((char*)ws + sp_bytes, ws_bytes - sp_bytes);
+  // Few pairs (the reference caller's loop runs ONE pair per call): a single image leaves most of the chip idle in the
+  // 1/4- and 1/8-resolution layers and in the detector post-processing, so the two images' SuperPoint passes run
+  // side by side -- image 1 on a forked stream with its own workspace (inside the captured graph: a parallel branch).
+  bool dual = B <= h->sp_dual_max && !h->prof.enabled && ws_bytes >= 2 * sp_bytes;
+  if (dual && !h->side_stream) {
+    if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      h->sp_dual_max = 0;
+      dual = false;
+    }
+  }
+  const size_t sp_total = dual ? 2 * sp_bytes : sp_bytes;
+  if (ws_bytes < sp_total) return fail(B200M_ERR_WORKSPACE, "matching workspace too small");
+  Arena A((char*)ws + sp_total, ws_bytes - sp_total);
   SgWs w;
   if (!sg_carve(h, B, cap, cap, A, w))
     return fail(B200M_ERR_WORKSPACE, "matching workspace too small: need %zu bytes", sp_bytes + A.off);
@@ -1429,13 +1462,27 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   // so they must be finite
   if (w.Np != cap) cudaMemsetAsync(w.X, 0, w.rows * 2 * D * sizeof(float), (cudaStream_t)stream);
   // SuperPoint writes token-major descriptors straight into X[:, :D] of its side
+  void* stream1 = stream;
+  if (dual) {
+    cudaError_t fe = cudaEventRecord(h->fork_ev, (cudaStream_t)stream);
+    if (fe == cudaSuccess) fe = cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0);
+    if (fe != cudaSuccess) return fail(B200M_ERR_CUDA, "stream fork failed: %s", cudaGetErrorString(fe));
+    stream1 = (void*)h->side_stream;
+  }
   int rc = sp_forward_impl(h, stream, image0, images_u8, B, H, W, keypoints0, scores0, descriptors0, counts0, cap, nullptr,
                            nullptr, w.X, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
+  const int rc1 = sp_forward_impl(h, stream1, image1, images_u8, B, H, W, keypoints1, scores1, descriptors1, counts1, cap,
+                                  nullptr, nullptr, w.X + rows * 2 * D, 2 * D, (size_t)w.Np * 2 * D,
+                                  (char*)ws + (dual ? sp_bytes : 0), sp_bytes);
+  if (dual) {                      // join (also on errors: a captured side stream must not be left dangling)
+    cudaError_t je = cudaEventRecord(h->join_ev, h->side_stream);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent((cudaStream_t)stream, h->join_ev, 0);
+    if (je != cudaSuccess && !rc && !rc1) return fail(B200M_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(je));
+  }
   if (rc) return rc;
-  rc = sp_forward_impl(h, stream, image1, images_u8, B, H, W, keypoints1, scores1, descriptors1, counts1, cap, nullptr,
-                       nullptr, w.X + rows * 2 * D, 2 * D, (size_t)w.Np * 2 * D, ws, sp_bytes);
-  if (rc) return rc;
+  if (rc1) return rc1;
   DeviceGuard dev_guard__(h->device);
+  h->pdl_now = B <= h->pdl_max_pairs;
   LaunchCtx ctx = make_ctx(h, stream);
   sg_core(h, ctx, w, keypoints0, scores0, counts0, keypoints1, scores1, counts1, B, cap, cap, H, W, H, W, matches0,
           matches1, mscores0, mscores1);

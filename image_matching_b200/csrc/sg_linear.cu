@@ -12,6 +12,8 @@ namespace b200m {
 constexpr int GM = 128, GN = 64, GK = 16;
 
 __global__ void __launch_bounds__(256) gemm_tn_kernel(GemmParams p) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   __shared__ float As[2][GK][GM + 4];
   __shared__ float Bs[2][GK][GN + 4];
   const int tid = threadIdx.x;
@@ -118,7 +120,7 @@ void launch_gemm(LaunchCtx& ctx, const GemmParams& p) {
   ProfScope prof__(ctx, "gemm");
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
   dim3 grid(cdiv(p.N, GN), cdiv(p.M, GM), p.batch);
-  gemm_tn_kernel<<<grid, 256, 0, ctx.stream>>>(p);
+  launch_pdl(ctx, gemm_tn_kernel, dim3(grid), dim3(256), 0, p);
   B200M_LAUNCH_CHECK(ctx, "gemm_tn");
 }
 
@@ -207,6 +209,8 @@ void launch_qkv_to_f16_planes(LaunchCtx& ctx, const float* qkv, void* hi, void* 
 // rows of (x_norm, y_norm, score, 0) -- K padded 3 -> 4 so the first layer is a float4 GEMM.
 __global__ void kenc_input_kernel(const float* __restrict__ kpts, const float* __restrict__ scores, int N, int Np,
                                   float cx, float cy, float scale, float4* __restrict__ out, int total) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int b = i / Np, k = i - b * Np;
@@ -224,7 +228,7 @@ void launch_kenc_input(LaunchCtx& ctx, const float* kpts, const float* scores, i
                        float cx, float cy, float scale, float* out4) {
   ProfScope prof__(ctx, "kenc_input");
   int total = B * Np;
-  kenc_input_kernel<<<cdiv(total, 256), 256, 0, ctx.stream>>>(kpts, scores, N, Np, cx, cy, scale,
+  launch_pdl(ctx, kenc_input_kernel, dim3(cdiv(total, 256)), dim3(256), 0, kpts, scores, N, Np, cx, cy, scale,
                                                                 reinterpret_cast<float4*>(out4), total);
   B200M_LAUNCH_CHECK(ctx, "kenc_input");
 }

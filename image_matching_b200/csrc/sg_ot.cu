@@ -23,6 +23,8 @@ __device__ __forceinline__ PairDims pair_dims(const OtParams& p, int b) {
 }
 
 __global__ void ot_init_kernel(float* u, float* v, int total) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) { u[i] = 0.f; v[i] = 0.f; }
 }
@@ -30,7 +32,7 @@ __global__ void ot_init_kernel(float* u, float* v, int total) {
 void launch_ot_init(LaunchCtx& ctx, const OtParams& p) {
   ProfScope prof__(ctx, "ot_init");
   int total = p.B * p.ld_uv;
-  ot_init_kernel<<<cdiv(total, 256), 256, 0, ctx.stream>>>(p.u, p.v, total);
+  launch_pdl(ctx, ot_init_kernel, dim3(cdiv(total, 256)), dim3(256), 0, p.u, p.v, total);
   B200M_LAUNCH_CHECK(ctx, "ot_init");
 }
 
@@ -134,7 +136,7 @@ void launch_ot_col_update(LaunchCtx& ctx, const OtParams& p) {
 //   into the new v.
 constexpr int kOtFusedMaxM = 1024;
 constexpr int kOtWideMaxM = 4096;        // ot_iter_wide_kernel (rows kept in shared memory)
-constexpr int kOtMaxParts = 20;          // CTAs (= partial rows) per pair, upper bound (register-resident kernel)
+constexpr int kOtMaxParts = 64;          // CTAs (= partial rows) per pair, upper bound (register-resident kernel)
 constexpr int kOtWideMaxParts = 48;      // same for the wide kernels (few pairs of many rows: one CTA per SM)
 constexpr int kOtCtasPerSm = 2;   // (3 per SM = 80 registers with spills: measured 1.71 -> 2.11 ms)
 constexpr int kOtRing = 2;                // rows in flight per warp (3 measured no faster)
@@ -147,13 +149,20 @@ constexpr float kOtHeadroom = 60.f;      // nats
 constexpr float kOtTiny = 1.17549435e-38f;
 
 // CTAs per pair: the whole grid (parts x pairs) should be resident at once -- one wave, no tail, and the per-CTA
-// prologue / merge cost is paid as few times as possible -- but never fewer than 8 rows per warp-sized slice
+// prologue / merge cost is paid as few times as possible -- but never fewer than 2 rows per warp.  Few pairs (the
+// reference caller's batch of ONE, superpoint_glue_test.py:66) get up to 64 CTAs each: with 20 (the former bound) a warp
+// walked 7 rows one after the other and an iteration took 19 us at one pair.
+int ot_parts_cap(int pairs) {            // what the scratch buffer is sized for
+  const int by_slots = 320 / (pairs > 0 ? pairs : 1);
+  return by_slots > kOtMaxParts ? kOtMaxParts : (by_slots < 20 ? 20 : by_slots);
+}
 int ot_fused_parts(int pairs, int N, int num_sms) {
   const int slots = num_sms * kOtCtasPerSm;
   int parts = slots / (pairs > 0 ? pairs : 1);
   parts = parts < 1 ? 1 : parts;
-  parts = parts > kOtMaxParts ? kOtMaxParts : parts;
-  const int by_rows = cdiv(N + 1, 8);
+  const int cap = ot_parts_cap(pairs);
+  parts = parts > cap ? cap : parts;
+  const int by_rows = cdiv(N + 1, 16);
   return parts > by_rows ? by_rows : parts;
 }
 
@@ -176,9 +185,11 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const PairDims d = pair_dims(p, b);
-  if (d.n == 0 || d.m == 0) return;                       // uniform per block
   const int parts = cdiv(d.n + 1, rows_per_cta);
-  if ((int)blockIdx.x >= parts) return;                   // uniform per block
+  if (d.n == 0 || d.m == 0 || (int)blockIdx.x >= parts) {   // uniform per block
+    pdl_wait();                                             // (no CTA leaves before the predecessor completed: the chain of
+    return;                                                 // PDL waits stays transitive even if every CTA takes this exit)
+  }
   // ---- this warp's rows stream in through kOtRing 4 KB buffers (cp.async.bulk + mbarrier): the first ones are requested
   // before the prologue so their DRAM latency hides behind it
   const int rows_per_warp = rows_per_cta >> 3;            // rows_per_cta is a multiple of 8
@@ -194,12 +205,19 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
       tc::bulk_load(wrow + ((i - row0) % kOtRing) * kOtFusedMaxM, S + (size_t)i * p.ldS, row_bytes, bar);
     }
   };
+  // PDL: S does not change between iterations -- the first rows are requested while the PREVIOUS iteration's last CTAs
+  // still fold their partial sums; u, v, partials and tickets are touched only behind pdl_wait().  This kernel triggers
+  // AFTER its wait, so when a successor starts, everything up to this kernel's predecessor has completed (the first
+  // iteration, whose predecessors wrote S, waits before it requests anything).
+  if (first) pdl_wait();
   if (lane == 0) {
     for (int q = 0; q < kOtRing; ++q) tc::mbar_init(&bars[warp * kOtRing + q], 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
     for (int q = 0; q < kOtRing; ++q) request(row0 + q);
   }
+  if (!first) pdl_wait();
+  pdl_trigger();
   __syncwarp();
   // ---- prologue: v of the previous iteration (zeros before the first one), in log2 units
   float* vrow = p.v + (size_t)b * p.ld_uv;
@@ -314,16 +332,28 @@ __global__ void __launch_bounds__(256, kOtCtasPerSm) ot_iter_kernel(OtParams p, 
   // ---- the last CTA of the pair folds the partial rows into v_j = log_nu_j - logsumexp_i(c_ij + u_i)
   //      = log_nu_j - (ln(sum_j) + mu_bin - v_j(old) - 60)
   __threadfence();
-  for (int j = threadIdx.x; j <= d.m; j += 256) {
-    const float* col = partials + (size_t)b * max_parts * ld_part + j;
-    float t = 0.f;
-    float tq[kOtMaxParts];
+  // (thread = four adjacent columns, 16 partial rows in flight per thread; the partial rows are added in CTA order)
+  const int ngroups = (d.m + 4) >> 2;                        // float4 groups covering columns 0 .. m (ld_part % 4 == 0)
+  for (int g = threadIdx.x; g < ngroups; g += 256) {
+    const float4* col = reinterpret_cast<const float4*>(partials + (size_t)b * max_parts * ld_part) + g;
+    const size_t pitch4 = (size_t)(ld_part >> 2);
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q0 = 0; q0 < parts; q0 += 16) {
+      float4 tq[16];
 #pragma unroll
-    for (int q = 0; q < kOtMaxParts; ++q) tq[q] = q < parts ? __ldcg(col + (size_t)q * ld_part) : 0.f;
+      for (int q = 0; q < 16; ++q)
+        tq[q] = q0 + q < parts ? __ldcg(col + (size_t)(q0 + q) * pitch4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < kOtMaxParts; ++q) t += tq[q];
-    const float lse = logf(fmaxf(t, kOtTiny)) + ((d.mu_bin - vrow[j]) - kOtHeadroom);
-    vrow[j] = (j == d.m ? d.nu_bin : d.norm) - lse;
+      for (int q = 0; q < 16; ++q) { t[0] += tq[q].x; t[1] += tq[q].y; t[2] += tq[q].z; t[3] += tq[q].w; }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * g + e;
+      if (j <= d.m) {
+        const float lse = logf(fmaxf(t[e], kOtTiny)) + ((d.mu_bin - vrow[j]) - kOtHeadroom);
+        vrow[j] = (j == d.m ? d.nu_bin : d.norm) - lse;
+      }
+    }
   }
   if (threadIdx.x == 0) tickets[b] = 0;    // ready for the next iteration (next launch)
 }
@@ -353,9 +383,11 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp >> 1, side = warp & 1;
   const PairDims d = pair_dims(p, b);
-  if (d.n == 0 || d.m == 0) return;                       // uniform per block
   const int parts = cdiv(d.n + 1, rows_per_cta);
-  if ((int)blockIdx.x >= parts) return;                   // uniform per block
+  if (d.n == 0 || d.m == 0 || (int)blockIdx.x >= parts) {   // uniform per block
+    pdl_wait();                                             // (no CTA leaves before the predecessor completed: the chain of
+    return;                                                 // PDL waits stays transitive even if every CTA takes this exit)
+  }
   const int rows_per_team = rows_per_cta / NTEAM;         // rows_per_cta is a multiple of NTEAM
   const int row0 = blockIdx.x * rows_per_cta + team * rows_per_team;
   const int row_end = min(row0 + rows_per_team, d.n + 1);
@@ -372,12 +404,19 @@ __global__ void __launch_bounds__(NW * 32, 1) ot_iter_wide_kernel(OtParams p, fl
       tc::bulk_load(wrow + ((i - row0) % kOtRing) * HALF, S + (size_t)i * p.ldS, row_bytes, bar);
     }
   };
+  // PDL: S does not change between iterations -- the first rows are requested while the PREVIOUS iteration's last CTAs
+  // still fold their partial sums; u, v, partials and tickets are touched only behind pdl_wait().  This kernel triggers
+  // AFTER its wait, so when a successor starts, everything up to this kernel's predecessor has completed (the first
+  // iteration, whose predecessors wrote S, waits before it requests anything).
+  if (first) pdl_wait();
   if (lane == 0) {
     for (int q = 0; q < kOtRing; ++q) tc::mbar_init(&bars[warp * kOtRing + q], 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
     for (int q = 0; q < kOtRing; ++q) request(row0 + q);
   }
+  if (!first) pdl_wait();
+  pdl_trigger();
   __syncwarp();
   float* vrow = p.v + (size_t)b * p.ld_uv;
   for (int j0 = threadIdx.x; j0 < MAXM + 4; j0 += 8 * NT) {      // eight loads in flight per thread, then the stores
@@ -540,7 +579,7 @@ bool ot_fused_supported(const OtParams& p) {
 
 // floats of scratch for `pairs` pairs: per-pair tickets + one set of partial rows
 size_t ot_fused_scratch_floats(int pairs, int N, int M) {
-  return (size_t)round_up(pairs, 64) + (size_t)pairs * (M > kOtFusedMaxM ? kOtWideMaxParts : kOtMaxParts) * round_up(M + 1, 4);
+  return (size_t)round_up(pairs, 64) + (size_t)pairs * (M > kOtFusedMaxM ? kOtWideMaxParts : ot_parts_cap(pairs)) * round_up(M + 1, 4);
 }
 
 // `iters` full Sinkhorn iterations (u update then v update) starting from u = v = 0 (launch_ot_init); leaves u and v in
@@ -556,7 +595,8 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
   max_parts = std::min(max_parts, cdiv(p.N + 1, 24));
   if (!wide) max_parts = ot_fused_parts(p.B, p.N, num_sms);
   const int ld_part = round_up(p.M + 1, 4);
-  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), 24);                      // a multiple of 8 and of the 6 / 8 row teams
+  // a multiple of the 8 warps (register-resident kernel) or of the 6 / 8 row teams (wide kernels)
+  const int rows_per_cta = round_up(cdiv(p.N + 1, max_parts), wide ? 24 : 8);
   int* tickets = reinterpret_cast<int*>(scratch);
   float* partials = scratch + round_up(p.B, 64);
   cudaMemsetAsync(tickets, 0, sizeof(int) * p.B, ctx.stream);
@@ -564,14 +604,14 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
     ProfScope prof__(ctx, "ot_iter_fused");
     dim3 grid(max_parts, p.B);
     if (wide == 0)
-      ot_iter_kernel<<<grid, 256, kOtSmemBytes, ctx.stream>>>(p, partials, tickets, max_parts, ld_part, rows_per_cta,
-                                                              it == 0);
+      launch_pdl(ctx, ot_iter_kernel, grid, dim3(256), kOtSmemBytes, p, partials, tickets, max_parts, ld_part,
+                 rows_per_cta, (int)(it == 0));
     else if (wide == 1)
-      ot_iter_wide_kernel<8, 16><<<grid, 512, ot_wide_smem_bytes<8, 16>(), ctx.stream>>>(
-          p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
+      launch_pdl(ctx, ot_iter_wide_kernel<8, 16>, grid, dim3(512), ot_wide_smem_bytes<8, 16>(), p, partials, tickets,
+                 max_parts, ld_part, rows_per_cta, (int)(it == 0));
     else
-      ot_iter_wide_kernel<16, 12><<<grid, 384, ot_wide_smem_bytes<16, 12>(), ctx.stream>>>(
-          p, partials, tickets, max_parts, ld_part, rows_per_cta, it == 0);
+      launch_pdl(ctx, ot_iter_wide_kernel<16, 12>, grid, dim3(384), ot_wide_smem_bytes<16, 12>(), p, partials, tickets,
+                 max_parts, ld_part, rows_per_cta, (int)(it == 0));
     B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
   }
 }
@@ -607,6 +647,8 @@ __device__ __forceinline__ float z_at(const ZSource& z, int b, int i, int j, flo
 __global__ void __launch_bounds__(256) row_argmax_kernel(ZSource z, const int* counts0, const int* counts1,
                                                          int N, int M, int* __restrict__ idx0,
                                                          float* __restrict__ max0, int ld) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   const int b = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -631,6 +673,8 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(ZSource z, const int* c
 
 __global__ void __launch_bounds__(256) col_argmax_kernel(ZSource z, const int* counts0, const int* counts1,
                                                          int N, int M, int* __restrict__ idx1, int ld) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   __shared__ float rv[8][33];
   __shared__ int ri[8][33];
   const int b = blockIdx.y;
@@ -664,10 +708,10 @@ static void launch_argmax_common(LaunchCtx& ctx, const ZSource& z, const int* c0
   ProfScope prof__(ctx, "argmax");
   if (N <= 0 || M <= 0) return;
   dim3 g0(cdiv(N, 8), B);
-  row_argmax_kernel<<<g0, 256, 0, ctx.stream>>>(z, c0, c1, N, M, idx0, max0, ld);
+  launch_pdl(ctx, row_argmax_kernel, dim3(g0), dim3(256), 0, z, c0, c1, N, M, idx0, max0, ld);
   B200M_LAUNCH_CHECK(ctx, "row_argmax");
   dim3 g1(cdiv(M, 32), B);
-  col_argmax_kernel<<<g1, 256, 0, ctx.stream>>>(z, c0, c1, N, M, idx1, ld);
+  launch_pdl(ctx, col_argmax_kernel, dim3(g1), dim3(256), 0, z, c0, c1, N, M, idx1, ld);
   B200M_LAUNCH_CHECK(ctx, "col_argmax");
 }
 
@@ -688,6 +732,8 @@ __global__ void match_select_kernel(const int* __restrict__ idx0, const float* _
                                     int N, int M, float thr, long long* __restrict__ matches0,
                                     long long* __restrict__ matches1, float* __restrict__ ms0,
                                     float* __restrict__ ms1) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = counts0 ? counts0[b] : N, m = counts1 ? counts1[b] : M;
@@ -731,7 +777,7 @@ void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, con
   int T = N > M ? N : M;
   if (T <= 0) return;
   dim3 grid(cdiv(T, 256), B);
-  match_select_kernel<<<grid, 256, 0, ctx.stream>>>(idx0, max0, idx1, ld, counts0, counts1, N, M, thr, matches0,
+  launch_pdl(ctx, match_select_kernel, dim3(grid), dim3(256), 0, idx0, max0, idx1, ld, counts0, counts1, N, M, thr, matches0,
                                                     matches1, ms0, ms1);
   B200M_LAUNCH_CHECK(ctx, "match_select");
 }

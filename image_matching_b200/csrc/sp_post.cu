@@ -13,6 +13,8 @@ namespace b200m {
 // rows receives one 1024 B contiguous run per warp.
 __global__ void __launch_bounds__(128) softmax_heat_kernel(const float4* __restrict__ semi, int c4_total,
                                                            float* __restrict__ heat, int hc, int wc) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   const int n = blockIdx.z;
   const int cx = blockIdx.x * blockDim.x + threadIdx.x;
   const int cy = blockIdx.y;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(128) softmax_heat_kernel(const float4* __restr
 void launch_softmax_heat(LaunchCtx& ctx, const float* semi_c4, int c4_total, float* heat, int n, int hc, int wc) {
   ProfScope prof__(ctx, "softmax_heat");
   dim3 grid(cdiv(wc, 128), hc, n);
-  softmax_heat_kernel<<<grid, 128, 0, ctx.stream>>>(reinterpret_cast<const float4*>(semi_c4), c4_total, heat, hc, wc);
+  launch_pdl(ctx, softmax_heat_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<const float4*>(semi_c4), c4_total, heat, hc, wc);
   B200M_LAUNCH_CHECK(ctx, "softmax_heat");
 }
 
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(NT) nms_fused_r4_kernel(const float* __restric
                                                           unsigned long long* __restrict__ cand_keys,
                                                           int* __restrict__ cand_counts, int cand_cap,
                                                           int* __restrict__ overflow_flag) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   using SM = NmsFusedSmem<T>;
   extern __shared__ __align__(16) unsigned char nms_smem_raw[];
   SM& S = *reinterpret_cast<SM*>(nms_smem_raw);
@@ -317,8 +321,8 @@ static void launch_nms_fused_r4_t(LaunchCtx& ctx, const float* heat, float* nms_
   auto kern = nms_fused_r4_kernel<T, NT>;
   opt.ensure(kern, (int)sizeof(NmsFusedSmem<T>));
   dim3 grid(cdiv(W8, T), cdiv(H8, T), n);
-  kern<<<grid, NT, sizeof(NmsFusedSmem<T>), ctx.stream>>>(heat, nms_dense, H8, W8, thr, border, cand_keys, cand_counts,
-                                                         cand_cap, overflow_flag);
+  launch_pdl(ctx, kern, grid, dim3(NT), sizeof(NmsFusedSmem<T>), heat, nms_dense, H8, W8, thr, border, cand_keys,
+             cand_counts, cand_cap, overflow_flag);
   B200M_LAUNCH_CHECK(ctx, "nms_fused");
 }
 
@@ -390,6 +394,8 @@ __global__ void __launch_bounds__(1024) select_keypoints_kernel(unsigned long lo
                                                                 float* __restrict__ keypoints,
                                                                 float* __restrict__ scores,
                                                                 int* __restrict__ counts, int cap) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   extern __shared__ unsigned long long skeys[];
   const int n = blockIdx.x;
   unsigned long long* gk = cand_keys + (size_t)n * cand_cap;
@@ -480,7 +486,7 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
   static SmemOptIn opt;
   size_t bytes = (size_t)kSelectSmemKeys * sizeof(unsigned long long);
   opt.ensure(select_keypoints_kernel, (int)bytes);
-  select_keypoints_kernel<<<n, 1024, bytes, ctx.stream>>>(cand_keys, cand_counts, cand_cap, W8, max_kp,
+  launch_pdl(ctx, select_keypoints_kernel, dim3(n), dim3(1024), bytes, cand_keys, cand_counts, cand_cap, W8, max_kp,
                                                         keypoints, scores, counts, cap);
   B200M_LAUNCH_CHECK(ctx, "select_keypoints");
 }
@@ -488,6 +494,8 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
 // Sticky error flags (candidate-list overflow, fp16 activation overflow) are surfaced through the per-image counts
 // the caller reads back anyway: counts[i] = -1 / -2, so no extra host synchronisation is needed.
 __global__ void apply_flags_kernel(const int* __restrict__ flags, int* __restrict__ counts, int n) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (flags[1]) counts[i] = -2;
@@ -496,7 +504,7 @@ __global__ void apply_flags_kernel(const int* __restrict__ flags, int* __restric
 
 void launch_apply_flags(LaunchCtx& ctx, const int* flags, int* counts, int n) {
   ProfScope prof__(ctx, "apply_flags");
-  apply_flags_kernel<<<cdiv(n, 128), 128, 0, ctx.stream>>>(flags, counts, n);
+  launch_pdl(ctx, apply_flags_kernel, dim3(cdiv(n, 128)), dim3(128), 0, flags, counts, n);
   B200M_LAUNCH_CHECK(ctx, "apply_flags");
 }
 
@@ -509,6 +517,8 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
                                                           float* __restrict__ out_dcn, float* __restrict__ out_tok,
                                                           int tok_ld, size_t tok_img_stride,
                                                           const float* __restrict__ sumsq, int ncb) {
+  pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
+  pdl_wait();
   const int n = blockIdx.y;
   const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -604,7 +614,7 @@ void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_tota
   ProfScope prof__(ctx, "sample_descriptors");
   if (cap <= 0) return;
   dim3 grid(cdiv(cap, 8), n);
-  sample_desc_kernel<<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const float4*>(desc_c4), c4_total, D, hc, wc,
+  launch_pdl(ctx, sample_desc_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<const float4*>(desc_c4), c4_total, D, hc, wc,
                                                    keypoints, counts, cap, align_corners, out_dcn, out_tok,
                                                    tok_ld, tok_img_stride, sumsq, ncb);
   B200M_LAUNCH_CHECK(ctx, "sample_descriptors");

@@ -246,6 +246,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PDL: the key counts and the first Q / K / V^T loads of the set-up below already depend on earlier kernels of the
+  // stream, so the wait comes first; what overlaps the predecessor's tail is this grid's launch and CTA scheduling
+  pdl_trigger();
+  pdl_wait();
 #ifdef B200M_ATTN_TRACE
   long long* const tr = g_attn_trace ? g_attn_trace + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   if (tr && threadIdx.x == 64) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tr[0] = sm; tr[1] = clock64(); }
@@ -613,7 +617,7 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
     cudaMemcpyToSymbol(g_attn_trace, &tbuf, sizeof(tbuf));
   }
 #endif
-  kern<<<grid, 320, SM::BYTES, ctx.stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
+  launch_pdl(ctx, kern, grid, dim3(320), SM::BYTES, mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_attention");
 #ifdef B200M_ATTN_TRACE
   if (tbuf && n == 40) {

@@ -119,6 +119,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barriers, tensor memory, descriptor prefetch) and the producer's weight requests below are
+  // independent of the preceding kernel; activations are only read, and outputs only written, behind pdl_wait()
+  pdl_trigger();
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
   auto decode = [&](int tile, int& cb, int& x0, int& y0, int& img) {
     cb = tile % ncb;
@@ -148,6 +152,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       for (int i = 0; i < kTcNB; ++i)
         bulk_load(sB + i * SM::B_SLOT, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)i * SM::B_SLOT, SM::B_SLOT, w_full);
     }
+    pdl_wait();
     if (!FUSE1 && (int)blockIdx.x < total) issue_A(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int cb = tile % ncb;
@@ -443,7 +448,7 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   if (!opt.ensure(kern, (int)SM::BYTES)) return false;
   const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
   const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, SM::THREADS, SM::BYTES, ctx.stream>>>(tm_hi, tm_lo, p);
+  launch_pdl(ctx, kern, dim3(grid), dim3(SM::THREADS), SM::BYTES, tm_hi, tm_lo, p);
   B200M_LAUNCH_CHECK(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
   return true;
 }

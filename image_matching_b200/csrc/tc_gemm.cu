@@ -61,6 +61,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();      // PDL: barrier / tensor-memory set-up runs under the preceding kernel's tail
 #ifdef B200M_GEMM_TRACE
   long long* const tr = g_gemm_trace;
   bool traced = false;
@@ -87,6 +88,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // operands are read, and anything written, only from here on
 
   if (warp == 0 && lane == 0) {
     int s = 0, ph = 0;
@@ -402,7 +404,7 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   cudaMemcpyToSymbolAsync(g_gemm_trace, &arg, sizeof(arg), 0, cudaMemcpyHostToDevice, ctx.stream);
   if (want) cudaMemsetAsync(tbuf, 0, 128 * 8, ctx.stream);
 #endif
-  tc_gemm_kernel<<<grid, 320, kGemmSmem, ctx.stream>>>(ma, mh, ml, p);
+  launch_pdl(ctx, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
 #ifdef B200M_GEMM_TRACE
   if (want) {

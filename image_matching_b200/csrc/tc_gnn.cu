@@ -95,6 +95,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
 #define GT_ARM(cond) do { } while (0)
 #endif
   if (smem_u32(smem) & 1023) __trap();
+  pdl_trigger();      // PDL: biases (weights), barriers and tensor memory are set up under the preceding kernel's tail
   for (int i = threadIdx.x; i < kGnBiasFloats; i += blockDim.x) sBias[i] = p.bias[i];
   const int ntiles = cdiv(p.rows, 128);
   const int n_wtiles = 12 + 2 * p.nt4;      // weight tiles per token tile after GEMM1: GEMM2 8, GEMM3 4, GEMM4 2 per column tile
@@ -119,6 +120,7 @@ tc_gnn_layer_kernel(const __grid_constant__ CUtensorMap tm_att_hi, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // activations are read, and anything written, only from here on
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -581,7 +583,7 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
     cudaMemcpyToSymbol(g_gnn_trace, &tbuf, sizeof(tbuf));
   }
 #endif
-  tc_gnn_layer_kernel<<<grid, 320, kGnSmem, ctx.stream>>>(ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
+  launch_pdl(ctx, tc_gnn_layer_kernel, dim3(grid), dim3(320), kGnSmem, ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gnn_layer");
 #ifdef B200M_GNN_TRACE
   if (tbuf) {
