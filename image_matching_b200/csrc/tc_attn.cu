@@ -185,16 +185,61 @@ struct TcAttnParams {
   int ldq; long long rows;
 };
 
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long splat_f32x2(float v) { return pack_f32x2(v, v); }
+
+// EXPERIMENT, off in the product (B200M_ATTN_NPOLY = 0): measured on B200 at C2, moving 2 / 3 / 4 of a thread's 16
+// pairs per tile from the MUFU to this polynomial made the kernel SLOWER (4.76 -> 5.09 / 5.23 / 5.28 ms per step): the
+// tile loop is paced by instruction issue and dependency latency, not by MUFU throughput alone.
+// (2^xa, 2^xb) on the FMA pipe instead of the MUFU: round-to-nearest range reduction x = n + f (magic-number add),
+// degree-5 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 2.1e-7 evaluated in fp32 -- the class of
+// ex2.approx's 2^-22), n added to the exponent field with integer arithmetic.  Packed fp32 instructions (two IEEE
+// operations per issue slot).  Inputs are clamped to [-126, 127]: below, the result (~1e-38) packs to an fp16 zero exactly
+// like ex2.approx.ftz's 0; above, 2^127 packs to an fp16 infinity, which raises the reference like an overflowed ex2.
+#ifndef B200M_ATTN_NPOLY
+#define B200M_ATTN_NPOLY 0            // pairs of a thread's 16 per key tile that take this path (0 = all MUFU)
+#endif
+__device__ __forceinline__ void exp2_poly_x2(unsigned long long x, float& ya, float& yb) {
+  float xa, xb;
+  unpack_f32x2(x, xa, xb);
+  x = pack_f32x2(fminf(fmaxf(xa, -126.f), 127.f), fminf(fmaxf(xb, -126.f), 127.f));
+  const unsigned long long t = add_f32x2(x, splat_f32x2(12582912.f));          // 1.5 * 2^23: integer part in the low mantissa bits
+  const unsigned long long n = add_f32x2(t, splat_f32x2(-12582912.f));
+  const unsigned long long f = fma_f32x2(n, splat_f32x2(-1.f), x);             // exact
+  unsigned long long p = splat_f32x2(0.0013276472454890609f);
+  p = fma_f32x2(p, f, splat_f32x2(0.009675540961325169f));
+  p = fma_f32x2(p, f, splat_f32x2(0.05550713092088699f));
+  p = fma_f32x2(p, f, splat_f32x2(0.24022120237350464f));
+  p = fma_f32x2(p, f, splat_f32x2(0.6931469440460205f));
+  p = fma_f32x2(p, f, splat_f32x2(1.0000001192092896f));
+  float pa, pb, ta, tb;
+  unpack_f32x2(p, pa, pb);
+  unpack_f32x2(t, ta, tb);
+  ya = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+  yb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
+}
+
 // this thread's KH scores -> p = 2^(s c + neg) as packed fp16 hi / lo words; returns the packed maximum of the hi words
 // SUM: also returns the sum of the p (otherwise the packed maximum of the hi words, as a float)
 template <int KH, bool SUM>
 __device__ __forceinline__ float softmax_words(const float* s, float c, float neg, uint32_t* hi, uint32_t* lo) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};                                    // four chains: the adds hide behind the MUFU
   __half2 pm = __float2half2_rn(0.f);
+  const unsigned long long c2 = splat_f32x2(c), neg2 = splat_f32x2(neg);
 #pragma unroll
   for (int i = 0; i < KH / 2; ++i) {
-    const float a = fast_exp2(fmaf(s[2 * i], c, neg));                    // exp2(-inf) = 0 for masked keys
-    const float b = fast_exp2(fmaf(s[2 * i + 1], c, neg));
+    float a, b;
+    if (B200M_ATTN_NPOLY > 0 && (i * B200M_ATTN_NPOLY) % (KH / 2) < B200M_ATTN_NPOLY && KH == 32) {
+      exp2_poly_x2(fma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), c2, neg2), a, b);
+    } else {
+      // (one packed fma.rn.f32x2 for the pair's two arguments measured slower as well: 4.45 -> 4.8 ms)
+      a = fast_exp2(fmaf(s[2 * i], c, neg));                                // exp2(-inf) = 0 for masked keys
+      b = fast_exp2(fmaf(s[2 * i + 1], c, neg));
+    }
     if constexpr (SUM) acc[i & 3] += a + b;
     const uint32_t h = pack_f16x2(a, b);
     float ra, rb;

@@ -38,4 +38,4 @@ for B in sizes:
     e1.record()
     torch.cuda.synchronize()
     out.append(f"B={B}: {e0.elapsed_time(e1) / n:.3f} ms")
-print("  ".join(out), f"(valid matches of the last batch: {int((o['matches0'] > -1).sum())})")
+print("  ".join(out), f"(valid matches of the last batch: {int((o['matches0'] > -1).sum())}; graph replays {m._engine.graph_replays()})")
