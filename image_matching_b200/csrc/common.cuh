@@ -118,9 +118,22 @@ inline bool pdl_enabled() {
   return on != 0;
 }
 
+// Kernel classes for the large-batch PDL mask: which classes keep the attribute when LaunchCtx::pdl is off.  Default: the
+// Sinkhorn iterations only -- the next iteration's CTAs request their first rows of S while the last CTA of each pair
+// still folds the partial column sums (64 pairs per call: 27.17 -> 27.05 ms per step, twice on the same box; conv,
+// attention + fused layer, post-processing classes each measured neutral or slower).  B200M_PDL_MASK overrides.
+enum PdlClass { kPdlConv = 1, kPdlAttn = 2, kPdlGnn = 4, kPdlGemm = 8, kPdlOt = 16, kPdlPost = 32 };
+inline int pdl_large_mask() {
+  static const int m = [] {
+    const char* e = getenv("B200M_PDL_MASK");
+    return e ? atoi(e) : (int)kPdlOt;
+  }();
+  return m;
+}
+
 // kern<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialisation attribute
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(LaunchCtx& ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+inline void launch_pdl(LaunchCtx& ctx, int cls, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -130,7 +143,7 @@ inline void launch_pdl(LaunchCtx& ctx, void (*kern)(KArgs...), dim3 grid, dim3 b
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (ctx.pdl && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && (ctx.pdl || (pdl_large_mask() & cls))) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -120,7 +120,7 @@ void launch_gemm(LaunchCtx& ctx, const GemmParams& p) {
   ProfScope prof__(ctx, "gemm");
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
   dim3 grid(cdiv(p.N, GN), cdiv(p.M, GM), p.batch);
-  launch_pdl(ctx, gemm_tn_kernel, dim3(grid), dim3(256), 0, p);
+  launch_pdl(ctx, kPdlGemm, gemm_tn_kernel, dim3(grid), dim3(256), 0, p);
   B200M_LAUNCH_CHECK(ctx, "gemm_tn");
 }
 
@@ -228,7 +228,7 @@ void launch_kenc_input(LaunchCtx& ctx, const float* kpts, const float* scores, i
                        float cx, float cy, float scale, float* out4) {
   ProfScope prof__(ctx, "kenc_input");
   int total = B * Np;
-  launch_pdl(ctx, kenc_input_kernel, dim3(cdiv(total, 256)), dim3(256), 0, kpts, scores, N, Np, cx, cy, scale,
+  launch_pdl(ctx, kPdlGemm, kenc_input_kernel, dim3(cdiv(total, 256)), dim3(256), 0, kpts, scores, N, Np, cx, cy, scale,
                                                                 reinterpret_cast<float4*>(out4), total);
   B200M_LAUNCH_CHECK(ctx, "kenc_input");
 }

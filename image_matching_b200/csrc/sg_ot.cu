@@ -32,7 +32,7 @@ __global__ void ot_init_kernel(float* u, float* v, int total) {
 void launch_ot_init(LaunchCtx& ctx, const OtParams& p) {
   ProfScope prof__(ctx, "ot_init");
   int total = p.B * p.ld_uv;
-  launch_pdl(ctx, ot_init_kernel, dim3(cdiv(total, 256)), dim3(256), 0, p.u, p.v, total);
+  launch_pdl(ctx, kPdlPost, ot_init_kernel, dim3(cdiv(total, 256)), dim3(256), 0, p.u, p.v, total);
   B200M_LAUNCH_CHECK(ctx, "ot_init");
 }
 
@@ -604,13 +604,13 @@ void launch_ot_sinkhorn_fused(LaunchCtx& ctx, const OtParams& p, int iters, floa
     ProfScope prof__(ctx, "ot_iter_fused");
     dim3 grid(max_parts, p.B);
     if (wide == 0)
-      launch_pdl(ctx, ot_iter_kernel, grid, dim3(256), kOtSmemBytes, p, partials, tickets, max_parts, ld_part,
+      launch_pdl(ctx, kPdlOt, ot_iter_kernel, grid, dim3(256), kOtSmemBytes, p, partials, tickets, max_parts, ld_part,
                  rows_per_cta, (int)(it == 0));
     else if (wide == 1)
-      launch_pdl(ctx, ot_iter_wide_kernel<8, 16>, grid, dim3(512), ot_wide_smem_bytes<8, 16>(), p, partials, tickets,
+      launch_pdl(ctx, kPdlOt, ot_iter_wide_kernel<8, 16>, grid, dim3(512), ot_wide_smem_bytes<8, 16>(), p, partials, tickets,
                  max_parts, ld_part, rows_per_cta, (int)(it == 0));
     else
-      launch_pdl(ctx, ot_iter_wide_kernel<16, 12>, grid, dim3(384), ot_wide_smem_bytes<16, 12>(), p, partials, tickets,
+      launch_pdl(ctx, kPdlOt, ot_iter_wide_kernel<16, 12>, grid, dim3(384), ot_wide_smem_bytes<16, 12>(), p, partials, tickets,
                  max_parts, ld_part, rows_per_cta, (int)(it == 0));
     B200M_LAUNCH_CHECK(ctx, "ot_iter_fused");
   }
@@ -708,10 +708,10 @@ static void launch_argmax_common(LaunchCtx& ctx, const ZSource& z, const int* c0
   ProfScope prof__(ctx, "argmax");
   if (N <= 0 || M <= 0) return;
   dim3 g0(cdiv(N, 8), B);
-  launch_pdl(ctx, row_argmax_kernel, dim3(g0), dim3(256), 0, z, c0, c1, N, M, idx0, max0, ld);
+  launch_pdl(ctx, kPdlPost, row_argmax_kernel, dim3(g0), dim3(256), 0, z, c0, c1, N, M, idx0, max0, ld);
   B200M_LAUNCH_CHECK(ctx, "row_argmax");
   dim3 g1(cdiv(M, 32), B);
-  launch_pdl(ctx, col_argmax_kernel, dim3(g1), dim3(256), 0, z, c0, c1, N, M, idx1, ld);
+  launch_pdl(ctx, kPdlPost, col_argmax_kernel, dim3(g1), dim3(256), 0, z, c0, c1, N, M, idx1, ld);
   B200M_LAUNCH_CHECK(ctx, "col_argmax");
 }
 
@@ -777,7 +777,7 @@ void launch_match_select(LaunchCtx& ctx, const int* idx0, const float* max0, con
   int T = N > M ? N : M;
   if (T <= 0) return;
   dim3 grid(cdiv(T, 256), B);
-  launch_pdl(ctx, match_select_kernel, dim3(grid), dim3(256), 0, idx0, max0, idx1, ld, counts0, counts1, N, M, thr, matches0,
+  launch_pdl(ctx, kPdlPost, match_select_kernel, dim3(grid), dim3(256), 0, idx0, max0, idx1, ld, counts0, counts1, N, M, thr, matches0,
                                                     matches1, ms0, ms1);
   B200M_LAUNCH_CHECK(ctx, "match_select");
 }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) softmax_heat_kernel(const float4* __restr
 void launch_softmax_heat(LaunchCtx& ctx, const float* semi_c4, int c4_total, float* heat, int n, int hc, int wc) {
   ProfScope prof__(ctx, "softmax_heat");
   dim3 grid(cdiv(wc, 128), hc, n);
-  launch_pdl(ctx, softmax_heat_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<const float4*>(semi_c4), c4_total, heat, hc, wc);
+  launch_pdl(ctx, kPdlPost, softmax_heat_kernel, dim3(grid), dim3(128), 0, reinterpret_cast<const float4*>(semi_c4), c4_total, heat, hc, wc);
   B200M_LAUNCH_CHECK(ctx, "softmax_heat");
 }
 
@@ -321,7 +321,7 @@ static void launch_nms_fused_r4_t(LaunchCtx& ctx, const float* heat, float* nms_
   auto kern = nms_fused_r4_kernel<T, NT>;
   opt.ensure(kern, (int)sizeof(NmsFusedSmem<T>));
   dim3 grid(cdiv(W8, T), cdiv(H8, T), n);
-  launch_pdl(ctx, kern, grid, dim3(NT), sizeof(NmsFusedSmem<T>), heat, nms_dense, H8, W8, thr, border, cand_keys,
+  launch_pdl(ctx, kPdlPost, kern, grid, dim3(NT), sizeof(NmsFusedSmem<T>), heat, nms_dense, H8, W8, thr, border, cand_keys,
              cand_counts, cand_cap, overflow_flag);
   B200M_LAUNCH_CHECK(ctx, "nms_fused");
 }
@@ -486,7 +486,7 @@ void launch_select_keypoints(LaunchCtx& ctx, unsigned long long* cand_keys, cons
   static SmemOptIn opt;
   size_t bytes = (size_t)kSelectSmemKeys * sizeof(unsigned long long);
   opt.ensure(select_keypoints_kernel, (int)bytes);
-  launch_pdl(ctx, select_keypoints_kernel, dim3(n), dim3(1024), bytes, cand_keys, cand_counts, cand_cap, W8, max_kp,
+  launch_pdl(ctx, kPdlPost, select_keypoints_kernel, dim3(n), dim3(1024), bytes, cand_keys, cand_counts, cand_cap, W8, max_kp,
                                                         keypoints, scores, counts, cap);
   B200M_LAUNCH_CHECK(ctx, "select_keypoints");
 }
@@ -504,7 +504,7 @@ __global__ void apply_flags_kernel(const int* __restrict__ flags, int* __restric
 
 void launch_apply_flags(LaunchCtx& ctx, const int* flags, int* counts, int n) {
   ProfScope prof__(ctx, "apply_flags");
-  launch_pdl(ctx, apply_flags_kernel, dim3(cdiv(n, 128)), dim3(128), 0, flags, counts, n);
+  launch_pdl(ctx, kPdlPost, apply_flags_kernel, dim3(cdiv(n, 128)), dim3(128), 0, flags, counts, n);
   B200M_LAUNCH_CHECK(ctx, "apply_flags");
 }
 
@@ -614,7 +614,7 @@ void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_tota
   ProfScope prof__(ctx, "sample_descriptors");
   if (cap <= 0) return;
   dim3 grid(cdiv(cap, 8), n);
-  launch_pdl(ctx, sample_desc_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<const float4*>(desc_c4), c4_total, D, hc, wc,
+  launch_pdl(ctx, kPdlPost, sample_desc_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<const float4*>(desc_c4), c4_total, D, hc, wc,
                                                    keypoints, counts, cap, align_corners, out_dcn, out_tok,
                                                    tok_ld, tok_img_stride, sumsq, ncb);
   B200M_LAUNCH_CHECK(ctx, "sample_descriptors");

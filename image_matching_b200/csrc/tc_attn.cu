@@ -662,7 +662,7 @@ static bool launch_tc_attn_t(LaunchCtx& ctx, const void* qkv_hi, const void* qkv
     cudaMemcpyToSymbol(g_attn_trace, &tbuf, sizeof(tbuf));
   }
 #endif
-  launch_pdl(ctx, kern, grid, dim3(320), SM::BYTES, mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
+  launch_pdl(ctx, kPdlAttn, kern, grid, dim3(320), SM::BYTES, mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_attention");
 #ifdef B200M_ATTN_TRACE
   if (tbuf && n == 40) {

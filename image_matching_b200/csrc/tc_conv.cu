@@ -448,7 +448,7 @@ static bool launch_tc_t(LaunchCtx& ctx, const TcConvParams& p, int num_sms) {
   if (!opt.ensure(kern, (int)SM::BYTES)) return false;
   const int total = p.n * cdiv(p.H, kTcTile) * cdiv(p.W, kTcTile) * (p.cout_pad / NB);
   const int grid = total < num_sms ? total : num_sms;
-  launch_pdl(ctx, kern, dim3(grid), dim3(SM::THREADS), SM::BYTES, tm_hi, tm_lo, p);
+  launch_pdl(ctx, kPdlConv, kern, dim3(grid), dim3(SM::THREADS), SM::BYTES, tm_hi, tm_lo, p);
   B200M_LAUNCH_CHECK(ctx, KS == 3 ? "tc_conv3x3" : "tc_conv1x1");
   return true;
 }

@@ -404,7 +404,7 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   cudaMemcpyToSymbolAsync(g_gemm_trace, &arg, sizeof(arg), 0, cudaMemcpyHostToDevice, ctx.stream);
   if (want) cudaMemsetAsync(tbuf, 0, 128 * 8, ctx.stream);
 #endif
-  launch_pdl(ctx, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, mh, ml, p);
+  launch_pdl(ctx, kPdlGemm, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
 #ifdef B200M_GEMM_TRACE
   if (want) {

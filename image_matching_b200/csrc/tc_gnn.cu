@@ -583,7 +583,7 @@ bool launch_tc_gnn_layer(LaunchCtx& ctx, const GnnFusedParams& p, const void* at
     cudaMemcpyToSymbol(g_gnn_trace, &tbuf, sizeof(tbuf));
   }
 #endif
-  launch_pdl(ctx, tc_gnn_layer_kernel, dim3(grid), dim3(320), kGnSmem, ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
+  launch_pdl(ctx, kPdlGnn, tc_gnn_layer_kernel, dim3(grid), dim3(320), kGnSmem, ma_hi, ma_lo, mx, mq_hi, mq_lo, mv_hi, mv_lo, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gnn_layer");
 #ifdef B200M_GNN_TRACE
   if (tbuf) {
