@@ -1443,7 +1443,8 @@ static int matching_forward_impl(b200m_handle* h, const void* image0, const void
   // Few pairs (the reference caller's loop runs ONE pair per call): a single image leaves most of the chip idle in the
   // 1/4- and 1/8-resolution layers and in the detector post-processing, so the two images' SuperPoint passes run
   // side by side -- image 1 on a forked stream with its own workspace (inside the captured graph: a parallel branch).
-  bool dual = B <= h->sp_dual_max && !h->prof.enabled && ws_bytes >= 2 * sp_bytes;
+  bool dual = B <= h->sp_dual_max && !h->prof.enabled &&
+              ws_bytes >= 2 * sp_bytes + b200m_superglue_workspace_bytes(h, B, cap, cap);   // (else: one after the other)
   if (dual && !h->side_stream) {
     if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess ||

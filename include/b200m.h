@@ -177,6 +177,11 @@ int b200m_match_select(b200m_handle* h, const float* Z, int B, int N, int M,
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Matching (the drop-in entry point) ---------------------------------------------------- */
+/* Workspace for B pairs.  For B <= 16 it holds one SuperPoint workspace PER IMAGE SIDE: the two sides' SuperPoint
+ * passes of a small batch then run concurrently (image1 on a handle-owned stream forked from / joined to `stream`,
+ * a parallel branch of the captured graph) -- the reference's caller runs one pair per call
+ * (superpoint_glue_test.py:65-78), where a single image leaves most of the chip idle.  A smaller workspace (the
+ * single-side size) is accepted and runs the sides one after the other.  B200M_SP_DUAL_MAX overrides the bound. */
 size_t b200m_matching_workspace_bytes(const b200m_handle* h, int B, int H, int W);
 /* image0/image1 (B,1,H,W) fp32 device.  SuperPoint outputs as in b200m_superpoint_forward for each
  * side (capacity `cap`); matches0/1 (B,cap) int64, matching_scores0/1 (B,cap).  No host sync:
