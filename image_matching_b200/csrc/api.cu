@@ -712,6 +712,8 @@ struct SgWs {
   int Np, ldS, ld_uv;
   size_t rows;           // 2 * B * Np
   float *X, *QKV, *QKV_lo, *VT, *VT_lo, *MSG, *HID, *IN4, *S, *u, *v, *max0, *ot_part;
+  float* XP;             // [x ; merged message] as fp16 operand planes (hi [rows][2D] halves, then lo): the A operand of
+                         // the layer GEMMs when the layers run as tc_gemm launches (D != 128); null on the fused path
   int *idx0, *idx1;
 };
 // pairs per Sinkhorn micro-batch: their score matrices share the L2
@@ -736,6 +738,9 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
   w.VT_lo = h->use_tc_attn ? A.take<float>(w.rows * D) : nullptr;
   w.MSG = A.take<float>(w.rows * D);
   w.HID = A.take<float>(w.rows * 2 * D);
+  // (widths whose head size the tensor-core attention kernel covers: 16, 32, 64)
+  w.XP = (h->use_tc_attn && h->use_tc_gemm && !(h->use_fused_gnn && D == 128) && (D == 64 || D == 128 || D == 256))
+             ? A.take<float>(w.rows * 2 * D) : nullptr;
   w.IN4 = A.take<float>(w.rows * 4);
   w.S = A.take<float>((size_t)B * std::max(N, 1) * w.ldS);
   w.u = A.take<float>((size_t)B * w.ld_uv);
@@ -747,10 +752,21 @@ bool sg_carve(const b200m_handle* h, int B, int N, int M, Arena& A, SgWs& w) {
   return A.ok;
 }
 
+// operand-plane input (A_hi / A_lo, lda_p halves) and the additional plane copy of an fp32 result (P_hi / P_lo, ldp)
+struct PlaneIO {
+  const void* A_hi = nullptr; const void* A_lo = nullptr; int lda_p = 0;
+  void* P_hi = nullptr; void* P_lo = nullptr; int ldp = 0;
+};
+
 void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A, int lda, float* C, int ldc,
                 size_t M, bool relu, bool accumulate, float* C_lo = nullptr, float* VT = nullptr,
-                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1, float lo_scale = 1.f) {   // C_lo set => fp16 plane outputs
+                float* VT_lo = nullptr, int vt_col0 = 0, int vt_np = 1, float lo_scale = 1.f,   // C_lo set => fp16 plane outputs
+                const PlaneIO* pio = nullptr) {
   GemmParams p;
+  if (pio) {
+    p.A_hi_p = pio->A_hi; p.A_lo_p = pio->A_lo; p.lda_p = pio->lda_p;
+    p.P_hi = pio->P_hi; p.P_lo = pio->P_lo; p.ldp = pio->ldp;
+  }
   p.A = A; p.lda = lda; p.strideA = 0;
   p.Bw = h->d_w + L.w_off; p.ldb = L.K; p.strideB = 0;
   p.C = C; p.ldc = ldc; p.strideC = 0;
@@ -761,6 +777,13 @@ void run_linear(b200m_handle* h, LaunchCtx& ctx, const Linear& L, const float* A
   p.VT = VT; p.VT_lo = VT_lo; p.vt_col0 = vt_col0; p.vt_np = vt_np; p.lo_scale = lo_scale;
   p.single = h->single_gemm ? 1 : 0;
   if (h->use_tc_gemm && launch_tc_gemm(ctx, p, h->d_w + L.w_hi_off, h->d_w + L.w_lo_off, h->num_sms)) return;
+  if (pio) {                 // plane operands / outputs exist only on the tensor-core path: no CUDA-core fallback
+    if (ctx.err == cudaSuccess) {
+      ctx.err = cudaErrorLaunchFailure;
+      *ctx.err_where = "tc_gemm with operand planes (launch declined)";
+    }
+    return;
+  }
   launch_gemm(ctx, p);
 }
 
@@ -824,6 +847,45 @@ void sg_gnn(b200m_handle* h, LaunchCtx& ctx, const SgWs& w, int B, const int* c0
         ctx.err = cudaErrorLaunchFailure;
         *ctx.err_where = "fused GNN layer (launch declined)";
       }
+    }
+    return;
+  }
+  if (w.XP && h->use_tc_attn && h->use_tc_gemm && l_begin < l_end) {
+    // Layers as tc_gemm launches (D != 128: the fused kernel's operands do not fit one SM) with every A
+    // operand in fp16 hi / lo*2048 PLANE format, written by the producing kernel's epilogue: the GEMMs skip their
+    // in-kernel split (at D = 256 the kernel is bound by shared-memory bandwidth, and the split moves 64 of the 208 KB
+    // a pipeline stage moves).  The planes hold exactly the values the in-kernel split derives from the fp32 data, so
+    // the results are bit-identical to the fp32-input path.
+    //   XP = [x ; merged message] planes, MSG = attention output planes, HID = hidden-layer planes, X[:, :D] fp32 residual
+    __half* xp_hi = reinterpret_cast<__half*>(w.XP);
+    __half* xp_lo = xp_hi + w.rows * 2 * D;
+    __half* att_hi = reinterpret_cast<__half*>(w.MSG);
+    __half* att_lo = att_hi + w.rows * D;
+    __half* hid_hi = reinterpret_cast<__half*>(w.HID);
+    __half* hid_lo = hid_hi + w.rows * 2 * D;
+    launch_split_planes(ctx, w.X, 2 * D, xp_hi, xp_lo, 2 * D, w.rows, D);
+    bool ok = true;
+    for (int l = l_begin; l < l_end && ok; ++l) {
+      const b200m_handle::Gnn& G = h->gnn[l];
+      const bool cross = h->cfg.gnn_cross[l] != 0;
+      PlaneIO x_in;   x_in.A_hi = xp_hi; x_in.A_lo = xp_lo; x_in.lda_p = 2 * D;
+      run_linear(h, ctx, G.qkv, w.X, 2 * D, w.QKV, 3 * D, w.rows, false, false, w.QKV_lo, w.VT, w.VT_lo, 2 * D, w.Np, 1.f,
+                 &x_in);
+      ok = launch_tc_attention(ctx, w.QKV, w.QKV_lo, w.VT, w.VT_lo, nullptr, B, w.Np, D, kHeads, c0, c1, N, M, cross,
+                               att_hi, att_lo, h->single_attn);
+      PlaneIO att_in; att_in.A_hi = att_hi; att_in.A_lo = att_lo; att_in.lda_p = D;
+      run_linear(h, ctx, G.merge, nullptr, D, reinterpret_cast<float*>(xp_hi + D), 2 * D, w.rows, false, false,
+                 reinterpret_cast<float*>(xp_lo + D), nullptr, nullptr, 0, 1, 2048.f, &att_in);       // -> XP[:, D:2D]
+      run_linear(h, ctx, G.mlp1, nullptr, 2 * D, reinterpret_cast<float*>(hid_hi), 2 * D, w.rows, true, false,
+                 reinterpret_cast<float*>(hid_lo), nullptr, nullptr, 0, 1, 2048.f, &x_in);            // relu(bn(W1 [x;msg]))
+      PlaneIO hid_io; hid_io.A_hi = hid_hi; hid_io.A_lo = hid_lo; hid_io.lda_p = 2 * D;
+      hid_io.P_hi = xp_hi; hid_io.P_lo = xp_lo; hid_io.ldp = 2 * D;
+      run_linear(h, ctx, G.mlp2, nullptr, 2 * D, w.X, 2 * D, w.rows, false, true, nullptr, nullptr, nullptr, 0, 1, 1.f,
+                 &hid_io);                                                                          // x += W2 hid (+ planes)
+    }
+    if (!ok && ctx.err == cudaSuccess) {
+      ctx.err = cudaErrorLaunchFailure;
+      *ctx.err_where = "tensor-core attention (launch declined)";
     }
     return;
   }

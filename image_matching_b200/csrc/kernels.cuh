@@ -135,11 +135,19 @@ struct GemmParams {
   // tensor-core GEMM, batch > 1: rows of A / W of problem b start at b * batch_rows_a / b * batch_rows_b of the same arrays
   int batch_rows_a = 0, batch_rows_b = 0;
   int single = 0;              // precision experiment (B200M_SINGLE=gemm): hi planes only
+  // tensor-core GEMM only.  A given as fp16 hi / lo*2048 operand planes [M][lda_p] (halves) instead of fp32: the planes go
+  // straight from TMA into the MMA's operand tiles and the in-kernel split (its 64 KB of shared-memory traffic per stage)
+  // is skipped.  A stays the fp32 alias for the CUDA-core fallback and may be null when the planes are given.
+  const void* A_hi_p = nullptr; const void* A_lo_p = nullptr; int lda_p = 0;
+  // fp32 epilogue: ALSO write the result as fp16 hi / lo*2048 planes P_hi / P_lo [M][ldp] (halves) -- the next GEMM's A
+  void* P_hi = nullptr; void* P_lo = nullptr; int ldp = 0;
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
 // tcgen05 fp16x3 version for weight GEMMs (w_hi / w_lo: [N][K] fp16 planes, lo scaled by 2048); false if declined
 bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, const float* w_lo, int num_sms);
 void gemm_pack_fp16_planes(const float* w, size_t n, float* hi_as_float, float* lo_as_float);   // host
+// fp32 [rows][ld_in] (first `cols` columns, cols % 8 == 0) -> fp16 operand planes hi / lo*2048 [rows][ld_out] (halves)
+void launch_split_planes(LaunchCtx& ctx, const float* in, int ld_in, void* hi, void* lo, int ld_out, size_t rows, int cols);
 // (B,C,N) channel-major <-> token-major [B][N][ld] (first C columns)
 void launch_bcn_to_tokens(LaunchCtx& ctx, const float* in, int B, int C, int N, float* out, int Np, int ld);
 void launch_tokens_to_bcn(LaunchCtx& ctx, const float* in, int Np, int ld, float* out, int B, int C, int N);

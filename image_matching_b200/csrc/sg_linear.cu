@@ -205,6 +205,39 @@ void launch_qkv_to_f16_planes(LaunchCtx& ctx, const float* qkv, void* hi, void* 
   B200M_LAUNCH_CHECK(ctx, "qkv_to_f16_planes");
 }
 
+// fp32 columns [0, cols) of a row-major matrix -> fp16 operand planes hi = fp16(v), lo = fp16((v - hi) * 2048): the
+// A-operand format tc_gemm.cu consumes without its in-kernel split (the D != 128 GNN layers, api.cu sg_gnn)
+__global__ void split_planes_kernel(const float* __restrict__ in, int ld_in, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, int ld_out, size_t rows, int cols8) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (size_t)cols8) return;
+  const size_t r = i / cols8;
+  const int c = (int)(i - r * cols8) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+  const float4 b = *reinterpret_cast<const float4*>(in + r * ld_in + c + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __align__(16) __half h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h[j] = __float2half_rn(v[j]);
+    l[j] = __float2half_rn((v[j] - __half2float(h[j])) * 2048.f);
+  }
+  *reinterpret_cast<uint4*>(hi + r * ld_out + c) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo + r * ld_out + c) = *reinterpret_cast<const uint4*>(l);
+}
+
+void launch_split_planes(LaunchCtx& ctx, const float* in, int ld_in, void* hi, void* lo, int ld_out, size_t rows,
+                         int cols) {
+  ProfScope prof__(ctx, "split_planes");
+  const size_t n = rows * (size_t)(cols / 8);
+  if (n == 0) return;
+  launch_pdl(ctx, kPdlGemm, split_planes_kernel, dim3((unsigned)cdivz(n, 256)), dim3(256), 0, in, ld_in,
+             reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ld_out, rows, cols / 8);
+  B200M_LAUNCH_CHECK(ctx, "split_planes");
+}
+
 // normalize_keypoints (:63-70) fused with the cat([kpts^T, scores]) of KeypointEncoder.forward (:80-82):
 // rows of (x_norm, y_norm, score, 0) -- K padded 3 -> 4 so the first layer is a float4 GEMM.
 __global__ void kenc_input_kernel(const float* __restrict__ kpts, const float* __restrict__ scores, int N, int Np,

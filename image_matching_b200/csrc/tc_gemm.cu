@@ -48,8 +48,8 @@ __device__ long long* g_gemm_trace = nullptr;
 #define GMT(slot) do { } while (0)
 #endif
 __global__ void __launch_bounds__(320, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w_hi,
-               const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmBarOff);
@@ -81,7 +81,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&split[i], 4); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
-    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -89,6 +89,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();         // operands are read, and anything written, only from here on
+  const bool a_planes = p.A_hi_p != nullptr;   // A arrives as operand planes: no split (warps 2..5 idle)
 
   if (warp == 0 && lane == 0) {
     int s = 0, ph = 0;
@@ -100,8 +101,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], 2 * kGemmATile + 2 * kGemmBTile);
         uint8_t* st = smem + s * kGemmStage;
-        tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, ra);
-        tma_load_2d(st + kGemmATile, &tm_a, &full[s], kb * kGemmKB + 32, ra);
+        if (a_planes) {               // 64 fp16 columns of each plane = the tile image the splitter would have written
+          tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, ra);
+          tma_load_2d(st + kGemmATile, &tm_a_lo, &full[s], kb * kGemmKB, ra);
+        } else {
+          tma_load_2d(st, &tm_a, &full[s], kb * kGemmKB, ra);
+          tma_load_2d(st + kGemmATile, &tm_a, &full[s], kb * kGemmKB + 32, ra);
+        }
         tma_load_2d(st + 2 * kGemmATile, &tm_w_hi, &full[s], kb * kGemmKB, rb);
         tma_load_2d(st + 2 * kGemmATile + kGemmBTile, &tm_w_lo, &full[s], kb * kGemmKB, rb);
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
@@ -126,7 +132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t d = tmem_base + buf * (2 * kGemmNT);   // main accumulator; cross terms at d + NT
       for (int kb = 0; kb < nkb; ++kb) {
         GMT(2 + 2 * kb);
-        mbar_wait(&split[s], ph);
+        mbar_wait(a_planes ? &full[s] : &split[s], ph);
         GMT(3 + 2 * kb);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * kGemmStage), a_lo = a_hi + kGemmATile;
@@ -154,7 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ------------------------------------------------------------------ splitter: raw fp32 A -> fp16 hi / lo planes
     const int t = threadIdx.x - 64;    // 0..127
     int s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total && !a_planes; tile += gridDim.x) {
       GMT_ARM();
       for (int kb = 0; kb < nkb; ++kb) {
         if (warp == 2) GMT(32 + 2 * kb);
@@ -268,6 +274,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               v[8 * g2 + 4] += b.x; v[8 * g2 + 5] += b.y; v[8 * g2 + 6] += b.z; v[8 * g2 + 7] += b.w;
             }
           }
+          if (p.P_hi && rok && c0 + 32 <= p.N) {
+            // the same values once more as operand planes (hi, lo * 2048) for the next GEMM: 64 contiguous bytes per plane
+            uint4* ph4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.P_hi) + (size_t)r * p.ldp + c0);
+            uint4* pl4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.P_lo) + (size_t)r * p.ldp + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 h4, l4;
+              split8_f16(v + 8 * q, 2048.f, h4, l4);
+              ph4[q] = h4;
+              pl4[q] = l4;
+            }
+          }
 #pragma unroll
           for (int g2 = 0; g2 < 4; ++g2) {
             const float4 a0 = make_float4(v[8 * g2], v[8 * g2 + 1], v[8 * g2 + 2], v[8 * g2 + 3]);
@@ -379,14 +397,28 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   if (p.batch > 1 && (p.out_f16 || p.accumulate || p.strideC % 4)) return false;
   if (p.out_f16 && p.accumulate) return false;       // the plane epilogue has no residual read
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(w_hi)) & 15) return false;
+  const bool a_planes = p.A_hi_p != nullptr;
+  if (a_planes && (!p.A_lo_p || p.batch != 1 || p.lda_p % 8 || p.K % 64 ||
+                   ((reinterpret_cast<uintptr_t>(p.A_hi_p) | reinterpret_cast<uintptr_t>(p.A_lo_p)) & 15)))
+    return false;
+  if (p.P_hi && (!p.P_lo || p.out_f16 || p.batch != 1 || p.N % 32 || p.ldp % 8 ||
+                 ((reinterpret_cast<uintptr_t>(p.P_hi) | reinterpret_cast<uintptr_t>(p.P_lo)) & 15)))
+    return false;
   ProfScope prof__(ctx, "tc_gemm");
-  CUtensorMap ma, mh, ml;
+  CUtensorMap ma, ma_lo, mh, ml;
   // batched: the maps span all stacked problems (rows beyond a problem's own M / N are computed but never stored)
   const size_t a_rows = p.batch > 1 ? (size_t)(p.batch - 1) * p.batch_rows_a + p.M : (size_t)p.M;
   const size_t w_rows = p.batch > 1 ? (size_t)(p.batch - 1) * p.batch_rows_b + p.N : (size_t)p.N;
   const int ldw = p.batch > 1 ? p.ldb : p.K;
-  if (!make_sw128_map2(&ma, p.A, a_rows, p.K, p.lda, 128) ||
-      !make_sw128_map_f16(&mh, w_hi, w_rows, p.K, ldw, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, w_rows, p.K, ldw, kGemmNT))
+  if (a_planes) {
+    if (!make_sw128_map_f16(&ma, p.A_hi_p, a_rows, p.K, p.lda_p, 128) ||
+        !make_sw128_map_f16(&ma_lo, p.A_lo_p, a_rows, p.K, p.lda_p, 128))
+      return false;
+  } else {
+    if (!make_sw128_map2(&ma, p.A, a_rows, p.K, p.lda, 128)) return false;
+    ma_lo = ma;
+  }
+  if (!make_sw128_map_f16(&mh, w_hi, w_rows, p.K, ldw, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, w_rows, p.K, ldw, kGemmNT))
     return false;
   static SmemOptIn opt;
   if (!opt.ensure(tc_gemm_kernel, (int)kGemmSmem)) return false;
@@ -404,7 +436,7 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   cudaMemcpyToSymbolAsync(g_gemm_trace, &arg, sizeof(arg), 0, cudaMemcpyHostToDevice, ctx.stream);
   if (want) cudaMemsetAsync(tbuf, 0, 128 * 8, ctx.stream);
 #endif
-  launch_pdl(ctx, kPdlGemm, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, mh, ml, p);
+  launch_pdl(ctx, kPdlGemm, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, ma_lo, mh, ml, p);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
 #ifdef B200M_GEMM_TRACE
   if (want) {
