@@ -176,6 +176,22 @@ __device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, un
   return d;
 }
 
+// ---------------------------------------------------------------- 32-byte global stores / loads (sm_100: STG / LDG .256)
+// A thread that owns a row writes 32 contiguous bytes = one full sector per instruction instead of two half sectors in
+// two instructions; the LSU's cost is per (instruction, cache line), so the row-per-thread epilogues halve theirs.
+// The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- fp16 hi / lo operand split
 // {upper half = fp16(b), lower half = fp16(a)}: element a sits in the low 16 bits (the even element of a pair)
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {

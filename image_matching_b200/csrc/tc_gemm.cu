@@ -195,6 +195,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ------------------------------------------------------------------ epilogue (thread = output row)
     const int w4 = warp & 3;
     const int mrow = w4 * 32 + lane;
+    // every row segment this epilogue touches starts on a 32-byte boundary: 32-byte stores / loads (st_global_256)
+    const int esz = p.out_f16 ? 2 : 4;
+    const bool wide32 = p.batch == 1 && (((size_t)p.ldc * esz) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0 &&
+                        (!p.out_f16 || (reinterpret_cast<uintptr_t>(p.C_lo) & 31) == 0) &&
+                        (!p.P_hi || ((((size_t)p.ldp * 2) & 31) == 0 && ((reinterpret_cast<uintptr_t>(p.P_hi) |
+                                                                         reinterpret_cast<uintptr_t>(p.P_lo)) & 31) == 0));
     int lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int bt = tile / per_batch, tt = tile - bt * per_batch;
@@ -239,6 +245,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           v[j] = t;
         }
         if (warp == 6) GMT(72 + 4 * ch);
+        if (!p.out_f16 && wide32 && c0 + 32 <= p.N) {
+          // fp32 output, 32-byte aligned rows: four 32-byte stores per thread and chunk (full sectors without the lane
+          // swap below), the residual read the same way, all loads issued before the first store
+          if (rok) {
+            if (p.accumulate) {
+              uint32_t old[4][8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ld_global_256(crow + c0 + 8 * q, old[q]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 * q + j] += __uint_as_float(old[q][j]);
+            }
+            if (p.P_hi) {
+              uint8_t* ph = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(p.P_hi) + (size_t)r * p.ldp + c0);
+              uint8_t* pl = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(p.P_lo) + (size_t)r * p.ldp + c0);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint4 h0, l0, h1, l1;
+                split8_f16(v + 16 * q, 2048.f, h0, l0);
+                split8_f16(v + 16 * q + 8, 2048.f, h1, l1);
+                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                st_global_256(ph + 32 * q, hw);
+                st_global_256(pl + 32 * q, lw);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w8[j] = __float_as_uint(v[8 * q + j]);
+              st_global_256(crow + c0 + 8 * q, w8);
+            }
+          }
+          continue;
+        }
         if (!p.out_f16) {
           // fp32 output (and the residual read).  A thread owns a row, so a plain 16-byte store per thread touches 32
           // different rows per warp instruction and HALF of each 32-byte sector; the LSU's cost is per sector (clock64
@@ -340,12 +383,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
           }
           if (wide_planes && !v_only) {
-            uint4* ch = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c0);
-            uint4* cl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c0);
+            __half* chh = reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c0;
+            __half* clh = reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c0;
+            if (wide32) {            // 64 bytes per plane = two 32-byte stores (full sectors)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              ch[q] = *reinterpret_cast<const uint4*>(&hrow[4 * q]);
-              cl[q] = *reinterpret_cast<const uint4*>(&lrow[4 * q]);
+              for (int q = 0; q < 2; ++q) {
+                st_global_256(chh + 16 * q, reinterpret_cast<const uint32_t*>(&hrow[8 * q]));
+                st_global_256(clh + 16 * q, reinterpret_cast<const uint32_t*>(&lrow[8 * q]));
+              }
+            } else {
+              uint4* ch = reinterpret_cast<uint4*>(chh);
+              uint4* cl = reinterpret_cast<uint4*>(clh);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                ch[q] = *reinterpret_cast<const uint4*>(&hrow[4 * q]);
+                cl[q] = *reinterpret_cast<const uint4*>(&lrow[4 * q]);
+              }
             }
           }
         }
