@@ -568,22 +568,31 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
       const float inv = l > 0.f ? 1.f / l : 0.f;
       const size_t off = ((size_t)(side * p.B + b) * p.Np + row) * p.D + head * HD;
       if (p.msg_hi) {
-        uint4* dh = reinterpret_cast<uint4*>(p.msg_hi + off);
-        uint4* dl = reinterpret_cast<uint4*>(p.msg_lo + off);
+        // a thread owns a row: 32-byte stores (one full sector per instruction; the LSU's cost is per instruction and line)
+        __half* dh = p.msg_hi + off;
+        __half* dl = p.msg_lo + off;
+        const bool wide32 = ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dl)) & 31) == 0;
 #pragma unroll
-        for (int g = 0; g < HD / 8; ++g) {
-          uint32_t h4[4], l4[4];
+        for (int g = 0; g < HD / 16; ++g) {
+          uint32_t h8[8], l8[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float a = (o[8 * g + 2 * t] * ca + xch[2 + 8 * g + 2 * t] * cb) * inv;
-            const float bb = (o[8 * g + 2 * t + 1] * ca + xch[2 + 8 * g + 2 * t + 1] * cb) * inv;
-            h4[t] = pack_f16x2(a, bb);
+          for (int t = 0; t < 8; ++t) {
+            const float a = (o[16 * g + 2 * t] * ca + xch[2 + 16 * g + 2 * t] * cb) * inv;
+            const float bb = (o[16 * g + 2 * t + 1] * ca + xch[2 + 16 * g + 2 * t + 1] * cb) * inv;
+            h8[t] = pack_f16x2(a, bb);
             float ra, rb;
-            residual_f16x2(h4[t], a, bb, ra, rb);
-            l4[t] = pack_f16x2(ra * 2048.f, rb * 2048.f);
+            residual_f16x2(h8[t], a, bb, ra, rb);
+            l8[t] = pack_f16x2(ra * 2048.f, rb * 2048.f);
           }
-          dh[g] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-          dl[g] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+          if (wide32) {
+            st_global_256(dh + 16 * g, h8);
+            st_global_256(dl + 16 * g, l8);
+          } else {
+            reinterpret_cast<uint4*>(dh + 16 * g)[0] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            reinterpret_cast<uint4*>(dh + 16 * g)[1] = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+            reinterpret_cast<uint4*>(dl + 16 * g)[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+            reinterpret_cast<uint4*>(dl + 16 * g)[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+          }
         }
       } else {
         float4* dst = reinterpret_cast<float4*>(p.msg + off);

@@ -77,9 +77,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int total = per_batch * p.batch;
   const int nkb = cdiv(p.K, kGemmKB);
 
+  // A as operand planes: no split -- warps 2..5 become a SECOND epilogue team (column chunks 2, 3 of every tile; the
+  // epilogue, not the MMA stream, paces this kernel: clock64 trace)
+  const bool a_planes = p.A_hi_p != nullptr;
+  const int n_teams = a_planes ? 2 : 1;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&split[i], 4); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * n_teams); }
     fence_barrier_init();
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
   }
@@ -89,7 +93,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();         // operands are read, and anything written, only from here on
-  const bool a_planes = p.A_hi_p != nullptr;   // A arrives as operand planes: no split (warps 2..5 idle)
 
   if (warp == 0 && lane == 0) {
     int s = 0, ph = 0;
@@ -156,11 +159,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp >= 2 && warp < 6 && !a_planes) {
     // ------------------------------------------------------------------ splitter: raw fp32 A -> fp16 hi / lo planes
     const int t = threadIdx.x - 64;    // 0..127
     int s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < total && !a_planes; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       GMT_ARM();
       for (int kb = 0; kb < nkb; ++kb) {
         if (warp == 2) GMT(32 + 2 * kb);
@@ -191,8 +194,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (++s == kGemmStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue (thread = output row)
+    // team 0 = warps 6..9; with plane-format A also team 1 = warps 2..5 (TMEM lane quadrant = warp & 3 either way)
+    const int team = warp >= 6 ? 0 : 1;
+    const int ch_per_team = (kGemmNT / 32) / n_teams;
     const int w4 = warp & 3;
     const int mrow = w4 * 32 + lane;
     // every row segment this epilogue touches starts on a 32-byte boundary: 32-byte stores / loads (st_global_256)
@@ -216,7 +222,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       float* crow = p.C + (size_t)bt * p.strideC + (size_t)r * p.ldc;
       const int blk = p.VT ? r / p.vt_np : 0, rr = p.VT ? r - blk * p.vt_np : 0;
 #pragma unroll 1
-      for (int ch = 0; ch < kGemmNT / 32; ++ch) {
+      for (int ch = team * ch_per_team; ch < (team + 1) * ch_per_team; ++ch) {
         float v[32], vc[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(w4 * 32) << 16) + buf * (2 * kGemmNT) + ch * 32;
         if (warp == 6) GMT(70 + 4 * ch);
