@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace b200m {
 
@@ -519,19 +520,44 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
                                                           const float* __restrict__ sumsq, int ncb) {
   pdl_trigger();   // PDL (common.cuh): the next kernel may be scheduled; nothing is read or written before the wait
   pdl_wait();
+  // channel-major output (B, D, cap): a warp owns ONE keypoint, so writing it directly puts 4 bytes into each of D
+  // different sectors.  With cap % 8 == 0 the block's 8 keypoints are transposed through shared memory instead and every
+  // channel row leaves as one 32-byte store (a full sector): the kernel ran at 28 % of the HBM rate because of the
+  // partial-sector writes.
+  __shared__ __align__(16) float s_t[8][256];           // [keypoint of this block][channel], D <= 256
+  const bool staged = out_dcn != nullptr && (cap & 7) == 0 && D <= 256 &&
+                      (reinterpret_cast<uintptr_t>(out_dcn) & 31) == 0;      // uniform per launch
   const int n = blockIdx.y;
-  const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int wk = threadIdx.x >> 5;
+  const int k = blockIdx.x * (blockDim.x / 32) + wk;
   const int lane = threadIdx.x & 31;
-  if (k >= cap) return;
-  const int cnt = counts ? counts[n] : cap;
   const int G = D / 4;
+  auto flush = [&]() {                                   // all 256 threads
+    __syncthreads();
+    const int k0 = blockIdx.x * 8;
+    if ((int)threadIdx.x < D && k0 < cap) {
+      uint32_t r[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[q] = __float_as_uint(s_t[q][threadIdx.x]);
+      tc::st_global_256(out_dcn + ((size_t)n * D + threadIdx.x) * cap + k0, r);
+    }
+  };
+  if (k >= cap) {
+    if (staged) flush();
+    return;
+  }
+  const int cnt = counts ? counts[n] : cap;
   if (k >= cnt) {   // zero the padding entries so stacked tensors are deterministic
     for (int g = lane; g < G; g += 32) {
-      if (out_dcn)
+      if (staged) {
+        *reinterpret_cast<float4*>(&s_t[wk][g * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (out_dcn) {
         for (int j = 0; j < 4; ++j) out_dcn[((size_t)n * D + g * 4 + j) * cap + k] = 0.f;
+      }
       if (out_tok)
         reinterpret_cast<float4*>(out_tok + n * tok_img_stride + (size_t)k * tok_ld)[g] = make_float4(0, 0, 0, 0);
     }
+    if (staged) flush();
     return;
   }
   const float s = 8.f;
@@ -598,13 +624,16 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const float4* __restri
     int g = lane + 32 * t;
     if (g < G) {
       float4 o = make_float4(acc[t].x / nrm, acc[t].y / nrm, acc[t].z / nrm, acc[t].w / nrm);
-      if (out_dcn) {
+      if (staged) {
+        *reinterpret_cast<float4*>(&s_t[wk][g * 4]) = o;
+      } else if (out_dcn) {
         float* d = out_dcn + ((size_t)n * D + g * 4) * cap + k;
         d[0] = o.x; d[(size_t)cap] = o.y; d[(size_t)2 * cap] = o.z; d[(size_t)3 * cap] = o.w;
       }
       if (out_tok) reinterpret_cast<float4*>(out_tok + n * tok_img_stride + (size_t)k * tok_ld)[g] = o;
     }
   }
+  if (staged) flush();
 }
 
 void launch_sample_descriptors(LaunchCtx& ctx, const float* desc_c4, int c4_total, int D, int n, int hc, int wc,
