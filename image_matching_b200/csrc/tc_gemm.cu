@@ -203,7 +203,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int mrow = w4 * 32 + lane;
     // every row segment this epilogue touches starts on a 32-byte boundary: 32-byte stores / loads (st_global_256)
     const int esz = p.out_f16 ? 2 : 4;
-    const bool wide32 = p.batch == 1 && (((size_t)p.ldc * esz) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0 &&
+    const bool wide32 = (p.batch == 1 || (((size_t)p.strideC * esz) & 31) == 0) && (((size_t)p.ldc * esz) & 31) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.C) & 31) == 0 &&
                         (!p.out_f16 || (reinterpret_cast<uintptr_t>(p.C_lo) & 31) == 0) &&
                         (!p.P_hi || ((((size_t)p.ldp * 2) & 31) == 0 && ((reinterpret_cast<uintptr_t>(p.P_hi) |
                                                                          reinterpret_cast<uintptr_t>(p.P_lo)) & 31) == 0));
