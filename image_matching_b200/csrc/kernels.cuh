@@ -141,6 +141,7 @@ struct GemmParams {
   const void* A_hi_p = nullptr; const void* A_lo_p = nullptr; int lda_p = 0;
   // fp32 epilogue: ALSO write the result as fp16 hi / lo*2048 planes P_hi / P_lo [M][ldp] (halves) -- the next GEMM's A
   void* P_hi = nullptr; void* P_lo = nullptr; int ldp = 0;
+  int stage_planes = 0;        // set by launch_tc_gemm: plane outputs leave through shared-memory staging + TMA tensor stores
 };
 void launch_gemm(LaunchCtx& ctx, const GemmParams& p);
 // tcgen05 fp16x3 version for weight GEMMs (w_hi / w_lo: [N][K] fp16 planes, lo scaled by 2048); false if declined

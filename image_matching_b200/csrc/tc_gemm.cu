@@ -36,7 +36,13 @@ constexpr int kGemmATile = 128 * 128;        // bytes: 128 rows x 128 B (32 fp32
 constexpr int kGemmBTile = kGemmNT * 128;    // NT rows x 64 fp16
 constexpr int kGemmStage = 2 * kGemmATile + 2 * kGemmBTile;   // A box0 -> hi, A box1 -> lo, W hi, W lo
 constexpr int kGemmBarOff = kGemmStages * kGemmStage;
-constexpr size_t kGemmSmem = 1024 + kGemmBarOff + (3 * kGemmStages + 4) * 8 + 16;
+// plane-output staging: per epilogue team one 32-column chunk of both planes (128 rows x 64 B each, SWIZZLE_64B box layout)
+constexpr int kGemmStgOff = kGemmBarOff + 1024;          // barriers + TMEM slot live in the 1 KB in front of it
+constexpr int kGemmStgPlane = 128 * 64;
+constexpr int kGemmStgTeam = 2 * kGemmStgPlane;
+constexpr size_t kGemmSmem = 1024 + kGemmStgOff + 2 * kGemmStgTeam;
+static_assert((3 * kGemmStages + 4) * 8 + 16 <= 1024, "barrier block");
+static_assert(kGemmSmem <= 232448, "shared memory budget");
 
 // Developer aid (make EXTRA=-DB200M_GEMM_TRACE, run with B200M_GEMM_TRACE=1 B200M_GRAPHS=0): clock64 stamps of one CTA's
 // fourth tile for the MMA warp, the first splitter warp and the first epilogue warp (per 32-column chunk), printed for a
@@ -49,7 +55,8 @@ __device__ long long* g_gemm_trace = nullptr;
 #endif
 __global__ void __launch_bounds__(320, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+               const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmBarOff);
@@ -86,6 +93,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * n_teams); }
     fence_barrier_init();
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+    if (p.stage_planes) { tma_prefetch_desc(&tm_c_hi); tma_prefetch_desc(&tm_c_lo); }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -201,6 +209,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int ch_per_team = (kGemmNT / 32) / n_teams;
     const int w4 = warp & 3;
     const int mrow = w4 * 32 + lane;
+    // Plane outputs through shared memory + TMA tensor stores (p.stage_planes): a thread owns a row, so direct stores cost
+    // the LSU one (instruction, line) visit per 32 bytes -- the kernel's bottleneck at D = 256.  Each team
+    // stages one 32-column chunk of both planes in the SWIZZLE_64B box layout (16-byte unit q of row r sits at
+    // q ^ ((r >> 1) & 3): conflict-free row-per-thread writes) and its first thread issues two tensor stores.
+    uint8_t* stg = smem + kGemmStgOff + team * kGemmStgTeam;
+    const bool storer = lane == 0 && (warp == 6 || warp == 2);
+    auto team_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + team) : "memory"); };
     // every row segment this epilogue touches starts on a 32-byte boundary: 32-byte stores / loads (st_global_256)
     const int esz = p.out_f16 ? 2 : 4;
     const bool wide32 = (p.batch == 1 || (((size_t)p.strideC * esz) & 31) == 0) && (((size_t)p.ldc * esz) & 31) == 0 &&
@@ -349,14 +364,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
           continue;
         }
+        // the V third of a q|k|v projection is consumed only through V^T: its plane copy is not written
+        const bool v_only = p.out_f16 && p.VT && c0 >= p.vt_col0;
+        const bool wide_planes = p.out_f16 && c0 + 32 <= p.N;
+        const bool stage_this = p.stage_planes && wide_planes && !v_only;      // uniform per team
+        if (stage_this) {                  // the previous chunk's tensor stores must have read the staging buffer
+          if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          team_sync();
+        }
         if (rok) {
           // fp16 planes: a thread's 32 columns are 64 contiguous bytes per plane -> four 16-byte stores instead of sixteen
           // 4-byte ones (the q|k|v projections were bound by the store instructions, not by HBM: 0.87 -> 0.65 ms per step,
           // C3's per-GEMM GNN 8.1 -> 6.2 ms; also transposing the V^T stores inside lane quads measured neutral)
-          const bool wide_planes = p.out_f16 && c0 + 32 <= p.N;
           __half2 hrow[16], lrow[16];
-          // the V third of a q|k|v projection is consumed only through V^T: its plane copy is not written
-          const bool v_only = p.out_f16 && p.VT && c0 >= p.vt_col0;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int c = c0 + 4 * g;
@@ -389,7 +409,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               }
             }
           }
-          if (wide_planes && !v_only) {
+          if (stage_this) {
+            const int sw = (mrow >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *reinterpret_cast<uint4*>(stg + mrow * 64 + ((q ^ sw) << 4)) = *reinterpret_cast<const uint4*>(&hrow[4 * q]);
+              *reinterpret_cast<uint4*>(stg + kGemmStgPlane + mrow * 64 + ((q ^ sw) << 4)) =
+                  *reinterpret_cast<const uint4*>(&lrow[4 * q]);
+            }
+          } else if (wide_planes && !v_only) {
             __half* chh = reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + c0;
             __half* clh = reinterpret_cast<__half*>(p.C_lo) + (size_t)r * p.ldc + c0;
             if (wide32) {            // 64 bytes per plane = two 32-byte stores (full sectors)
@@ -409,12 +437,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
           }
         }
+        if (stage_this) {                  // rows >= M of the last row tile hold garbage: the tensor store clips them
+          fence_proxy_async();
+          team_sync();
+          if (storer) {
+            tma_store_2d(&tm_c_hi, stg, c0, m0);
+            tma_store_2d(&tm_c_lo, stg + kGemmStgPlane, c0, m0);
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (warp == 6) GMT(66);
     }
+    if (storer && p.stage_planes) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores done
   }
   tc_fence_before();
   __syncthreads();
@@ -433,6 +471,20 @@ static bool make_sw128_map_f16(CUtensorMap* m, const void* base, size_t rows, in
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// fp16 [rows][ld] output plane, 32-column x 128-row store boxes in the SWIZZLE_64B layout the epilogue stages
+static bool make_sw64_store_map_f16(CUtensorMap* m, const void* base, size_t rows, int cols, int ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -480,6 +532,15 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   }
   if (!make_sw128_map_f16(&mh, w_hi, w_rows, p.K, ldw, kGemmNT) || !make_sw128_map_f16(&ml, w_lo, w_rows, p.K, ldw, kGemmNT))
     return false;
+  // plane outputs: staged in shared memory and written by TMA tensor stores (B200M_GEMM_STAGED=0: direct 32-byte stores)
+  static const bool staged_on = [] { const char* e = getenv("B200M_GEMM_STAGED"); return !(e && e[0] == '0'); }();
+  GemmParams q = p;
+  CUtensorMap mc_hi = mh, mc_lo = ml;
+  if (staged_on && p.out_f16 && p.batch == 1 && p.N >= 32 && p.ldc % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.C_lo)) & 15) == 0 &&
+      make_sw64_store_map_f16(&mc_hi, p.C, (size_t)p.M, p.N, p.ldc) &&
+      make_sw64_store_map_f16(&mc_lo, p.C_lo, (size_t)p.M, p.N, p.ldc))
+    q.stage_planes = 1;
   static SmemOptIn opt;
   if (!opt.ensure(tc_gemm_kernel, (int)kGemmSmem)) return false;
   const int total = cdiv(p.M, 128) * cdiv(p.N, kGemmNT) * p.batch;
@@ -496,7 +557,7 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
   cudaMemcpyToSymbolAsync(g_gemm_trace, &arg, sizeof(arg), 0, cudaMemcpyHostToDevice, ctx.stream);
   if (want) cudaMemsetAsync(tbuf, 0, 128 * 8, ctx.stream);
 #endif
-  launch_pdl(ctx, kPdlGemm, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, ma_lo, mh, ml, p);
+  launch_pdl(ctx, kPdlGemm, tc_gemm_kernel, dim3(grid), dim3(320), kGemmSmem, ma, ma_lo, mh, ml, mc_hi, mc_lo, q);
   B200M_LAUNCH_CHECK(ctx, "tc_gemm");
 #ifdef B200M_GEMM_TRACE
   if (want) {
