@@ -270,6 +270,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (!p.out_f16 && wide32 && c0 + 32 <= p.N) {
           // fp32 output, 32-byte aligned rows: four 32-byte stores per thread and chunk (full sectors without the lane
           // swap below), the residual read the same way, all loads issued before the first store
+          const bool stage_p = p.stage_planes && p.P_hi != nullptr;      // uniform per launch
+          if (stage_p) {                   // the previous chunk's tensor stores must have read the staging buffer
+            if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            team_sync();
+          }
           if (rok) {
             if (p.accumulate) {
               uint32_t old[4][8];
@@ -280,7 +285,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[8 * q + j] += __uint_as_float(old[q][j]);
             }
-            if (p.P_hi) {
+            if (stage_p) {
+              const int sw = (mrow >> 1) & 3;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 h4, l4;
+                split8_f16(v + 8 * q, 2048.f, h4, l4);
+                *reinterpret_cast<uint4*>(stg + mrow * 64 + ((q ^ sw) << 4)) = h4;
+                *reinterpret_cast<uint4*>(stg + kGemmStgPlane + mrow * 64 + ((q ^ sw) << 4)) = l4;
+              }
+            } else if (p.P_hi) {
               uint8_t* ph = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(p.P_hi) + (size_t)r * p.ldp + c0);
               uint8_t* pl = reinterpret_cast<uint8_t*>(reinterpret_cast<__half*>(p.P_lo) + (size_t)r * p.ldp + c0);
 #pragma unroll
@@ -300,6 +314,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 8; ++j) w8[j] = __float_as_uint(v[8 * q + j]);
               st_global_256(crow + c0 + 8 * q, w8);
+            }
+          }
+          if (stage_p) {
+            fence_proxy_async();
+            team_sync();
+            if (storer) {
+              tma_store_2d(&tm_c_hi, stg, c0, m0);
+              tma_store_2d(&tm_c_lo, stg + kGemmStgPlane, c0, m0);
+              tma_store_commit();
             }
           }
           continue;
@@ -540,6 +563,12 @@ bool launch_tc_gemm(LaunchCtx& ctx, const GemmParams& p, const float* w_hi, cons
       ((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.C_lo)) & 15) == 0 &&
       make_sw64_store_map_f16(&mc_hi, p.C, (size_t)p.M, p.N, p.ldc) &&
       make_sw64_store_map_f16(&mc_lo, p.C_lo, (size_t)p.M, p.N, p.ldc))
+    q.stage_planes = 1;
+  // ... and the plane copy of an fp32 result (MLP2 at D != 128: residual + planes of the new x)
+  if (staged_on && !p.out_f16 && p.P_hi && p.batch == 1 && p.N >= 32 && p.ldp % 8 == 0 && p.ldc % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.C) & 31) == 0 &&      // (the kernel's 32-byte fp32 path is the one that stages)
+      make_sw64_store_map_f16(&mc_hi, p.P_hi, (size_t)p.M, p.N, p.ldp) &&
+      make_sw64_store_map_f16(&mc_lo, p.P_lo, (size_t)p.M, p.N, p.ldp))
     q.stage_planes = 1;
   static SmemOptIn opt;
   if (!opt.ensure(tc_gemm_kernel, (int)kGemmSmem)) return false;
