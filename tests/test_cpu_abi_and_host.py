@@ -170,3 +170,23 @@ def test_reference_script_resolves_to_the_shim(tmp_path):
     assert "Loaded SuperPoint model" in out and "Loaded SuperGlue model weights" in out, out[-2000:]
     if not torch.cuda.is_available():
         assert "no CPU fallback" in out, out[-2000:]
+
+
+def test_bench_work_model_accounts_every_gnn_flop_once():
+    """bench.py's roofline numerators: at D = 128 the layer GEMMs belong to the fused layer kernel, at any
+    other width they run as tc_gemm launches -- either way the sum over the SuperGlue kernels is the same formula, and
+    the whole-path total stays within a few percent of the per-pair GFLOP figure the configuration quotes."""
+    import bench
+    for name in ("C2", "C3"):
+        c = bench.CONFIGS[name]
+        w = bench.kernel_work(c, 1)
+        D, N = c["D"], c["K"]
+        tok = 2 * N
+        gnn = tok * 2.0 * D * D * (7 * 18 + 3 * 17)
+        got = w["tc_gemm"][1] + (w["tc_gnn_layer"][1] if "tc_gnn_layer" in w else 0.0)
+        kch = [3] + list(c["kenc"]) + [D]
+        lin = tok * 2.0 * (sum(a * b for a, b in zip(kch[:-1], kch[1:])) + 5 * D * D) + 2.0 * N * N * D
+        assert abs(got - (gnn + lin)) < 1e-6 * got
+        assert ("tc_gnn_layer" in w) == (D == 128)
+        total = sum(v for kind, v in w.values() if kind == "tensor")
+        assert abs(total / 1e9 - c["gf_pair"]) < 0.03 * c["gf_pair"], (name, total / 1e9, c["gf_pair"])
